@@ -1,0 +1,357 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- never linked into, loaded by or called from the product path.
+ *
+ * Scalar C restatement of the waterfall hot path as specified in DESIGN.md section 4:
+ *
+ *   IQ frame -> Hann window -> mixed-radix DIF FFT (float32, fixed operation order)
+ *            -> |X|^2 -> Kiwi byte (dBm + 255, utils_supersdr.py:789) by threshold counting
+ *            -> time-binning mean of n byte lines (utils_supersdr.py:881-886)
+ *            -> dB cal + percentile auto-scale + colour row (utils_supersdr.py:787-813)
+ *            -> uint8 pixel row.
+ *
+ * The FFT / log-magnitude stage is ABSENT from the reference (it runs on the KiwiSDR server):
+ * PARITY UNPINNED for that stage; this file is the builder-defined, bit-exact statement of it.
+ * The stages after the byte line restate reference arithmetic and are pinned through
+ * oracle/tier_p.py (same results, checked in tests/test_oracle_*.py).
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: no implicit FMA contraction; every fused
+ * multiply-add in the spec is an explicit fmaf()).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SO_FS 32768.0
+#define SO_PI 3.14159265358979323846
+#define SO_MAX_PASSES 8
+
+typedef struct { float re, im; } cpx;
+
+/* ---- spec constants ----------------------------------------------------- */
+static const float K_A = 0.92387953251128674f;   /* cos(pi/8)  */
+static const float K_B = 0.70710678118654752f;   /* sqrt(1/2)  */
+static const float K_C = 0.38268343236508977f;   /* sin(pi/8)  */
+
+/* cos(2*pi*m/16), sin(2*pi*m/16) built from {1, A, B, C, 0} by symmetry (exact negations) */
+static void unit16(int m, float* c, float* s) {
+    static const float q[5] = {1.0f, 0.92387953251128674f, 0.70710678118654752f,
+                               0.38268343236508977f, 0.0f};
+    int mm = m & 15, quad = mm >> 2, r = mm & 3;
+    float cr = q[r], sr = q[4 - r];
+    switch (quad) {
+    case 0: *c = cr;  *s = sr;  break;
+    case 1: *c = -sr; *s = cr;  break;
+    case 2: *c = -cr; *s = -sr; break;
+    default: *c = sr; *s = -cr; break;
+    }
+}
+
+/* ---- plan: radix list, product == N ---------------------------------------- */
+int so_fft_plan(int N, int* radices) {
+    int lg = 0;
+    while ((1 << lg) < N) lg++;
+    if ((1 << lg) != N || lg < 4 || lg > 16) return -1;
+    int np = 0, rem = lg;
+    while (rem >= 4 + 2 || rem == 4) { radices[np++] = 16; rem -= 4; }   /* leave 2,3,5 -> below */
+    if (rem == 5) { radices[np++] = 8; radices[np++] = 4; }
+    else if (rem == 3) radices[np++] = 8;
+    else if (rem == 2) radices[np++] = 4;
+    else if (rem == 1) return -1;
+    return np;
+}
+
+void so_twiddle_table(int N, float* tab) {
+    for (int k = 0; k < N; ++k) {
+        double a = 2.0 * SO_PI * (double)k / (double)N;
+        tab[2 * k] = (float)cos(a);
+        tab[2 * k + 1] = (float)(-sin(a));
+    }
+}
+
+/* byte >= k  <=>  P >= T[k], k = 1..255;  T[0] = 0 */
+void so_thresholds(int N, double cal_db, float* T) {
+    double ref = ((double)N * SO_FS * 0.5);
+    ref = ref * ref;
+    T[0] = 0.0f;
+    for (int k = 1; k < 256; ++k)
+        T[k] = (float)(ref * pow(10.0, ((double)k - 0.5 - 255.0 - cal_db) / 10.0));
+}
+
+/* ---- arithmetic primitives (each line is one IEEE float32 operation) ----------------------- */
+static inline cpx cadd(cpx a, cpx b) { cpx r = {a.re + b.re, a.im + b.im}; return r; }
+static inline cpx csub(cpx a, cpx b) { cpx r = {a.re - b.re, a.im - b.im}; return r; }
+static inline cpx cmul(cpx u, cpx w) {
+    cpx r;
+    float t0 = u.im * w.im;
+    float t1 = u.im * w.re;
+    r.re = fmaf(u.re, w.re, -t0);
+    r.im = fmaf(u.re, w.im, t1);
+    return r;
+}
+static inline cpx mul_mi(cpx u) { cpx r = {u.im, -u.re}; return r; }                 /* * (-i)      */
+static inline cpx mul_w8(cpx u) { cpx r = {(u.re + u.im) * K_B, (u.im - u.re) * K_B}; return r; }   /* * B(1-i)  */
+static inline cpx mul_w83(cpx u) { cpx r = {(u.im - u.re) * K_B, (u.re + u.im) * (-K_B)}; return r; } /* * -B(1+i) */
+
+static inline void dft2(cpx* x) { cpx a = x[0], b = x[1]; x[0] = cadd(a, b); x[1] = csub(a, b); }
+
+static inline void dft4(cpx* x) {
+    cpx a = cadd(x[0], x[2]), b = csub(x[0], x[2]);
+    cpx c = cadd(x[1], x[3]), d = mul_mi(csub(x[1], x[3]));
+    x[0] = cadd(a, c); x[2] = csub(a, c);
+    x[1] = cadd(b, d); x[3] = csub(b, d);
+}
+
+static void dft8(cpx* x) {
+    cpx u[2][4];
+    for (int m0 = 0; m0 < 4; ++m0) {
+        cpx t[2] = {x[m0], x[m0 + 4]};
+        dft2(t);
+        u[0][m0] = t[0]; u[1][m0] = t[1];
+    }
+    u[1][1] = mul_w8(u[1][1]);
+    u[1][2] = mul_mi(u[1][2]);
+    u[1][3] = mul_w83(u[1][3]);
+    for (int p = 0; p < 2; ++p) {
+        dft4(u[p]);
+        for (int s = 0; s < 4; ++s) x[p + 2 * s] = u[p][s];
+    }
+}
+
+static void dft16(cpx* x) {
+    cpx u[4][4];   /* u[p][m0] */
+    const cpx w1 = {K_A, -K_C}, w3 = {K_C, -K_A}, w9 = {-K_A, K_C};
+    for (int m0 = 0; m0 < 4; ++m0) {
+        cpx t[4] = {x[m0], x[m0 + 4], x[m0 + 8], x[m0 + 12]};
+        dft4(t);
+        for (int p = 0; p < 4; ++p) u[p][m0] = t[p];
+    }
+    /* internal twiddles W16^(m0*p) */
+    u[1][1] = cmul(u[1][1], w1);  u[1][2] = mul_w8(u[1][2]);  u[1][3] = cmul(u[1][3], w3);
+    u[2][1] = mul_w8(u[2][1]);    u[2][2] = mul_mi(u[2][2]);  u[2][3] = mul_w83(u[2][3]);
+    u[3][1] = cmul(u[3][1], w3);  u[3][2] = mul_w83(u[3][2]); u[3][3] = cmul(u[3][3], w9);
+    for (int p = 0; p < 4; ++p) {
+        dft4(u[p]);
+        for (int s = 0; s < 4; ++s) x[p + 4 * s] = u[p][s];
+    }
+}
+
+/* twiddle powers w[1..r-1] from w[1] by the fixed minimum-depth chain */
+static void tw_chain(cpx* w, int r) {
+    w[2] = cmul(w[1], w[1]);
+    w[3] = cmul(w[2], w[1]);
+    if (r <= 4) return;
+    w[4] = cmul(w[2], w[2]);
+    w[5] = cmul(w[4], w[1]);
+    w[6] = cmul(w[3], w[3]);
+    w[7] = cmul(w[4], w[3]);
+    if (r <= 8) return;
+    w[8] = cmul(w[4], w[4]);
+    w[9] = cmul(w[8], w[1]);
+    w[10] = cmul(w[5], w[5]);
+    w[11] = cmul(w[8], w[3]);
+    w[12] = cmul(w[6], w[6]);
+    w[13] = cmul(w[8], w[5]);
+    w[14] = cmul(w[7], w[7]);
+    w[15] = cmul(w[8], w[7]);
+}
+
+#define SO_TABLE_PASS_MAX 1024   /* a pass uses exact table twiddles iff (L/r)*(r-1) <= this */
+
+/* In-place mixed-radix DIF FFT on d[0..N); output in digit-reversed order. */
+static void fft_dif(cpx* d, int N, const int* radices, int np, const float* tab) {
+    int L = N;
+    for (int p = 0; p < np; ++p) {
+        int r = radices[p], M = L / r, step = N / L;
+        int use_table = (M * (r - 1) <= SO_TABLE_PASS_MAX);
+        for (int base = 0; base < N; base += L) {
+            for (int j = 0; j < M; ++j) {
+                cpx x[16], w[16];
+                for (int m = 0; m < r; ++m) x[m] = d[base + j + m * M];
+                if (r == 16) dft16(x); else if (r == 8) dft8(x); else if (r == 4) dft4(x); else dft2(x);
+                if (M > 1) {
+                    if (use_table) {
+                        for (int q = 1; q < r; ++q) {
+                            int k = j * q * step;
+                            w[q].re = tab[2 * k]; w[q].im = tab[2 * k + 1];
+                        }
+                    } else {
+                        int k = j * step;
+                        w[1].re = tab[2 * k]; w[1].im = tab[2 * k + 1];
+                        if (r > 2) tw_chain(w, r);
+                    }
+                    for (int q = 1; q < r; ++q) x[q] = cmul(x[q], w[q]);
+                }
+                for (int q = 0; q < r; ++q) d[base + j + q * M] = x[q];
+            }
+        }
+        L = M;
+    }
+}
+
+/* position -> bin (mixed-radix digit reversal) */
+static int pos_to_bin(int pos, int N, const int* radices, int np) {
+    int M = N, k = 0, mult = 1;
+    for (int p = 0; p < np; ++p) {
+        M /= radices[p];
+        int q = pos / M; pos -= q * M;
+        k += q * mult; mult *= radices[p];
+    }
+    return k;
+}
+
+static inline uint8_t quantise(float P, const float* T) {
+    int lo = 0, hi = 255;            /* largest k with P >= T[k]; T[0] = 0, T increasing */
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (P >= T[mid]) lo = mid; else hi = mid - 1;
+    }
+    return (uint8_t)lo;
+}
+
+/* Window (first-pass form): w[j + m*M0] = 0.5 - 0.5*cos(theta_j + 2*pi*m/r0) evaluated from
+ * Wtab[j] and the unit16 constants, DESIGN.md 4.1. */
+static void apply_window(cpx* d, int N, int r0, const float* tab) {
+    int M0 = N / r0;
+    for (int j = 0; j < M0; ++j) {
+        float c = tab[2 * j], dd = tab[2 * j + 1];       /* cos(theta_j), -sin(theta_j) */
+        for (int m = 0; m < r0; ++m) {
+            float C, S;
+            unit16(m * (16 / r0), &C, &S);
+            float t = dd * S;
+            float cm = fmaf(c, C, t);                    /* cos(theta_j + phi_m) */
+            float w = fmaf(-0.5f, cm, 0.5f);
+            cpx* e = &d[j + m * M0];
+            e->re = e->re * w; e->im = e->im * w;
+        }
+    }
+}
+
+/* One frame: interleaved float32 IQ[N] -> Kiwi bytes[N], fftshifted (bin 0 = lowest frequency).
+ * If spec_out != NULL also returns the raw FFT (natural order) for diagnostics. */
+int so_wf_frame_bytes(const float* iq, int N, int window, double cal_db, uint8_t* bytes, float* spec_out) {
+    int radices[SO_MAX_PASSES];
+    int np = so_fft_plan(N, radices);
+    if (np < 0) return -1;
+    float* tab = (float*)malloc(sizeof(float) * 2 * (size_t)N);
+    cpx* d = (cpx*)malloc(sizeof(cpx) * (size_t)N);
+    float T[256];
+    so_twiddle_table(N, tab);
+    so_thresholds(N, cal_db, T);
+    memcpy(d, iq, sizeof(cpx) * (size_t)N);
+    if (window) apply_window(d, N, radices[0], tab);
+    fft_dif(d, N, radices, np, tab);
+    for (int pos = 0; pos < N; ++pos) {
+        int k = pos_to_bin(pos, N, radices, np);
+        float t = d[pos].im * d[pos].im;
+        float P = fmaf(d[pos].re, d[pos].re, t);
+        bytes[(k + N / 2) & (N - 1)] = quantise(P, T);
+        if (spec_out) { spec_out[2 * k] = d[pos].re; spec_out[2 * k + 1] = d[pos].im; }
+    }
+    free(d); free(tab);
+    return 0;
+}
+
+/* ---- Tier-P tail in strict float32 (restates oracle/tier_p.py; utils_supersdr.py:787-813) --- */
+typedef struct {
+    int zoom, auto_scale, delta_low_db, delta_high_db;
+    int p_lo;            /* percentile lower index and lerp weight, computed by the caller with */
+    float p_gamma;       /* numpy's own float32 expression (tier_p.percentile_virtual_index)     */
+    float low_clip_db, dynamic_range;   /* in: values kept when auto_scale == 0; out: updated  */
+    float high_clip_db, wf_min_db, wf_max_db;
+} so_colour_t;
+
+static int cmp_u16(const void* a, const void* b) {
+    return (int)*(const uint16_t*)a - (int)*(const uint16_t*)b;
+}
+
+/* sums: per-bin integer sum of n byte lines. */
+void so_colour_row(const uint16_t* sums, int W, int n, so_colour_t* st, float* spectrum,
+                   float* colour, uint8_t* pixels) {
+    float fn = (float)n, z3 = (float)(3 * st->zoom);
+    uint16_t* srt = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)W);
+#define WFDB(s) ((((float)(s) / fn - 255.0f) - 13.0f) + z3)
+    for (int i = 0; i < W; ++i) {
+        if (spectrum) spectrum[i] = (float)sums[i] / fn;
+        srt[i] = sums[i ? i : 1];                        /* wf_db[0] = wf_db[1] */
+    }
+    if (st->auto_scale) {
+        qsort(srt, (size_t)W, sizeof(uint16_t), cmp_u16);
+        int lo = st->p_lo, hi = lo + 1 < W ? lo + 1 : W - 1;
+        float a = WFDB(srt[lo]), b = WFDB(srt[hi]), g = st->p_gamma, d = b - a, p;
+        if (g >= 0.5f) { float t = 1.0f - g; t = d * t; p = b - t; }
+        else { float t = d * g; p = a + t; }
+        st->low_clip_db = p;
+        st->high_clip_db = WFDB(srt[W - 1]);
+        float dyn = st->high_clip_db - st->low_clip_db;
+        st->dynamic_range = dyn > 40.0f ? dyn : 40.0f;
+    }
+    float low = st->low_clip_db + (float)st->delta_low_db;
+    float nf = st->dynamic_range + (float)st->delta_high_db;
+    float den = nf - (float)st->delta_low_db;
+    st->wf_min_db = low - z3;
+    st->wf_max_db = (st->low_clip_db + nf) - z3;
+    for (int i = 0; i < W; ++i) {
+        float w = WFDB(sums[i ? i : 1]);
+        float c = (w - low) / den;
+        c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);     /* NaN (den == 0) propagates like np.clip */
+        c = c * 254.0f;
+        c = c < 0.0f ? 0.0f : (c > 255.0f ? 255.0f : c);
+        if (colour) colour[i] = c;
+        if (pixels) pixels[i] = (uint8_t)rintf(c);
+    }
+#undef WFDB
+    free(srt);
+}
+
+/* Full chain for a batch: iq[B][n][N] float32 interleaved -> pixels[B][N] (+ optional outputs).
+ * Channels are independent; callers parallelise by calling this on channel slices from several
+ * threads (ctypes releases the GIL). */
+int so_wf_rows(const float* iq, int B, int n, int N, int window, double cal_db, const so_colour_t* st_in,
+               uint8_t* pixels, float* colour, float* spectrum, uint16_t* sums_out, float* scalars) {
+    int radices[SO_MAX_PASSES];
+    if (so_fft_plan(N, radices) < 0) return -1;
+    int rc = 0;
+    for (int b = 0; b < B; ++b) {
+        uint16_t* sums = (uint16_t*)calloc((size_t)N, sizeof(uint16_t));
+        uint8_t* line = (uint8_t*)malloc((size_t)N);
+        for (int f = 0; f < n; ++f) {
+            if (so_wf_frame_bytes(iq + 2 * ((size_t)b * n + f) * N, N, window, cal_db, line, NULL)) rc = -1;
+            for (int i = 0; i < N; ++i) sums[i] = (uint16_t)(sums[i] + line[i]);
+        }
+        so_colour_t st = *st_in;
+        so_colour_row(sums, N, n, &st, spectrum ? spectrum + (size_t)b * N : NULL,
+                      colour ? colour + (size_t)b * N : NULL, pixels ? pixels + (size_t)b * N : NULL);
+        if (sums_out) memcpy(sums_out + (size_t)b * N, sums, sizeof(uint16_t) * (size_t)N);
+        if (scalars) {
+            float* s = scalars + 5 * (size_t)b;
+            s[0] = st.low_clip_db; s[1] = st.high_clip_db; s[2] = st.dynamic_range;
+            s[3] = st.wf_min_db; s[4] = st.wf_max_db;
+        }
+        free(sums); free(line);
+    }
+    return rc;
+}
+
+/* ---- Tier-P audio interpolator (utils_supersdr.py:1121-1138) in float64 ------------------- */
+/* x: int16[n] at 12 kHz; hist: float64[n_tap-1] (updated); h: float64[n_tap]; out: int16[4n][2] */
+void so_play_buffer(const int16_t* x, int n, double volume, double balance, const double* h,
+                    int n_tap, int ratio, double* hist, int16_t* out, double* mono_out) {
+    int L = ratio * n, H = n_tap - 1;
+    double* z = (double*)calloc((size_t)(H + L), sizeof(double));
+    memcpy(z, hist, sizeof(double) * (size_t)H);
+    for (int k = 0; k < n; ++k) z[H + ratio * k] = (double)x[k] * (volume / 100.0);
+    memcpy(hist, z + L, sizeof(double) * (size_t)H);
+    double lv = 1.0 - balance < 1.0 ? 1.0 - balance : 1.0;
+    double rv = 1.0 + balance < 1.0 ? 1.0 + balance : 1.0;
+    lv *= lv; rv *= rv;
+    for (int j = 0; j < L; ++j) {
+        double acc = 0.0;
+        for (int t = 0; t < n_tap; ++t) acc += h[t] * z[j + H - t];
+        acc *= (double)ratio;
+        if (mono_out) mono_out[j] = acc;
+        out[2 * j] = (int16_t)(int32_t)(acc * lv);
+        out[2 * j + 1] = (int16_t)(int32_t)(acc * rv);
+    }
+    free(z);
+}
