@@ -1,0 +1,133 @@
+"""TEST INFRASTRUCTURE ONLY -- generates the committed fixtures under tests/golden/.
+
+Tier-P fixtures (``tier_p_*.npz``) are OUTPUTS OF THE UNMODIFIED REFERENCE: its functions are imported
+headless from /root/reference (oracle/ref_import.py) and run on seeded inputs; this only works in
+the build container, which is why the vectors are committed.  Tier-U fixtures (``tier_u_*.npz``)
+come from the builder-defined oracles (oracle/c/ssdr_oracle.c, oracle/tier_u.py) -- parity unpinned.
+
+    python -m oracle.make_golden
+"""
+import os
+import queue
+import sys
+from collections import deque
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import ref_import, tier_u, c_oracle   # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_waterfall_line(m, lines_u8, zoom, auto, dlow, dhigh, low_clip=None, dyn=None):
+    """Run the reference's own averaging (utils:881-886) + spectrum_db2col (utils:787-813)."""
+    wf = m.kiwi_waterfall.__new__(m.kiwi_waterfall)
+    wf.zoom, wf.wf_auto_scaling = zoom, auto
+    wf.delta_low_db, wf.delta_high_db = dlow, dhigh
+    wf.dynamic_range = wf.MIN_DYN_RANGE if dyn is None else dyn
+    if low_clip is not None:
+        wf.low_clip_db = low_clip
+    n = lines_u8.shape[0]
+    if n > 1:
+        dq = deque([], n)
+        for k in range(n):
+            # receive_spectrum, utils:783-784
+            dq.append(np.ndarray(len(lines_u8[k].tobytes()), dtype='B', buffer=lines_u8[k].tobytes()).astype(np.float32))
+        wf.spectrum = np.mean(dq, axis=0)
+    else:
+        wf.spectrum = lines_u8[0].astype(np.float32)
+    spectrum = wf.spectrum.copy()
+    wf.spectrum_db2col()
+    return spectrum, wf.wf_color.copy(), np.array([wf.low_clip_db, wf.high_clip_db, wf.dynamic_range,
+                                                   wf.wf_min_db, wf.wf_max_db], np.float32)
+
+
+def gen_tier_p_waterfall(m):
+    rng = np.random.default_rng(20261017)
+    cases = []
+    specs = [(1024, 1, 0), (1024, 10, 3), (1024, 100, 14), (256, 7, 1), (2048, 3, 5), (16384, 10, 2), (1024, 2, 0)]
+    for W, n, zoom in specs:
+        for kind in range(3):
+            if kind == 0:
+                lines = np.clip(rng.normal(110, 7, (n, W)), 0, 255)
+                lines[:, rng.integers(0, W, 5)] += 90
+            elif kind == 1:
+                lines = rng.integers(0, 256, (n, W))
+            else:
+                lines = np.full((n, W), int(rng.integers(0, 256)))      # flat line: dyn range = 40 floor
+            lines = np.clip(lines, 0, 255).astype(np.uint8)
+            auto = kind != 1 or n == 1
+            dlow, dhigh = (int(rng.integers(-15, 15)), int(rng.integers(-15, 15))) if kind == 0 else (0, 0)
+            spec, col, sc = ref_waterfall_line(m, lines, zoom, auto, dlow, dhigh, low_clip=-120 if not auto else None)
+            cases.append(dict(lines=lines, zoom=zoom, auto=auto, dlow=dlow, dhigh=dhigh, spectrum=spec, colour=col, scalars=sc))
+    flat = {}
+    for i, c in enumerate(cases):
+        for k, v in c.items():
+            flat["c%02d_%s" % (i, k)] = np.asarray(v)
+    flat["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(OUT, "tier_p_waterfall.npz"), **flat)
+    return len(cases)
+
+
+def gen_tier_p_audio(m):
+    rng = np.random.default_rng(77)
+    f = m.filtering(6000, 48000)
+    snd = m.kiwi_sound.__new__(m.kiwi_sound)
+    snd.kiwi_filter = f
+    snd.n_tap = f.n_tap
+    snd.old_buffer = np.zeros(f.n_tap - 1)
+    snd.late_flag = False
+    snd.audio_buffer = queue.Queue()
+    snd.rssi, snd.mute_counter, snd.max_rssi_before_mute, snd.muting_delay = -90, 0, -20, 15
+    snd.audio_rec = type("AR", (), {"recording_flag": False})()
+    xs, vols, bals, outs = [], [], [], []
+    for k in range(12):
+        x = rng.integers(-32768, 32768, 512).astype(np.int16)
+        if k == 3:
+            x[:] = 32767                      # full-scale DC: exercises the int16 wrap at volume 150
+        snd.volume = int(rng.integers(0, 16)) * 10 if k != 3 else 150
+        snd.audio_balance = float(np.round(rng.uniform(-1, 1), 2))
+        snd.audio_buffer.put(x)
+        out = np.zeros((2048, 2), np.int16)
+        snd.play_buffer(out, 2048, None, None)
+        xs.append(x); vols.append(snd.volume); bals.append(snd.audio_balance); outs.append(out.copy())
+    # SND frame parse, utils:1065-1072
+    body = rng.integers(-32768, 32768, 512).astype(">i2").tobytes()
+    msg = b"SND" + bytes([2]) + (1234).to_bytes(4, "little") + (870).to_bytes(2, "big") + body
+    np.savez_compressed(os.path.join(OUT, "tier_p_audio.npz"), h=f.h, x=np.stack(xs), volume=np.array(vols),
+                        balance=np.array(bals), out=np.stack(outs), snd_msg=np.frombuffer(msg, np.uint8),
+                        snd_samples=np.frombuffer(body, ">i2").astype(np.int16))
+    return len(xs)
+
+
+def gen_tier_u():
+    # waterfall: BASELINE config 1 (single 1024-pt frame) + one 16384-pt, 2-frame channel
+    x1 = tier_u.synth_iq(1024, seed=1234)
+    r1 = c_oracle.wf_rows(x1[None], zoom=0)
+    x2 = tier_u.synth_batch(2, 2, 16384, seed=99)
+    r2 = c_oracle.wf_rows(x2, zoom=3)
+    np.savez_compressed(os.path.join(OUT, "tier_u_waterfall.npz"), iq1=x1, bytes1=c_oracle.wf_frame_bytes(x1[0]),
+                        pixels1=r1["pixels"], spectrum1=r1["spectrum"], iq2=x2, pixels2=r2["pixels"],
+                        sums2=r2["sums"], scalars2=r2["scalars"])
+    # demod: one short stream per mode
+    d = {}
+    for mode in tier_u.MODES:
+        p = tier_u.DemodParams(mode, decay=1000 if mode == "cw" else 4000, hang=(mode == "cw"))
+        x = tier_u.synth_demod_iq(mode, 512 * 8, seed=5)
+        st = tier_u.DemodState()
+        pcm, rssi = tier_u.demod(x, p, st)
+        d["iq_" + mode], d["pcm_" + mode], d["rssi_" + mode] = x, pcm.astype(np.float32), rssi.astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "tier_u_demod.npz"), **d)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    m = ref_import.load()
+    print("tier_p waterfall cases:", gen_tier_p_waterfall(m))
+    print("tier_p audio blocks:", gen_tier_p_audio(m))
+    gen_tier_u()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

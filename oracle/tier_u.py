@@ -233,7 +233,9 @@ def demod(iq, p, st, fs=KIWI_RATE):
         rssi[b] = 10.0 * np.log10(max(np.mean(mb ** 2), 1e-30) / FS ** 2) + AGC_FS_DBM
         if mode == 4:                                        # NBFM: quadrature detector, no AGC
             prev = np.concatenate([[st.zprev], zb[:-1]])
-            pcm[sl] = np.angle(zb * np.conj(prev)) * (32767.0 / np.pi)
+            prod = zb * np.conj(prev)
+            # a zero product (first sample of a stream, or silence) demodulates to 0, not +-pi
+            pcm[sl] = np.where(prod == 0, 0.0, np.angle(prod)) * (32767.0 / np.pi)
             st.zprev = zb[-1]
         else:
             if mode == 0:                                    # AM: envelope minus tracked carrier

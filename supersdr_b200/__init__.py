@@ -1,0 +1,15 @@
+"""supersdr_b200 -- B200-native (sm_100a) IQ-sample DSP behind SuperSDR's waterfall and audio classes.
+
+Python host code over the C ABI of ``libssdr_b200.so`` (include/ssdr_b200.h); hand-written CUDA
+kernels, no PyTorch / Triton / cuFFT on the compute path and no CPU fallback.  Importing the package
+requires the built shared library; computing requires a B200.
+"""
+from ._lib import (SsdrError, init, last_error, DeviceBuffer, PinnedArray, lib, EXPORTS, LIB_PATH,
+                   SSDR_IQ_CF32, SSDR_IQ_S16BE, FS, WF_CAL_DB, KIWI_RATE, FRAME, FIR_TAPS)
+from .waterfall import WaterfallBank, kiwi_waterfall, percentile_index
+from .sound import (DemodBank, InterpBank, filtering, kiwi_sound, start_audio_stream, demod_params,
+                    design_lowpass, default_passband, unpack_iq)
+
+__all__ = ["SsdrError", "init", "last_error", "DeviceBuffer", "PinnedArray", "WaterfallBank", "kiwi_waterfall",
+           "percentile_index", "DemodBank", "InterpBank", "filtering", "kiwi_sound", "start_audio_stream",
+           "demod_params", "design_lowpass", "default_passband", "unpack_iq"]

@@ -1,0 +1,197 @@
+"""ctypes binding of libssdr_b200.so (include/ssdr_b200.h).
+
+There is no CPU fallback: if the shared library has not been built, importing this module raises;
+if no CUDA device is usable, every compute call raises ``SsdrError``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssdr_b200.so")
+
+SSDR_IQ_CF32, SSDR_IQ_S16BE = 0, 1
+MODE_AM, MODE_USB, MODE_LSB, MODE_CW, MODE_NBFM = 0, 1, 2, 3, 4
+FS = 32768.0
+WF_CAL_DB = -10.0
+KIWI_RATE = 12000
+FRAME = 512
+FIR_TAPS = 127
+INTERP_TAPS_MAX = 64
+
+
+class SsdrError(RuntimeError):
+    pass
+
+
+class WfDisplay(C.Structure):
+    _fields_ = [("zoom", C.c_int32), ("auto_scale", C.c_int32), ("delta_low_db", C.c_int32),
+                ("delta_high_db", C.c_int32), ("low_clip_db", C.c_float), ("dynamic_range", C.c_float)]
+
+
+class WfScalars(C.Structure):
+    _fields_ = [("low_clip_db", C.c_float), ("high_clip_db", C.c_float), ("dynamic_range", C.c_float),
+                ("wf_min_db", C.c_float), ("wf_max_db", C.c_float)]
+
+
+class DemodParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("low_cut_hz", C.c_float), ("high_cut_hz", C.c_float),
+                ("freq_offset_hz", C.c_float), ("agc_on", C.c_int32), ("agc_hang", C.c_int32),
+                ("agc_thresh_dbm", C.c_float), ("agc_slope_db", C.c_float), ("agc_decay_ms", C.c_float),
+                ("agc_man_gain_db", C.c_float), ("taps", C.c_float * FIR_TAPS)]
+
+
+SCALARS_DTYPE = np.dtype([("low_clip_db", "<f4"), ("high_clip_db", "<f4"), ("dynamic_range", "<f4"),
+                          ("wf_min_db", "<f4"), ("wf_max_db", "<f4")])
+
+_vp, _i, _f, _d, _sz, _u32 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_uint32
+_pvp = C.POINTER(C.c_void_p)
+
+_PROTOS = {
+    "ssdr_abi_version": (C.c_int, []),
+    "ssdr_last_error": (C.c_char_p, []),
+    "ssdr_init": (_i, [_i]),
+    "ssdr_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.c_char_p, _i]),
+    "ssdr_launch_count": (C.c_uint64, []),
+    "ssdr_dev_alloc": (_i, [_pvp, _sz]),
+    "ssdr_dev_free": (_i, [_vp]),
+    "ssdr_host_alloc": (_i, [_pvp, _sz]),
+    "ssdr_host_free": (_i, [_vp]),
+    "ssdr_memcpy_h2d": (_i, [_vp, _vp, _sz]),
+    "ssdr_memcpy_d2h": (_i, [_vp, _vp, _sz]),
+    "ssdr_dev_memset": (_i, [_vp, _i, _sz]),
+    "ssdr_device_sync": (_i, []),
+    "ssdr_synth_iq_dev": (_i, [_vp, _i, _i, _i, _i, _u32]),
+    "ssdr_wf_create": (_i, [_pvp, _i, _i, _i, _i, _d, _i, _f]),
+    "ssdr_wf_destroy": (_i, [_vp]),
+    "ssdr_wf_set_display": (_i, [_vp, _i, _i, C.POINTER(WfDisplay)]),
+    "ssdr_wf_get_tables": (_i, [_vp, _vp, _vp, C.POINTER(_i)]),
+    "ssdr_wf_process": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ssdr_wf_process_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ssdr_wf_colorrow_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "ssdr_wf_colorrow_u8_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "ssdr_wf_sync": (_i, [_vp]),
+    "ssdr_wf_time_dev": (_i, [_vp, _vp, _i, _vp, _i, C.POINTER(_f)]),
+    "ssdr_demod_create": (_i, [_pvp, _i, _i]),
+    "ssdr_demod_destroy": (_i, [_vp]),
+    "ssdr_demod_set": (_i, [_vp, _i, _i, C.POINTER(DemodParams)]),
+    "ssdr_demod_reset": (_i, [_vp]),
+    "ssdr_demod_process": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "ssdr_demod_process_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "ssdr_demod_sync": (_i, [_vp]),
+    "ssdr_demod_time_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, C.POINTER(_f)]),
+    "ssdr_interp_create": (_i, [_pvp, _i, _i, _vp, _i, _i]),
+    "ssdr_interp_destroy": (_i, [_vp]),
+    "ssdr_interp_reset": (_i, [_vp]),
+    "ssdr_interp_process": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ssdr_interp_process_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ssdr_interp_sync": (_i, [_vp]),
+    "ssdr_fir_valid_f64": (_i, [_vp, _sz, _vp, _i, _vp]),
+    "ssdr_unpack_iq_s16be": (_i, [_vp, _vp, _sz]),
+    "ssdr_unpack_iq_s16be_dev": (_i, [_vp, _vp, _sz]),
+}
+EXPORTS = sorted(_PROTOS)
+
+if not os.path.isfile(LIB_PATH):
+    raise ImportError("libssdr_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "or `make -C supersdr_b200/csrc`); supersdr_b200 has no CPU fallback")
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in _PROTOS.items():
+    _fn = getattr(lib, _name)          # AttributeError here = header / library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+_initialised = False
+
+
+def last_error():
+    return lib.ssdr_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc < 0:
+        raise SsdrError("libssdr_b200 error %d: %s" % (rc, last_error()))
+    return rc
+
+
+def init(device=None):
+    """Select the CUDA device for this process (default: LOCAL_RANK or 0). Idempotent."""
+    global _initialised
+    if device is None:
+        if _initialised:
+            return
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    check(lib.ssdr_init(int(device)))
+    _initialised = True
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceBuffer:
+    """Device memory owned by Python (bench / resident-data callers)."""
+
+    def __init__(self, nbytes):
+        init()
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(lib.ssdr_dev_alloc(C.byref(p), self.nbytes))
+        self.ptr = p
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        check(lib.ssdr_memcpy_h2d(self.ptr, ptr(arr), arr.nbytes))
+        return self
+
+    def download(self, dtype, shape, offset_bytes=0):
+        out = np.empty(shape, dtype=dtype)
+        assert offset_bytes + out.nbytes <= self.nbytes
+        check(lib.ssdr_memcpy_d2h(ptr(out), C.c_void_p(self.ptr.value + offset_bytes), out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib.ssdr_dev_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedArray:
+    """A numpy array backed by pinned host memory (fast, truly asynchronous H2D/D2H)."""
+
+    def __init__(self, shape, dtype):
+        init()
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(lib.ssdr_host_alloc(C.byref(p), max(self.nbytes, 1)))
+        self._p = p
+        buf = (C.c_char * self.nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib.ssdr_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

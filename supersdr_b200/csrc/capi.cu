@@ -1,0 +1,642 @@
+// C ABI of libssdr_b200.so (include/ssdr_b200.h): handles, device buffers, streams, and the
+// host<->device pipelines around the kernels in wf_kernels.cu / demod_kernels.cu / misc_kernels.cu.
+// No CPU fallback: every compute entry point fails with SSDR_E_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "common.cuh"
+#include "demod_host.h"
+#include "misc_host.h"
+#include "wf_host.h"
+
+namespace ssdr {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+static int g_sm_count = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaDeviceProp p;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) g_sm_count = p.multiProcessorCount;
+        else g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+template <class Tp>
+static int dev_alloc(Tp** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return SSDR_OK;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(Tp));
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(Tp), cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? SSDR_E_NOMEM : SSDR_E_CUDA; }
+    return SSDR_OK;
+}
+
+}  // namespace ssdr
+
+using namespace ssdr;
+
+// =============================================================================================
+// handles
+// =============================================================================================
+struct ssdr_wf {
+    int nfft = 0, batch = 0, n_avg = 1, window = 1, p_lo = 0;
+    float p_gamma = 0.f;
+    double cal_db = 0.0;
+    float est_c1 = 0.f, est_c0 = 0.f;
+    std::vector<float> h_wtab, h_thr;
+    float* d_wtab = nullptr;
+    float* d_thr = nullptr;
+    ssdr_wf_display_t* d_disp = nullptr;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
+    // host-API staging (lazily allocated): double-buffered input chunks + full-size outputs
+    int chunk_ch = 0;
+    void* d_in[2] = {nullptr, nullptr};
+    size_t in_bytes = 0;
+    uint8_t* d_px = nullptr;
+    float* d_col = nullptr;
+    float* d_spec = nullptr;
+    ssdr_wf_scalars_t* d_sc = nullptr;
+};
+
+struct ssdr_demod {
+    int batch = 0, max_samples = 0;
+    DemodChan* d_chan = nullptr;
+    DemodState* d_state = nullptr;
+    float2* d_hist = nullptr;
+    float* d_taps = nullptr;
+    cudaStream_t compute = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    double am_pow16[5];
+    void* d_in = nullptr;
+    size_t in_bytes = 0;
+    float* d_f32 = nullptr;
+    int16_t* d_i16 = nullptr;
+    float* d_rssi = nullptr;
+};
+
+struct ssdr_interp {
+    int batch = 0, ratio = 0, n_taps = 0, max_samples = 0, hs = 0, cur = 0;
+    double* d_taps = nullptr;
+    double* d_hist[2] = {nullptr, nullptr};
+    cudaStream_t compute = nullptr;
+    int16_t* d_in = nullptr;
+    float* d_vol = nullptr;
+    float* d_bal = nullptr;
+    int16_t* d_out = nullptr;
+    double* d_mono = nullptr;
+};
+
+extern "C" {
+
+// =============================================================================================
+// library / device
+// =============================================================================================
+int ssdr_abi_version(void) { return SSDR_ABI_VERSION; }
+const char* ssdr_last_error(void) { return g_err; }
+uint64_t ssdr_launch_count(void) { return g_launches.load(); }
+
+int ssdr_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { set_error("no CUDA device: %s", cudaGetErrorString(e)); return SSDR_E_CUDA; }
+    SSDR_ARG(device >= 0 && device < n, "device %d out of range (0..%d)", device, n - 1);
+    SSDR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    SSDR_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) { set_error("libssdr_b200 is built for sm_100a only; device %d is sm_%d%d", device, p.major, p.minor); return SSDR_E_CUDA; }
+    g_sm_count = p.multiProcessorCount;
+    SSDR_CUDA(cudaFree(0));
+    return SSDR_OK;
+}
+
+int ssdr_device_info(int* sms, int* cc_major, int* cc_minor, size_t* hbm_bytes, char* name, int name_len) {
+    int dev = 0;
+    SSDR_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    SSDR_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sms) *sms = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
+    if (name && name_len > 0) { std::strncpy(name, p.name, (size_t)name_len - 1); name[name_len - 1] = 0; }
+    return SSDR_OK;
+}
+
+int ssdr_dev_alloc(void** dev, size_t bytes) {
+    SSDR_ARG(dev != nullptr, "null pointer");
+    return dev_alloc(reinterpret_cast<unsigned char**>(dev), bytes);
+}
+int ssdr_dev_free(void* dev) { SSDR_CUDA(cudaFree(dev)); return SSDR_OK; }
+int ssdr_host_alloc(void** host, size_t bytes) { SSDR_ARG(host != nullptr, "null pointer"); SSDR_CUDA(cudaMallocHost(host, bytes)); return SSDR_OK; }
+int ssdr_host_free(void* host) { SSDR_CUDA(cudaFreeHost(host)); return SSDR_OK; }
+int ssdr_memcpy_h2d(void* dev, const void* host, size_t bytes) { SSDR_CUDA(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice)); return SSDR_OK; }
+int ssdr_memcpy_d2h(void* host, const void* dev, size_t bytes) { SSDR_CUDA(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost)); return SSDR_OK; }
+int ssdr_dev_memset(void* dev, int value, size_t bytes) { SSDR_CUDA(cudaMemset(dev, value, bytes)); return SSDR_OK; }
+int ssdr_device_sync(void) { SSDR_CUDA(cudaDeviceSynchronize()); return SSDR_OK; }
+
+int ssdr_synth_iq_dev(void* iq_dev, int iq_format, int batch, int frames, int nfft, uint32_t seed) {
+    SSDR_ARG(iq_dev && batch > 0 && frames > 0 && nfft > 0, "bad synth arguments");
+    SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
+    int rc = synth_launch(iq_dev, iq_format, batch, frames, nfft, seed, 0);
+    if (rc) return rc;
+    SSDR_CUDA(cudaDeviceSynchronize());
+    return SSDR_OK;
+}
+
+// =============================================================================================
+// waterfall
+// =============================================================================================
+static size_t iq_sample_bytes(int fmt) { return fmt == SSDR_IQ_CF32 ? 8 : 4; }
+
+int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, double cal_db, int p_lo, float p_gamma) {
+    SSDR_ARG(out != nullptr, "null handle pointer");
+    *out = nullptr;
+    int radices[8];
+    SSDR_ARG(wf_plan(nfft, radices) > 0, "nfft %d unsupported (power of two 256..16384)", nfft);
+    SSDR_ARG(batch >= 1, "batch %d < 1", batch);
+    SSDR_ARG(n_avg >= 1 && n_avg <= 100, "n_avg %d outside 1..100 (supersdr.py:376-385)", n_avg);
+    SSDR_ARG(p_lo >= 0 && p_lo < nfft && p_gamma >= 0.f && p_gamma < 1.f, "bad percentile index (%d, %g)", p_lo, (double)p_gamma);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    ssdr_wf* h = new ssdr_wf();
+    h->nfft = nfft; h->batch = batch; h->n_avg = n_avg; h->window = window ? 1 : 0; h->cal_db = cal_db;
+    h->p_lo = p_lo; h->p_gamma = p_gamma;
+    // spec tables: twiddles W_N^k = (cos, -sin)(2 pi k / N) and the byte thresholds
+    h->h_wtab.resize(2 * (size_t)nfft);
+    for (int k = 0; k < nfft; ++k) {
+        double a = 2.0 * 3.14159265358979323846 * (double)k / (double)nfft;
+        h->h_wtab[2 * k] = (float)std::cos(a);
+        h->h_wtab[2 * k + 1] = (float)(-std::sin(a));
+    }
+    h->h_thr.resize(257);
+    double ref = (double)nfft * 32768.0 * 0.5;
+    ref = ref * ref;
+    h->h_thr[0] = 0.0f;
+    for (int k = 1; k < 256; ++k) h->h_thr[k] = (float)(ref * std::pow(10.0, ((double)k - 0.5 - 255.0 - cal_db) / 10.0));
+    h->h_thr[256] = std::numeric_limits<float>::infinity();
+    h->est_c1 = (float)(10.0 * std::log10(2.0));
+    h->est_c0 = (float)(-10.0 * std::log10(ref) + cal_db + 255.0 + 0.5);
+    int rc = SSDR_OK;
+    auto fail = [&](int code) { ssdr_wf_destroy(h); return code; };
+    if ((rc = dev_alloc(&h->d_wtab, 2 * (size_t)nfft))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_thr, 257))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_disp, (size_t)batch))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_sc, (size_t)batch))) return fail(rc);
+    if (cudaMemcpy(h->d_wtab, h->h_wtab.data(), sizeof(float) * 2 * nfft, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->d_thr, h->h_thr.data(), sizeof(float) * 257, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("table upload failed");
+        return fail(SSDR_E_CUDA);
+    }
+    std::vector<ssdr_wf_display_t> disp((size_t)batch);
+    for (auto& d : disp) { d.zoom = 0; d.auto_scale = 1; d.delta_low_db = 0; d.delta_high_db = 0; d.low_clip_db = -120.f; d.dynamic_range = 40.f; }
+    if (cudaMemcpy(h->d_disp, disp.data(), sizeof(ssdr_wf_display_t) * batch, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("display upload failed"); return fail(SSDR_E_CUDA); }
+    if (cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(SSDR_E_CUDA); }
+    for (int i = 0; i < 2; ++i) {
+        if (cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
+    }
+    if (cudaEventCreate(&h->ev_t0) != cudaSuccess || cudaEventCreate(&h->ev_t1) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
+    *out = h;
+    return SSDR_OK;
+}
+
+int ssdr_wf_destroy(ssdr_wf_t h) {
+    if (!h) return SSDR_OK;
+    if (h->compute) cudaStreamSynchronize(h->compute);
+    if (h->copy) cudaStreamSynchronize(h->copy);
+    cudaFree(h->d_wtab); cudaFree(h->d_thr); cudaFree(h->d_disp); cudaFree(h->d_in[0]); cudaFree(h->d_in[1]);
+    cudaFree(h->d_px); cudaFree(h->d_col); cudaFree(h->d_spec); cudaFree(h->d_sc);
+    for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->compute) cudaStreamDestroy(h->compute);
+    if (h->copy) cudaStreamDestroy(h->copy);
+    delete h;
+    return SSDR_OK;
+}
+
+int ssdr_wf_set_display(ssdr_wf_t h, int first, int count, const ssdr_wf_display_t* params) {
+    SSDR_ARG(h && params, "null argument");
+    SSDR_ARG(first >= 0 && count >= 0 && first + count <= h->batch, "channel range [%d, %d) outside batch %d", first, first + count, h->batch);
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    SSDR_CUDA(cudaMemcpy(h->d_disp + first, params, sizeof(ssdr_wf_display_t) * (size_t)count, cudaMemcpyHostToDevice));
+    return SSDR_OK;
+}
+
+int ssdr_wf_get_tables(ssdr_wf_t h, float* twiddles, float* thresholds, int* radices) {
+    SSDR_ARG(h != nullptr, "null handle");
+    if (twiddles) std::memcpy(twiddles, h->h_wtab.data(), sizeof(float) * 2 * (size_t)h->nfft);
+    if (thresholds) std::memcpy(thresholds, h->h_thr.data(), sizeof(float) * 256);
+    int r[8];
+    int np = wf_plan(h->nfft, r);
+    if (radices) for (int i = 0; i < np; ++i) radices[i] = r[i];
+    return np;
+}
+
+static WfLaunch wf_base(ssdr_wf_t h) {
+    WfLaunch a;
+    a.wtab = h->d_wtab; a.thr = h->d_thr; a.nfft = h->nfft; a.n_avg = h->n_avg; a.window = h->window;
+    a.p_lo = h->p_lo; a.p_gamma = h->p_gamma; a.est_c1 = h->est_c1; a.est_c0 = h->est_c0;
+    return a;
+}
+
+int ssdr_wf_process_dev(ssdr_wf_t h, const void* iq_dev, int iq_format, uint8_t* pixels_dev, float* colour_dev,
+                        float* spectrum_dev, ssdr_wf_scalars_t* scalars_dev) {
+    SSDR_ARG(h && iq_dev, "null argument");
+    SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
+    WfLaunch a = wf_base(h);
+    a.iq = iq_dev; a.iq_format = iq_format; a.disp = h->d_disp; a.batch = h->batch;
+    a.pixels = pixels_dev; a.colour = colour_dev; a.spectrum = spectrum_dev; a.scalars = scalars_dev ? scalars_dev : h->d_sc;
+    return wf_launch(a, h->compute);
+}
+
+int ssdr_wf_colorrow_u8_dev(ssdr_wf_t h, const uint8_t* lines_dev, uint8_t* pixels_dev, float* colour_dev,
+                            float* spectrum_dev, ssdr_wf_scalars_t* scalars_dev) {
+    SSDR_ARG(h && lines_dev, "null argument");
+    WfLaunch a = wf_base(h);
+    a.lines = lines_dev; a.disp = h->d_disp; a.batch = h->batch;
+    a.pixels = pixels_dev; a.colour = colour_dev; a.spectrum = spectrum_dev; a.scalars = scalars_dev ? scalars_dev : h->d_sc;
+    return wf_launch(a, h->compute);
+}
+
+int ssdr_wf_sync(ssdr_wf_t h) {
+    SSDR_ARG(h != nullptr, "null handle");
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    SSDR_CUDA(cudaStreamSynchronize(h->copy));
+    return SSDR_OK;
+}
+
+// lazily allocate the host-API staging buffers
+static int wf_ensure_staging(ssdr_wf_t h, size_t bytes_per_channel, bool want_col, bool want_spec) {
+    if (h->chunk_ch == 0 || h->in_bytes < bytes_per_channel * (size_t)h->chunk_ch) {
+        cudaFree(h->d_in[0]); cudaFree(h->d_in[1]);
+        h->d_in[0] = h->d_in[1] = nullptr;
+        // ~256 MiB per chunk: large enough to fill the GPU, small enough to overlap copy and compute
+        size_t ch = std::max<size_t>(1, ((size_t)256 << 20) / bytes_per_channel);
+        const size_t wave = (size_t)sm_count();
+        if (ch >= wave) ch = ch / wave * wave;
+        ch = std::min<size_t>(ch, (size_t)h->batch);
+        h->chunk_ch = (int)ch;
+        h->in_bytes = bytes_per_channel * ch;
+        int rc;
+        for (int i = 0; i < 2; ++i)
+            if ((rc = dev_alloc(reinterpret_cast<unsigned char**>(&h->d_in[i]), h->in_bytes))) return rc;
+    }
+    int rc;
+    if (!h->d_px && (rc = dev_alloc(&h->d_px, (size_t)h->batch * h->nfft))) return rc;
+    if (want_col && !h->d_col && (rc = dev_alloc(&h->d_col, (size_t)h->batch * h->nfft))) return rc;
+    if (want_spec && !h->d_spec && (rc = dev_alloc(&h->d_spec, (size_t)h->batch * h->nfft))) return rc;
+    return SSDR_OK;
+}
+
+static int wf_process_host(ssdr_wf_t h, const void* in_host, size_t bytes_per_channel, int iq_format, bool lines,
+                           uint8_t* pixels, float* colour, float* spectrum, ssdr_wf_scalars_t* scalars) {
+    int rc = wf_ensure_staging(h, bytes_per_channel, colour != nullptr, spectrum != nullptr);
+    if (rc) return rc;
+    const size_t N = (size_t)h->nfft;
+    int slot = 0;
+    for (int c0 = 0; c0 < h->batch; c0 += h->chunk_ch, slot ^= 1) {
+        const int nch = std::min(h->chunk_ch, h->batch - c0);
+        // the kernel that last read this slot must be done before we overwrite it
+        SSDR_CUDA(cudaStreamWaitEvent(h->copy, h->ev_done[slot], 0));
+        SSDR_CUDA(cudaMemcpyAsync(h->d_in[slot], static_cast<const unsigned char*>(in_host) + (size_t)c0 * bytes_per_channel,
+                                  (size_t)nch * bytes_per_channel, cudaMemcpyHostToDevice, h->copy));
+        SSDR_CUDA(cudaEventRecord(h->ev_copied[slot], h->copy));
+        SSDR_CUDA(cudaStreamWaitEvent(h->compute, h->ev_copied[slot], 0));
+        WfLaunch a = wf_base(h);
+        if (lines) a.lines = static_cast<const uint8_t*>(h->d_in[slot]);
+        else { a.iq = h->d_in[slot]; a.iq_format = iq_format; }
+        a.disp = h->d_disp + c0; a.batch = nch;
+        a.pixels = h->d_px + (size_t)c0 * N;
+        a.colour = colour ? h->d_col + (size_t)c0 * N : nullptr;
+        a.spectrum = spectrum ? h->d_spec + (size_t)c0 * N : nullptr;
+        a.scalars = h->d_sc + c0;
+        if ((rc = wf_launch(a, h->compute))) return rc;
+        SSDR_CUDA(cudaEventRecord(h->ev_done[slot], h->compute));
+        // results of this chunk go back on the compute stream (small next to the input)
+        if (pixels) SSDR_CUDA(cudaMemcpyAsync(pixels + (size_t)c0 * N, a.pixels, (size_t)nch * N, cudaMemcpyDeviceToHost, h->compute));
+        if (colour) SSDR_CUDA(cudaMemcpyAsync(colour + (size_t)c0 * N, a.colour, (size_t)nch * N * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
+        if (spectrum) SSDR_CUDA(cudaMemcpyAsync(spectrum + (size_t)c0 * N, a.spectrum, (size_t)nch * N * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
+        if (scalars) SSDR_CUDA(cudaMemcpyAsync(scalars + c0, a.scalars, (size_t)nch * sizeof(ssdr_wf_scalars_t), cudaMemcpyDeviceToHost, h->compute));
+    }
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    SSDR_CUDA(cudaStreamSynchronize(h->copy));
+    return SSDR_OK;
+}
+
+int ssdr_wf_process(ssdr_wf_t h, const void* iq_host, int iq_format, uint8_t* pixels, float* colour, float* spectrum,
+                    ssdr_wf_scalars_t* scalars) {
+    SSDR_ARG(h && iq_host, "null argument");
+    SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
+    return wf_process_host(h, iq_host, (size_t)h->n_avg * h->nfft * iq_sample_bytes(iq_format), iq_format, false,
+                           pixels, colour, spectrum, scalars);
+}
+
+int ssdr_wf_colorrow_u8(ssdr_wf_t h, const uint8_t* lines_host, uint8_t* pixels, float* colour, float* spectrum,
+                        ssdr_wf_scalars_t* scalars) {
+    SSDR_ARG(h && lines_host, "null argument");
+    return wf_process_host(h, lines_host, (size_t)h->n_avg * h->nfft, 0, true, pixels, colour, spectrum, scalars);
+}
+
+int ssdr_wf_time_dev(ssdr_wf_t h, const void* iq_dev, int iq_format, uint8_t* pixels_dev, int iters, float* total_ms) {
+    SSDR_ARG(h && iq_dev && total_ms && iters >= 1, "bad argument");
+    SSDR_CUDA(cudaEventRecord(h->ev_t0, h->compute));
+    for (int i = 0; i < iters; ++i) {
+        int rc = ssdr_wf_process_dev(h, iq_dev, iq_format, pixels_dev, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    SSDR_CUDA(cudaEventRecord(h->ev_t1, h->compute));
+    SSDR_CUDA(cudaEventSynchronize(h->ev_t1));
+    SSDR_CUDA(cudaEventElapsedTime(total_ms, h->ev_t0, h->ev_t1));
+    return SSDR_OK;
+}
+
+// =============================================================================================
+// demodulator
+// =============================================================================================
+int ssdr_demod_create(ssdr_demod_t* out, int batch, int max_samples) {
+    SSDR_ARG(out != nullptr, "null handle pointer");
+    *out = nullptr;
+    SSDR_ARG(batch >= 1, "batch %d < 1", batch);
+    SSDR_ARG(max_samples >= SSDR_FRAME && max_samples % SSDR_FRAME == 0, "max_samples_per_call %d must be a positive multiple of %d", max_samples, SSDR_FRAME);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    ssdr_demod* h = new ssdr_demod();
+    h->batch = batch; h->max_samples = max_samples;
+    double om16 = std::pow(1.0 - kDemodAmBeta, 16.0);
+    for (int s = 0; s < 5; ++s) { h->am_pow16[s] = om16; om16 *= om16; }
+    int rc;
+    auto fail = [&](int code) { ssdr_demod_destroy(h); return code; };
+    if ((rc = dev_alloc(&h->d_chan, (size_t)batch))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_state, (size_t)batch))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_hist, (size_t)batch * (SSDR_FIR_TAPS - 1)))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_taps, (size_t)batch * SSDR_FIR_TAPS))) return fail(rc);
+    if (cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(SSDR_E_CUDA); }
+    if (cudaEventCreate(&h->ev_t0) != cudaSuccess || cudaEventCreate(&h->ev_t1) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
+    cudaMemset(h->d_chan, 0, sizeof(DemodChan) * (size_t)batch);
+    cudaMemset(h->d_taps, 0, sizeof(float) * (size_t)batch * SSDR_FIR_TAPS);
+    *out = h;
+    if ((rc = ssdr_demod_reset(h))) { *out = nullptr; return fail(rc); }
+    return SSDR_OK;
+}
+
+int ssdr_demod_destroy(ssdr_demod_t h) {
+    if (!h) return SSDR_OK;
+    if (h->compute) cudaStreamSynchronize(h->compute);
+    cudaFree(h->d_chan); cudaFree(h->d_state); cudaFree(h->d_hist); cudaFree(h->d_taps);
+    cudaFree(h->d_in); cudaFree(h->d_f32); cudaFree(h->d_i16); cudaFree(h->d_rssi);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->compute) cudaStreamDestroy(h->compute);
+    delete h;
+    return SSDR_OK;
+}
+
+int ssdr_demod_reset(ssdr_demod_t h) {
+    SSDR_ARG(h != nullptr, "null handle");
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    SSDR_CUDA(cudaMemset(h->d_state, 0, sizeof(DemodState) * (size_t)h->batch));
+    SSDR_CUDA(cudaMemset(h->d_hist, 0, sizeof(float2) * (size_t)h->batch * (SSDR_FIR_TAPS - 1)));
+    return SSDR_OK;
+}
+
+static unsigned phase_inc(double f_hz) {
+    double v = std::nearbyint(f_hz / (double)SSDR_KIWI_RATE * 4294967296.0);
+    long long iv = (long long)v;
+    return (unsigned)((unsigned long long)iv & 0xffffffffull);
+}
+
+int ssdr_demod_set(ssdr_demod_t h, int first, int count, const ssdr_demod_params_t* p) {
+    SSDR_ARG(h && p, "null argument");
+    SSDR_ARG(first >= 0 && count >= 0 && first + count <= h->batch, "channel range [%d, %d) outside batch %d", first, first + count, h->batch);
+    std::vector<DemodChan> chan((size_t)count);
+    std::vector<float> taps((size_t)count * SSDR_FIR_TAPS);
+    for (int i = 0; i < count; ++i) {
+        const ssdr_demod_params_t& q = p[i];
+        SSDR_ARG(q.mode >= SSDR_MODE_AM && q.mode <= SSDR_MODE_NBFM, "channel %d: unknown mode %d", first + i, q.mode);
+        SSDR_ARG(q.high_cut_hz > q.low_cut_hz, "channel %d: high_cut %g <= low_cut %g", first + i, (double)q.high_cut_hz, (double)q.low_cut_hz);
+        SSDR_ARG(q.agc_decay_ms > 0.f, "channel %d: decay %g ms", first + i, (double)q.agc_decay_ms);
+        DemodChan& c = chan[(size_t)i];
+        const double fc = ((double)q.low_cut_hz + (double)q.high_cut_hz) / 2.0;
+        c.mode = q.mode; c.agc_on = q.agc_on ? 1 : 0; c.agc_hang = q.agc_hang ? 1 : 0;
+        c.inc1 = phase_inc((double)q.freq_offset_hz + fc);
+        c.inc2 = phase_inc(fc);
+        c.c2 = (float)(1.4426950408889634 / ((double)SSDR_KIWI_RATE * (double)q.agc_decay_ms / 1000.0));
+        c.knee2 = (float)(((double)q.agc_thresh_dbm - (double)kDemodFsDbm) / 20.0 * 3.321928094887362);
+        c.slope_m1 = (float)((double)q.agc_slope_db / 100.0 - 1.0);
+        c.man_gain = (float)std::pow(10.0, (double)q.agc_man_gain_db / 20.0);
+        std::memcpy(&taps[(size_t)i * SSDR_FIR_TAPS], q.taps, sizeof(float) * SSDR_FIR_TAPS);
+    }
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    SSDR_CUDA(cudaMemcpy(h->d_chan + first, chan.data(), sizeof(DemodChan) * (size_t)count, cudaMemcpyHostToDevice));
+    SSDR_CUDA(cudaMemcpy(h->d_taps + (size_t)first * SSDR_FIR_TAPS, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice));
+    return SSDR_OK;
+}
+
+int ssdr_demod_process_dev(ssdr_demod_t h, const void* iq_dev, int iq_format, int n_samples, float* pcm_f32_dev,
+                           int16_t* pcm_i16_dev, float* rssi_dev) {
+    SSDR_ARG(h && iq_dev, "null argument");
+    SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
+    SSDR_ARG(n_samples > 0 && n_samples % SSDR_FRAME == 0, "n_samples %d must be a positive multiple of %d", n_samples, SSDR_FRAME);
+    DemodLaunch a;
+    a.iq = iq_dev; a.iq_format = iq_format; a.chan = h->d_chan; a.state = h->d_state; a.hist = h->d_hist; a.taps = h->d_taps;
+    a.pcm_f32 = pcm_f32_dev; a.pcm_i16 = pcm_i16_dev; a.rssi = rssi_dev; a.batch = h->batch; a.n_samples = n_samples;
+    for (int s = 0; s < 5; ++s) a.am_pow16[s] = h->am_pow16[s];
+    return demod_launch(a, h->compute);
+}
+
+int ssdr_demod_process(ssdr_demod_t h, const void* iq_host, int iq_format, int n_samples, float* pcm_f32, int16_t* pcm_i16,
+                       float* rssi_dbm) {
+    SSDR_ARG(h && iq_host, "null argument");
+    SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
+    SSDR_ARG(n_samples > 0 && n_samples % SSDR_FRAME == 0 && n_samples <= h->max_samples,
+             "n_samples %d must be a multiple of %d and <= %d", n_samples, SSDR_FRAME, h->max_samples);
+    const size_t tot = (size_t)h->batch * n_samples, cap = (size_t)h->batch * h->max_samples;
+    int rc;
+    if (h->in_bytes < tot * iq_sample_bytes(iq_format)) {
+        cudaFree(h->d_in); h->d_in = nullptr;
+        h->in_bytes = cap * 8;
+        if ((rc = dev_alloc(reinterpret_cast<unsigned char**>(&h->d_in), h->in_bytes))) return rc;
+    }
+    if (pcm_f32 && !h->d_f32 && (rc = dev_alloc(&h->d_f32, cap))) return rc;
+    if (pcm_i16 && !h->d_i16 && (rc = dev_alloc(&h->d_i16, cap))) return rc;
+    if (rssi_dbm && !h->d_rssi && (rc = dev_alloc(&h->d_rssi, cap / SSDR_FRAME))) return rc;
+    SSDR_CUDA(cudaMemcpyAsync(h->d_in, iq_host, tot * iq_sample_bytes(iq_format), cudaMemcpyHostToDevice, h->compute));
+    if ((rc = ssdr_demod_process_dev(h, h->d_in, iq_format, n_samples, pcm_f32 ? h->d_f32 : nullptr, pcm_i16 ? h->d_i16 : nullptr,
+                                     rssi_dbm ? h->d_rssi : nullptr))) return rc;
+    if (pcm_f32) SSDR_CUDA(cudaMemcpyAsync(pcm_f32, h->d_f32, tot * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
+    if (pcm_i16) SSDR_CUDA(cudaMemcpyAsync(pcm_i16, h->d_i16, tot * sizeof(int16_t), cudaMemcpyDeviceToHost, h->compute));
+    if (rssi_dbm) SSDR_CUDA(cudaMemcpyAsync(rssi_dbm, h->d_rssi, tot / SSDR_FRAME * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    return SSDR_OK;
+}
+
+int ssdr_demod_sync(ssdr_demod_t h) {
+    SSDR_ARG(h != nullptr, "null handle");
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    return SSDR_OK;
+}
+
+int ssdr_demod_time_dev(ssdr_demod_t h, const void* iq_dev, int iq_format, int n_samples, float* pcm_f32_dev,
+                        int16_t* pcm_i16_dev, int iters, float* total_ms) {
+    SSDR_ARG(h && iq_dev && total_ms && iters >= 1, "bad argument");
+    SSDR_CUDA(cudaEventRecord(h->ev_t0, h->compute));
+    for (int i = 0; i < iters; ++i) {
+        int rc = ssdr_demod_process_dev(h, iq_dev, iq_format, n_samples, pcm_f32_dev, pcm_i16_dev, nullptr);
+        if (rc) return rc;
+    }
+    SSDR_CUDA(cudaEventRecord(h->ev_t1, h->compute));
+    SSDR_CUDA(cudaEventSynchronize(h->ev_t1));
+    SSDR_CUDA(cudaEventElapsedTime(total_ms, h->ev_t0, h->ev_t1));
+    return SSDR_OK;
+}
+
+// =============================================================================================
+// interpolator
+// =============================================================================================
+int ssdr_interp_create(ssdr_interp_t* out, int batch, int ratio, const double* taps, int n_taps, int max_samples) {
+    SSDR_ARG(out != nullptr, "null handle pointer");
+    *out = nullptr;
+    SSDR_ARG(batch >= 1 && ratio >= 1 && taps && max_samples >= 1, "bad argument");
+    SSDR_ARG(n_taps >= 1 && n_taps <= SSDR_INTERP_TAPS_MAX && (n_taps - 1) % ratio == 0,
+             "n_taps %d must be <= %d with (n_taps - 1) a multiple of the ratio %d", n_taps, SSDR_INTERP_TAPS_MAX, ratio);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    ssdr_interp* h = new ssdr_interp();
+    h->batch = batch; h->ratio = ratio; h->n_taps = n_taps; h->max_samples = max_samples; h->hs = (n_taps - 1) / ratio;
+    int rc;
+    auto fail = [&](int code) { ssdr_interp_destroy(h); return code; };
+    if ((rc = dev_alloc(&h->d_taps, (size_t)n_taps))) return fail(rc);
+    for (int i = 0; i < 2; ++i) if ((rc = dev_alloc(&h->d_hist[i], (size_t)batch * std::max(h->hs, 1)))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_vol, (size_t)batch))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_bal, (size_t)batch))) return fail(rc);
+    if (cudaMemcpy(h->d_taps, taps, sizeof(double) * (size_t)n_taps, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("tap upload failed"); return fail(SSDR_E_CUDA); }
+    if (cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(SSDR_E_CUDA); }
+    *out = h;
+    if ((rc = ssdr_interp_reset(h))) { *out = nullptr; return fail(rc); }
+    return SSDR_OK;
+}
+
+int ssdr_interp_destroy(ssdr_interp_t h) {
+    if (!h) return SSDR_OK;
+    if (h->compute) cudaStreamSynchronize(h->compute);
+    cudaFree(h->d_taps); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]); cudaFree(h->d_in); cudaFree(h->d_vol);
+    cudaFree(h->d_bal); cudaFree(h->d_out); cudaFree(h->d_mono);
+    if (h->compute) cudaStreamDestroy(h->compute);
+    delete h;
+    return SSDR_OK;
+}
+
+int ssdr_interp_reset(ssdr_interp_t h) {
+    SSDR_ARG(h != nullptr, "null handle");
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    for (int i = 0; i < 2; ++i) SSDR_CUDA(cudaMemset(h->d_hist[i], 0, sizeof(double) * (size_t)h->batch * std::max(h->hs, 1)));
+    return SSDR_OK;
+}
+
+int ssdr_interp_process_dev(ssdr_interp_t h, const int16_t* pcm_dev, int n, const float* volume_dev, const float* balance_dev,
+                            int16_t* stereo_dev, double* mono_dev) {
+    SSDR_ARG(h && pcm_dev && volume_dev && balance_dev && stereo_dev, "null argument");
+    SSDR_ARG(n >= h->hs, "n %d shorter than the filter history %d", n, h->hs);
+    InterpLaunch a;
+    a.kp.pcm = pcm_dev; a.kp.volume = volume_dev; a.kp.balance = balance_dev; a.kp.taps = h->d_taps;
+    a.kp.hist_in = h->d_hist[h->cur]; a.kp.hist_out = h->d_hist[h->cur ^ 1];
+    a.kp.stereo = stereo_dev; a.kp.mono = mono_dev; a.kp.n = n; a.kp.ratio = h->ratio; a.kp.n_taps = h->n_taps;
+    a.batch = h->batch;
+    int rc = interp_launch(a, h->compute);
+    if (rc) return rc;
+    h->cur ^= 1;
+    return SSDR_OK;
+}
+
+int ssdr_interp_process(ssdr_interp_t h, const int16_t* pcm_host, int n, const float* volume, const float* balance,
+                        int16_t* stereo_out, double* mono_f64) {
+    SSDR_ARG(h && pcm_host && volume && balance && stereo_out, "null argument");
+    SSDR_ARG(n >= 1 && n <= h->max_samples, "n %d outside 1..%d", n, h->max_samples);
+    const size_t cap = (size_t)h->batch * h->max_samples, tot = (size_t)h->batch * n;
+    int rc;
+    if (!h->d_in && (rc = dev_alloc(&h->d_in, cap))) return rc;
+    if (!h->d_out && (rc = dev_alloc(&h->d_out, cap * h->ratio * 2))) return rc;
+    if (mono_f64 && !h->d_mono && (rc = dev_alloc(&h->d_mono, cap * h->ratio))) return rc;
+    SSDR_CUDA(cudaMemcpyAsync(h->d_in, pcm_host, tot * sizeof(int16_t), cudaMemcpyHostToDevice, h->compute));
+    SSDR_CUDA(cudaMemcpyAsync(h->d_vol, volume, sizeof(float) * (size_t)h->batch, cudaMemcpyHostToDevice, h->compute));
+    SSDR_CUDA(cudaMemcpyAsync(h->d_bal, balance, sizeof(float) * (size_t)h->batch, cudaMemcpyHostToDevice, h->compute));
+    if ((rc = ssdr_interp_process_dev(h, h->d_in, n, h->d_vol, h->d_bal, h->d_out, mono_f64 ? h->d_mono : nullptr))) return rc;
+    SSDR_CUDA(cudaMemcpyAsync(stereo_out, h->d_out, tot * h->ratio * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost, h->compute));
+    if (mono_f64) SSDR_CUDA(cudaMemcpyAsync(mono_f64, h->d_mono, tot * h->ratio * sizeof(double), cudaMemcpyDeviceToHost, h->compute));
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    return SSDR_OK;
+}
+
+int ssdr_interp_sync(ssdr_interp_t h) {
+    SSDR_ARG(h != nullptr, "null handle");
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    return SSDR_OK;
+}
+
+int ssdr_fir_valid_f64(const double* x_host, size_t n, const double* taps, int n_taps, double* out_host) {
+    SSDR_ARG(x_host && taps && out_host && n_taps >= 1, "bad argument");
+    if (n < (size_t)n_taps) return SSDR_OK;
+    const size_t n_out = n - (size_t)n_taps + 1;
+    double *d_x = nullptr, *d_h = nullptr, *d_o = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&d_x, n)) || (rc = dev_alloc(&d_h, (size_t)n_taps)) || (rc = dev_alloc(&d_o, n_out))) {
+        cudaFree(d_x); cudaFree(d_h); cudaFree(d_o);
+        return rc;
+    }
+    cudaError_t e = cudaMemcpy(d_x, x_host, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_h, taps, (size_t)n_taps * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { rc = fir_valid_launch(d_x, d_h, n_taps, d_o, n_out, 0); if (!rc) e = cudaMemcpy(out_host, d_o, n_out * sizeof(double), cudaMemcpyDeviceToHost); }
+    cudaFree(d_x); cudaFree(d_h); cudaFree(d_o);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "fir_valid copy", __FILE__, __LINE__);
+    return SSDR_OK;
+}
+
+// =============================================================================================
+// IQ unpack
+// =============================================================================================
+int ssdr_unpack_iq_s16be_dev(const void* s16be_dev, float* cf32_dev, size_t n_complex) {
+    SSDR_ARG(s16be_dev && cf32_dev, "null argument");
+    int rc = unpack_launch(s16be_dev, cf32_dev, n_complex, 0);
+    if (rc) return rc;
+    SSDR_CUDA(cudaStreamSynchronize(0));
+    return SSDR_OK;
+}
+
+int ssdr_unpack_iq_s16be(const void* s16be_host, float* cf32_host, size_t n_complex) {
+    SSDR_ARG(s16be_host && cf32_host, "null argument");
+    if (n_complex == 0) return SSDR_OK;
+    unsigned char* d_in = nullptr;
+    float* d_out = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&d_in, n_complex * 4))) return rc;
+    if ((rc = dev_alloc(&d_out, n_complex * 2))) { cudaFree(d_in); return rc; }
+    cudaError_t e = cudaMemcpy(d_in, s16be_host, n_complex * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { rc = unpack_launch(d_in, d_out, n_complex, 0); if (!rc) e = cudaMemcpy(cf32_host, d_out, n_complex * 8, cudaMemcpyDeviceToHost); }
+    cudaFree(d_in); cudaFree(d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "unpack copy", __FILE__, __LINE__);
+    return SSDR_OK;
+}
+
+}  // extern "C"

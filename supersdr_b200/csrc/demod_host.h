@@ -1,0 +1,64 @@
+// Device-visible per-channel demodulator structures and the launch descriptor.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/ssdr_b200.h"
+
+namespace ssdr {
+
+constexpr float kDemodFsDbm = -10.0f;     // an IQ tone of amplitude FS reads -10 dBm
+constexpr float kDemodAgcOut = 0.5f;      // AGC_OUT
+constexpr double kDemodAmBeta = 1.0 / (12000.0 * 0.1);   // AM carrier tracker, tau = 0.1 s
+
+// derived per-channel constants (computed on the host from ssdr_demod_params_t)
+struct DemodChan {
+    int mode;
+    int agc_on, agc_hang;
+    unsigned inc1, inc2;      // 32-bit phase increments: (f_off + fc)/fs, fc/fs
+    float c2;                 // log2(e) / (fs * decay_s): envelope decay exponent per sample
+    float knee2;              // (thresh - FS_DBM)/20 * log2(10)
+    float slope_m1;           // slope/100 - 1
+    float man_gain;           // 10^(manGain/20)
+};
+
+struct DemodState {
+    unsigned ph1, ph2;
+    float e_in;
+    float zprev_re, zprev_im;
+    unsigned blk;
+    float ring[SSDR_HANG_BLOCKS];
+    double dc;
+};
+
+struct DemodKernelParams {
+    const void* iq;
+    const DemodChan* chan;
+    DemodState* state;
+    float2* hist;             // [batch][126] mixed samples
+    const float* taps;        // [batch][127]
+    float* pcm_f32;
+    int16_t* pcm_i16;
+    float* rssi;
+    int batch, n_samples;
+    double am_pow16[5];       // ((1-beta)^16)^(2^s)
+};
+
+struct DemodLaunch {
+    const void* iq = nullptr;
+    int iq_format = SSDR_IQ_CF32;
+    const DemodChan* chan = nullptr;
+    DemodState* state = nullptr;
+    float2* hist = nullptr;
+    const float* taps = nullptr;
+    float* pcm_f32 = nullptr;
+    int16_t* pcm_i16 = nullptr;
+    float* rssi = nullptr;
+    int batch = 0, n_samples = 0;
+    double am_pow16[5] = {0, 0, 0, 0, 0};
+};
+
+int demod_launch(const DemodLaunch& a, cudaStream_t st);
+
+}  // namespace ssdr

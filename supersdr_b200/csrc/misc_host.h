@@ -1,0 +1,34 @@
+// Launch descriptors of the small kernels (interpolator, unpack, synthetic IQ).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/ssdr_b200.h"
+
+namespace ssdr {
+
+struct InterpKernelParams {
+    const int16_t* pcm;       // [batch][n]
+    const float* volume;      // [batch] percent (kiwi_sound.volume)
+    const float* balance;     // [batch] (kiwi_sound.audio_balance)
+    const double* taps;       // [n_taps]
+    const double* hist_in;    // [batch][(n_taps-1)/ratio] scaled samples carried from the last call
+    double* hist_out;         // new history (a different buffer than hist_in)
+    int16_t* stereo;          // [batch][ratio*n][2]
+    double* mono;             // optional [batch][ratio*n]
+    int n, ratio, n_taps;
+};
+
+struct InterpLaunch {
+    InterpKernelParams kp;
+    int batch;
+};
+
+int interp_launch(const InterpLaunch& a, cudaStream_t st);
+int fir_valid_launch(const double* x, const double* h, int T, double* out, size_t n_out, cudaStream_t st);
+int unpack_launch(const void* in, float* out, size_t n, cudaStream_t st);
+int synth_launch(void* out, int fmt, int batch, int frames, int nfft, unsigned seed, cudaStream_t st);
+
+}  // namespace ssdr

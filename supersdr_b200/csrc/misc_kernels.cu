@@ -1,0 +1,169 @@
+// Small kernels: the Tier-P audio interpolator (K5), the IQ wire-format unpack (K6) and the
+// synthetic IQ generator used by the bench and the full-size tests.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "common.cuh"
+#include "misc_host.h"
+
+namespace ssdr {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// K5: kiwi_sound.play_buffer integer-ratio path, utils_supersdr.py:1121-1138, in polyphase form.
+//   z = concat(hist, zero-stuffed x * (volume/100)); out[j] = ratio * sum_t h[t] z[j + H - t]
+// Only taps with (j - t) % ratio == 0 meet non-zero samples, so output j = ratio*k + ph reads
+// xs[k + HS - i] * h[ph + ratio*i] (HS = H / ratio scaled history samples).  float64, separate
+// multiply and add in ascending tap order (oracle/c/ssdr_oracle.c so_play_buffer).
+// ---------------------------------------------------------------------------------------------
+constexpr int IT = 256;   // input samples per CTA tile
+
+__global__ void __launch_bounds__(IT)
+interp_kernel(const InterpKernelParams kp) {
+    __shared__ double xs[IT + SSDR_INTERP_TAPS_MAX];
+    __shared__ double hs[SSDR_INTERP_TAPS_MAX + 1];
+    const int ch = blockIdx.y;
+    const int k0 = blockIdx.x * IT;
+    const int HS = (kp.n_taps - 1) / kp.ratio;
+    const double scale = (double)kp.volume[ch] / 100.0;
+    const int16_t* x = kp.pcm + (size_t)ch * kp.n;
+    for (int i = threadIdx.x; i < IT + HS; i += IT) {
+        const int k = k0 - HS + i;            // input index, negative = history
+        double v = 0.0;
+        if (k < 0) { if (HS + k >= 0) v = kp.hist_in[(size_t)ch * HS + (HS + k)]; }
+        else if (k < kp.n) v = (double)x[k] * scale;
+        xs[i] = v;
+    }
+    for (int i = threadIdx.x; i < kp.n_taps; i += IT) hs[i] = kp.taps[i];
+    __syncthreads();
+    const int k = k0 + threadIdx.x;
+    if (k >= kp.n) return;
+    const double bal = (double)kp.balance[ch];
+    double lv = fmin(1.0 - bal, 1.0), rv = fmin(1.0 + bal, 1.0);
+    lv = lv * lv; rv = rv * rv;
+    // new history = the last HS scaled input samples of this call
+    if (k >= kp.n - HS) kp.hist_out[(size_t)ch * HS + (k - (kp.n - HS))] = xs[threadIdx.x + HS];
+    for (int ph = 0; ph < kp.ratio; ++ph) {
+        double acc = 0.0;
+        for (int i = 0; ph + kp.ratio * i < kp.n_taps; ++i) {
+            double p = __dmul_rn(hs[ph + kp.ratio * i], xs[threadIdx.x + HS - i]);
+            acc = __dadd_rn(acc, p);
+        }
+        acc = __dmul_rn(acc, (double)kp.ratio);
+        const size_t j = (size_t)ch * kp.n * kp.ratio + (size_t)k * kp.ratio + ph;
+        if (kp.mono) kp.mono[j] = acc;
+        // numpy astype(int16): C truncation toward zero, then wrap to 16 bits
+        const int l = __double2int_rz(__dmul_rn(acc, lv)), r = __double2int_rz(__dmul_rn(acc, rv));
+        reinterpret_cast<unsigned*>(kp.stereo)[j] = ((unsigned)l & 0xffffu) | ((unsigned)r << 16);
+    }
+}
+
+// filtering.lowpass, utils_supersdr.py:346-348: out[j] = sum_t h[t] x[j + T - 1 - t]  ("valid")
+__global__ void fir_valid_kernel(const double* __restrict__ x, const double* __restrict__ h, int T, double* __restrict__ out, size_t n_out) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (size_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int t = 0; t < T; ++t) acc = __dadd_rn(acc, __dmul_rn(h[t], x[j + (size_t)(T - 1 - t)]));
+        out[j] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: kiwi/client.py:449-453 -- big-endian int16 I,Q -> complex64 (unscaled counts)
+// ---------------------------------------------------------------------------------------------
+__global__ void unpack_kernel(const unsigned* __restrict__ in, float2* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned v = __ldcs(in + i);
+        const unsigned sw = __byte_perm(v, 0u, 0x2301);
+        const int a = (int)(short)(sw & 0xffffu), b = (int)sw >> 16;
+        __stcs(out + i, make_float2((float)a, (float)b));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic IQ in HBM: 3 tones + noise per channel, hash-based, deterministic
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+template <int FMT>
+__global__ void synth_kernel(void* out, int batch, int frames, int nfft, unsigned seed) {
+    const size_t per_ch = (size_t)frames * nfft;
+    const size_t total = (size_t)batch * per_ch;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned ch = (unsigned)(i / per_ch);
+        const unsigned n = (unsigned)(i - (size_t)ch * per_ch);
+        float re = 0.f, im = 0.f;
+        const float amp[3] = {0.5f, 0.05f, 0.005f};
+#pragma unroll
+        for (int tn = 0; tn < 3; ++tn) {
+            unsigned hb = mix32(seed * 0x9e3779b9u + ch * 3u + tn);
+            // frequency in cycles/sample with 1/2^20 resolution; phase exact in 32-bit arithmetic
+            unsigned fcw = hb & 0xfffff000u;
+            unsigned ph = fcw * n + mix32(hb);
+            float s, c;
+            sincospif((float)(int)ph * 4.656612873077393e-10f, &s, &c);
+            re += amp[tn] * c; im += amp[tn] * s;
+        }
+        unsigned r0 = mix32((unsigned)i * 2u + 0x1234567u + seed), r1 = mix32((unsigned)i * 2u + 1u + seed * 77u);
+        // sum of four 8-bit uniforms per component: ~Gaussian, std = 147.8 counts/2^8... scaled below
+        float nr = (float)((r0 & 255) + ((r0 >> 8) & 255) + ((r0 >> 16) & 255) + (r0 >> 24)) - 510.0f;
+        float ni = (float)((r1 & 255) + ((r1 >> 8) & 255) + ((r1 >> 16) & 255) + (r1 >> 24)) - 510.0f;
+        const float ns = 1e-3f * 0.70710678f / 147.8f;       // sigma 1e-3 FS (complex)
+        re = (re + nr * ns) * SSDR_FS; im = (im + ni * ns) * SSDR_FS;
+        if constexpr (FMT == SSDR_IQ_CF32) {
+            reinterpret_cast<float2*>(out)[i] = make_float2(re, im);
+        } else {
+            int a = max(-32768, min(32767, __float2int_rn(re))), b = max(-32768, min(32767, __float2int_rn(im)));
+            unsigned ua = (unsigned)a & 0xffffu, ub = (unsigned)b & 0xffffu;
+            // big-endian pairs: bytes I_hi I_lo Q_hi Q_lo
+            reinterpret_cast<unsigned*>(out)[i] = (ua >> 8) | ((ua & 0xff) << 8) | ((ub >> 8) << 16) | ((ub & 0xff) << 24);
+        }
+    }
+}
+
+}  // namespace
+
+int interp_launch(const InterpLaunch& a, cudaStream_t st) {
+    dim3 grid((a.kp.n + IT - 1) / IT, a.batch);
+    interp_kernel<<<grid, IT, 0, st>>>(a.kp);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+int fir_valid_launch(const double* x, const double* h, int T, double* out, size_t n_out, cudaStream_t st) {
+    if (n_out == 0) return SSDR_OK;
+    size_t blocks = (n_out + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    fir_valid_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, h, T, out, n_out);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+int unpack_launch(const void* in, float* out, size_t n, cudaStream_t st) {
+    if (n == 0) return SSDR_OK;
+    size_t blocks = (n + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    unpack_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const unsigned*>(in), reinterpret_cast<float2*>(out), n);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+int synth_launch(void* out, int fmt, int batch, int frames, int nfft, unsigned seed, cudaStream_t st) {
+    const int blocks = sm_count() * 8;
+    if (fmt == SSDR_IQ_CF32) synth_kernel<SSDR_IQ_CF32><<<blocks, 256, 0, st>>>(out, batch, frames, nfft, seed);
+    else synth_kernel<SSDR_IQ_S16BE><<<blocks, 256, 0, st>>>(out, batch, frames, nfft, seed);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+}  // namespace ssdr

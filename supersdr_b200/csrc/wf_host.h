@@ -1,0 +1,34 @@
+// Host-visible launch descriptors shared between capi.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/ssdr_b200.h"
+
+namespace ssdr {
+
+struct WfLaunch {
+    const void* iq = nullptr;          // device, [batch][n_avg][nfft]
+    int iq_format = SSDR_IQ_CF32;
+    const uint8_t* lines = nullptr;    // device, colorrow entry (iq ignored)
+    const float* wtab = nullptr;       // device, 2*nfft floats
+    const float* thr = nullptr;        // device, 257 floats
+    ssdr_wf_display_t* disp = nullptr; // device, [batch]
+    uint8_t* pixels = nullptr;
+    float* colour = nullptr;
+    float* spectrum = nullptr;
+    ssdr_wf_scalars_t* scalars = nullptr;
+    int nfft = 0, batch = 0, n_avg = 1, window = 1;
+    int p_lo = 0;
+    float p_gamma = 0.f;
+    float est_c1 = 0.f, est_c0 = 0.f;
+};
+
+int wf_plan(int nfft, int* radices);
+int wf_launch(const WfLaunch& a, cudaStream_t st);
+
+struct DemodLaunch;
+struct InterpLaunch;
+
+}  // namespace ssdr
