@@ -1,0 +1,142 @@
+"""GPU parity tests (through the C ABI) for the demodulator (Tier U, 1e-5 RMS vs the float64
+oracle) and the audio interpolator (Tier P, against fixtures from the unmodified reference)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tier_p, tier_u
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RMS_TOL = 1e-5          # north_star: float32 demod output within 1e-5 RMS of the numpy path
+
+
+def _rel_rms(a, b):
+    return np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-30)
+
+
+@pytest.mark.parametrize("mode", ["usb", "lsb", "cw", "am", "nbfm"])
+@pytest.mark.parametrize("hang,on,slope", [(False, True, 0), (True, True, 6), (False, False, 0)])
+def test_demod_vs_float64_oracle(ssdr, mode, hang, on, slope):
+    B, n = 6, 512 * 12
+    kw = dict(mode=mode, hang=hang, on=on, slope=slope, decay=1000 if mode == "cw" else 4000)
+    bank = ssdr.DemodBank(B, n)
+    bank.set_all(**kw)
+    iq = np.stack([tier_u.synth_demod_iq(mode, n, seed=10 + b, level=0.1 / (b + 1)) for b in range(B)])
+    r1 = bank.process(iq[:, : n // 2].copy())          # streamed in two calls: state carries over
+    r2 = bank.process(iq[:, n // 2:].copy())
+    got = np.concatenate([r1["pcm_f32"], r2["pcm_f32"]], 1)
+    gi = np.concatenate([r1["pcm_i16"], r2["pcm_i16"]], 1)
+    rssi = np.concatenate([r1["rssi"], r2["rssi"]], 1)
+    for b in range(B):
+        ref, rr = tier_u.demod(iq[b], tier_u.DemodParams(**kw), tier_u.DemodState())
+        assert _rel_rms(got[b], ref) < RMS_TOL
+        assert np.abs(gi[b].astype(int) - tier_u.pcm_to_i16(ref).astype(int)).max() <= 1
+        assert np.abs(rssi[b] - rr).max() < 1e-3
+    bank.close()
+
+
+def test_demod_golden_fixture(ssdr):
+    g = np.load(os.path.join(GOLD, "tier_u_demod.npz"))
+    for mode in tier_u.MODES:
+        bank = ssdr.DemodBank(1, 4096)
+        bank.set_all(mode=mode, decay=1000 if mode == "cw" else 4000, hang=(mode == "cw"))
+        got = bank.process(g["iq_" + mode][None])
+        assert _rel_rms(got["pcm_f32"][0], g["pcm_" + mode].astype(np.float64)) < RMS_TOL
+        assert np.abs(got["rssi"][0] - g["rssi_" + mode]).max() < 1e-3
+        bank.close()
+
+
+def test_demod_mixed_modes_and_chunking(ssdr):
+    """Config 4 in miniature: modes by ch % 5, per-channel tuning offsets; and the result does not
+    depend on how the stream is cut into calls (per-frame state is bit-reproducible)."""
+    modes = ["am", "lsb", "usb", "cw", "nbfm"]
+    B, n = 25, 512 * 8
+    params = [ssdr.demod_params(modes[b % 5], f_off=100.0 * (b % 3), thresh=-80 - b, decay=400 + 300 * b) for b in range(B)]
+    iq = np.stack([tier_u.synth_demod_iq(modes[b % 5], n, seed=b) for b in range(B)])
+    one = ssdr.DemodBank(B, n)
+    one.set_params(0, params)
+    whole = one.process(iq)
+    cut = ssdr.DemodBank(B, n)
+    cut.set_params(0, params)
+    parts = [cut.process(iq[:, i:i + 512 * k].copy()) for i, k in ((0, 1), (512, 3), (2048, 4))]
+    assert np.array_equal(np.concatenate([p["pcm_f32"] for p in parts], 1), whole["pcm_f32"])
+    assert np.array_equal(np.concatenate([p["pcm_i16"] for p in parts], 1), whole["pcm_i16"])
+    for b in range(B):
+        p = tier_u.DemodParams(modes[b % 5], f_off=100.0 * (b % 3), thresh=-80 - b, decay=400 + 300 * b)
+        ref, _ = tier_u.demod(iq[b], p, tier_u.DemodState())
+        assert _rel_rms(whole["pcm_f32"][b], ref) < RMS_TOL, b
+    one.close(); cut.close()
+
+
+def test_demod_wire_format_and_sideband_rejection(ssdr):
+    n = 512 * 16
+    iq = tier_u.synth_demod_iq("usb", n, seed=4)
+    iq = (np.rint(iq.real) + 1j * np.rint(iq.imag)).astype(np.complex64)
+    wire = np.ascontiguousarray(np.stack([iq.real, iq.imag], -1).astype(">i2")).view(np.uint8).reshape(1, n, 4)
+    bank = ssdr.DemodBank(1, n)
+    a = bank.process(iq[None])["pcm_f32"][0]
+    bank.reset()
+    b = bank.process(wire)["pcm_f32"][0]
+    assert np.array_equal(a, b)
+    F = np.abs(np.fft.rfft(a[-4096:] * np.hanning(4096)))
+    f = np.fft.rfftfreq(4096, 1 / 12000)
+    assert abs(f[F.argmax()] - 1000) < 5             # +1 kHz tone demodulated, -1 kHz image rejected:
+    bank.set_all(mode="lsb"); bank.reset()
+    l = bank.process(iq[None])["pcm_f32"][0]
+    assert np.sqrt(np.mean(l[-4096:] ** 2)) > 0.5 * np.sqrt(np.mean(a[-4096:] ** 2))   # LSB hears the -1 kHz tone
+    bank.close()
+
+
+def test_demod_silence_and_full_scale(ssdr):
+    bank = ssdr.DemodBank(2, 1024)
+    x = np.zeros((2, 1024), np.complex64)
+    x[1] = 32767 * np.exp(2j * np.pi * 1000 * np.arange(1024) / 12000)
+    r = bank.process(x)
+    assert np.all(r["pcm_f32"][0] == 0) and np.all(r["pcm_i16"][0] == 0) and np.all(np.isfinite(r["rssi"]))
+    ref, rr = tier_u.demod(x[1], tier_u.DemodParams("usb"), tier_u.DemodState())
+    assert _rel_rms(r["pcm_f32"][1], ref) < RMS_TOL and abs(r["rssi"][1, -1] - rr[-1]) < 1e-3
+    with pytest.raises(ssdr.SsdrError):
+        bank.process(np.zeros((2, 500), np.complex64))       # not a multiple of 512
+    bank.close()
+
+
+def test_interp_reference_golden(ssdr):
+    """kiwi_sound.play_buffer (utils_supersdr.py:1121-1138) fixtures from the unmodified reference:
+    int16 stereo within 1 LSB (np.convolve's summation order is BLAS-dependent)."""
+    g = np.load(os.path.join(GOLD, "tier_p_audio.npz"))
+    ib = ssdr.InterpBank(1, 4, taps=g["h"], max_samples=512)
+    st = tier_p.InterpState()
+    exact = 0
+    for k in range(g["x"].shape[0]):
+        out, mono = ib.process(g["x"][k][None], float(g["volume"][k]), float(g["balance"][k]), want_mono=True)
+        d = np.abs(out[0].astype(int) - g["out"][k].astype(int))
+        # the int16 wrap of numpy's astype is reproduced (block 3 is full-scale DC at volume 150)
+        assert (np.minimum(d, 65536 - d)).max() <= 1
+        exact += int(d.max() == 0)
+        buf, _ = tier_p.play_buffer(g["x"][k], st, int(g["volume"][k]), float(g["balance"][k]))
+        assert _rel_rms(mono[0], buf) < RMS_TOL or np.abs(buf).max() == 0
+    assert exact >= 8
+    ib.close()
+
+
+def test_interp_batched_streaming(ssdr):
+    rng = np.random.default_rng(1)
+    B, n = 9, 512
+    ib = ssdr.InterpBank(B, 4, max_samples=2 * n)
+    sts = [tier_p.InterpState() for _ in range(B)]
+    for it in range(5):
+        nn = n if it % 2 == 0 else 2 * n
+        x = rng.integers(-32768, 32768, (B, nn)).astype(np.int16)
+        vol = rng.integers(0, 16, B) * 10.0
+        bal = np.round(rng.uniform(-1, 1, B), 2).astype(np.float32)
+        out = ib.process(x, vol, bal)
+        for b in range(B):
+            _, o2 = tier_p.play_buffer(x[b], sts[b], float(vol[b]), float(bal[b]))
+            d = np.abs(out[b].astype(int) - o2.astype(int))
+            assert np.minimum(d, 65536 - d).max() <= 1
+    ib.close()
+    f = ssdr.filtering(6000, 48000)
+    x = rng.standard_normal(5000)
+    assert np.abs(f.lowpass(x) - np.convolve(x, f.h, "valid")).max() < 1e-12

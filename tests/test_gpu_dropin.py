@@ -1,0 +1,90 @@
+"""GPU: the drop-in classes keep the reference's call surface and produce what the
+reference pipeline would produce from the same server-side lines / PCM."""
+import types
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, tier_p, tier_u
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeKiwi:
+    """Headless IQ source standing in for the W/F and SND websockets."""
+
+    def __init__(self, wf_frames, snd_frames):
+        self.wf, self.snd = list(wf_frames), list(snd_frames)
+        self.keepalives = 0
+
+    def read_wf_frame(self):
+        return self.wf.pop(0) if self.wf else None
+
+    def read_snd_frame(self):
+        return (self.snd.pop(0), 0) if self.snd else None
+
+    def keepalive(self):
+        self.keepalives += 1
+
+
+def test_kiwi_waterfall_dropin(ssdr):
+    disp = types.SimpleNamespace(DISPLAY_WIDTH=1024, WF_HEIGHT=40)
+    frames = tier_u.synth_iq(1024, seed=9, frames=24)
+    src = FakeKiwi(frames, [])
+    wf = ssdr.kiwi_waterfall("fake", 8073, "", 3, 7100, None, disp, iq_source=src)
+    assert wf.WF_BINS == 1024 and wf.wf_data.shape == (40, 1024) and wf.span_khz == 30000 / 8
+    wf.averaging_n = 4
+    st = tier_p.ColourState()
+    st.zoom = 3
+    rows = []
+    for it in range(6):
+        assert wf.run_once()
+        lines = np.stack([c_oracle.wf_frame_bytes(frames[it * 4 + k]) for k in range(4)])
+        spec, col, px = tier_p.waterfall_line(lines, st)       # what the reference would compute from those lines
+        assert np.array_equal(wf.spectrum, spec) and np.array_equal(wf.wf_color, col)
+        assert np.float32(wf.wf_min_db) == st.wf_min_db and np.float32(wf.wf_max_db) == st.wf_max_db
+        rows.append(col)
+    # scroll buffer semantics utils:893-897: 3-line delay, newest on top
+    assert np.array_equal(wf.wf_data[0], rows[2].astype(np.float64)) and np.array_equal(wf.wf_data[2], rows[0])
+    assert src.keepalives == 24
+    assert not wf.run_once() and wf.terminate            # stream ended
+    assert wf.change_passband(10, -20) == (40, 2980)     # USB defaults utils:859-862
+    assert wf.set_freq_zoom(14200, 5) == 14200 and wf.span_khz == 30000 / 32
+    assert abs(wf.bins_to_khz(512) - 14200) < 1e-9
+
+
+def test_kiwi_sound_dropin(ssdr):
+    n_frames = 10
+    iq = tier_u.synth_demod_iq("usb", 512 * n_frames, seed=2)
+    src = FakeKiwi([], [iq[i * 512:(i + 1) * 512] for i in range(n_frames)])
+    wf = types.SimpleNamespace(host="fake", port=8073, terminate=False, kiwi_wf_timestamp=0)
+    snd = ssdr.kiwi_sound(7100, "USB", 30, 3000, "", wf, 4, iq_source=src)
+    assert snd.SAMPLE_RATIO == 4 and snd.n_tap == 33 and snd.KIWI_SAMPLES_PER_FRAME == 512
+    ref, rssi = tier_u.demod(iq, tier_u.DemodParams("usb", 30, 3000), tier_u.DemodState())
+    st = tier_p.InterpState()
+    snd.volume, snd.audio_balance = 80, 0.25
+    for k in range(n_frames):
+        pcm = snd.process_audio_stream()
+        assert pcm.dtype == np.int16 and pcm.shape == (512,)
+        assert np.abs(pcm.astype(int) - tier_u.pcm_to_i16(ref[k * 512:(k + 1) * 512]).astype(int)).max() <= 1
+        assert abs(snd.rssi - rssi[k]) < 1e-3
+        snd.audio_buffer.put(pcm)
+        out = np.zeros((2048, 2), np.int16)
+        snd.play_buffer(out, 2048, None, None)
+        _, o2 = tier_p.play_buffer(pcm, st, 80, 0.25)
+        assert np.abs(out.astype(int) - o2.astype(int)).max() <= 1
+    with pytest.raises(EOFError):
+        snd.process_audio_stream()
+    assert snd.terminate and wf.terminate
+    snd.radio_mode = "CW"
+    assert snd.change_passband(0, 0) == (400, 800)
+    snd.set_mode_freq_pb()
+    assert snd.decay == 1000                                   # decay_cw, utils_supersdr.py:1027
+    snd.change_agc_delay(100)
+    assert snd.decay == 1100 and snd.decay_cw == 1100
+    # TX mute, utils_supersdr.py:1141-1147
+    snd.rssi = -10
+    snd.audio_buffer.put(np.full(512, 1000, np.int16))
+    out = np.ones((2048, 2), np.int16)
+    snd.play_buffer(out, 2048, None, None)
+    assert snd.mute_counter == 15 and not out.any()
