@@ -152,7 +152,12 @@ def demod_taps(lc, hc, fs=KIWI_RATE, T=FIR_TAPS):
     unity DC gain -- the recipe of ``filtering`` (utils_supersdr.py:333-344) at a fixed length."""
     fl = (hc - lc) / 2.0
     h = np.sinc(2.0 * fl / fs * (np.arange(T) - (T - 1) / 2.0)) * np.blackman(T)
-    return h / np.sum(h)
+    h = h / np.sum(h)
+    # DESIGN.md 4.5: the Blackman window is exactly 0 at both ends (0.42 - 0.5 + 0.08); float64
+    # leaves +-1.4e-17 there, which would make the first output sample of a stream pure rounding
+    # noise (and its NBFM phase arbitrary).  The spec pins the two end taps to exactly 0.
+    h[0] = h[-1] = 0.0
+    return h
 
 
 def phase_inc(f_hz, fs=KIWI_RATE):

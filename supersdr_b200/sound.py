@@ -53,7 +53,9 @@ def demod_params(mode="usb", lc=None, hc=None, f_off=0.0, on=True, hang=False, t
     p.low_cut_hz, p.high_cut_hz, p.freq_offset_hz = float(lc), float(hc), float(f_off)
     p.agc_on, p.agc_hang = int(bool(on)), int(bool(hang))
     p.agc_thresh_dbm, p.agc_slope_db, p.agc_decay_ms, p.agc_man_gain_db = float(thresh), float(slope), float(decay), float(gain)
-    taps = design_lowpass((hc - lc) / 2.0, _lib.KIWI_RATE, _lib.FIR_TAPS).astype(np.float32)
+    taps = design_lowpass((hc - lc) / 2.0, _lib.KIWI_RATE, _lib.FIR_TAPS)
+    taps[0] = taps[-1] = 0.0      # Blackman end points are exactly zero, not +-1e-17
+    taps = taps.astype(np.float32)
     for i in range(_lib.FIR_TAPS):
         p.taps[i] = float(taps[i])
     return p
