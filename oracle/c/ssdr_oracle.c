@@ -33,12 +33,13 @@ static const float K_A = 0.92387953251128674f;   /* cos(pi/8)  */
 static const float K_B = 0.70710678118654752f;   /* sqrt(1/2)  */
 static const float K_C = 0.38268343236508977f;   /* sin(pi/8)  */
 
-/* cos(2*pi*m/16), sin(2*pi*m/16) built from {1, A, B, C, 0} by symmetry (exact negations) */
-static void unit16(int m, float* c, float* s) {
-    static const float q[5] = {1.0f, 0.92387953251128674f, 0.70710678118654752f,
-                               0.38268343236508977f, 0.0f};
-    int mm = m & 15, quad = mm >> 2, r = mm & 3;
-    float cr = q[r], sr = q[4 - r];
+/* cos(2*pi*m/32), sin(2*pi*m/32) built from the first-octant values by symmetry (exact negations) */
+static const float K_Q32[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                               0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f,
+                               0.19509032201612825f, 0.0f};
+static void unit32(int m, float* c, float* s) {
+    int mm = m & 31, quad = mm >> 3, r = mm & 7;
+    float cr = K_Q32[r], sr = K_Q32[8 - r];
     switch (quad) {
     case 0: *c = cr;  *s = sr;  break;
     case 1: *c = -sr; *s = cr;  break;
@@ -51,13 +52,13 @@ static void unit16(int m, float* c, float* s) {
 int so_fft_plan(int N, int* radices) {
     int lg = 0;
     while ((1 << lg) < N) lg++;
-    if ((1 << lg) != N || lg < 4 || lg > 16) return -1;
-    int np = 0, rem = lg;
-    while (rem >= 4 + 2 || rem == 4) { radices[np++] = 16; rem -= 4; }   /* leave 2,3,5 -> below */
-    if (rem == 5) { radices[np++] = 8; radices[np++] = 4; }
-    else if (rem == 3) radices[np++] = 8;
-    else if (rem == 2) radices[np++] = 4;
-    else if (rem == 1) return -1;
+    if ((1 << lg) != N || lg < 6 || lg > 16) return -1;
+    /* lg = r + 5k: one first pass of radix 2^r (r = 1..4; a radix-32 pass when r == 0) that reads
+     * the input and applies the window, followed by k radix-32 passes. */
+    int np = 0, k = lg / 5, r = lg - 5 * k;
+    if (r == 0) { r = 5; k -= 1; }
+    radices[np++] = 1 << r;
+    for (int i = 0; i < k; ++i) radices[np++] = 32;
     return np;
 }
 
@@ -136,24 +137,46 @@ static void dft16(cpx* x) {
     }
 }
 
-/* twiddle powers w[1..r-1] from w[1] by the fixed minimum-depth chain */
-static void tw_chain(cpx* w, int r) {
-    w[2] = cmul(w[1], w[1]);
-    w[3] = cmul(w[2], w[1]);
-    if (r <= 4) return;
-    w[4] = cmul(w[2], w[2]);
-    w[5] = cmul(w[4], w[1]);
-    w[6] = cmul(w[3], w[3]);
-    w[7] = cmul(w[4], w[3]);
-    if (r <= 8) return;
-    w[8] = cmul(w[4], w[4]);
-    w[9] = cmul(w[8], w[1]);
-    w[10] = cmul(w[5], w[5]);
-    w[11] = cmul(w[8], w[3]);
-    w[12] = cmul(w[6], w[6]);
-    w[13] = cmul(w[8], w[5]);
-    w[14] = cmul(w[7], w[7]);
-    w[15] = cmul(w[8], w[7]);
+/* 32 = 4 x 8: radix-4 across m1 (m = m0 + 8 m1), twiddle W32^(m0 p), radix-8 across m0; q = p + 4 s.
+ * W32^e = (cos, -sin)(2 pi e / 32) from the unit32 constants; e == 8 is the exact rotation by -i. */
+static void dft32(cpx* x) {
+    cpx u[4][8];   /* u[p][m0] */
+    for (int m0 = 0; m0 < 8; ++m0) {
+        cpx t[4] = {x[m0], x[m0 + 8], x[m0 + 16], x[m0 + 24]};
+        dft4(t);
+        for (int p = 0; p < 4; ++p) u[p][m0] = t[p];
+    }
+    for (int p = 1; p < 4; ++p)
+        for (int m0 = 1; m0 < 8; ++m0) {
+            int e = m0 * p;
+            if (e == 8) { u[p][m0] = mul_mi(u[p][m0]); continue; }
+            float c, s;
+            unit32(e, &c, &s);
+            cpx w = {c, -s};
+            u[p][m0] = cmul(u[p][m0], w);
+        }
+    for (int p = 0; p < 4; ++p) {
+        dft8(u[p]);
+        for (int s = 0; s < 8; ++s) x[p + 4 * s] = u[p][s];
+    }
+}
+
+/* Twiddles of a "chain" pass: output q = 4a + b of a radix-r butterfly is multiplied
+ * by W^(j q) as (x * A[a]) * B[b] with B[1] = w1 = W^j, B[2] = w1*w1, B[3] = B[2]*w1, A[1] = B[2]*B[2],
+ * A[2] = A[1]*A[1], A[3] = A[2]*A[1] -- six live twiddles instead of r - 1. */
+static void tw_two_level(cpx* x, int r, cpx w1) {
+    cpx B[4], A[4];
+    B[1] = w1;
+    if (r == 2) { x[1] = cmul(x[1], B[1]); return; }
+    B[2] = cmul(w1, w1);
+    B[3] = cmul(B[2], w1);
+    if (r > 4) A[1] = cmul(B[2], B[2]);
+    if (r > 8) { A[2] = cmul(A[1], A[1]); A[3] = cmul(A[2], A[1]); }
+    for (int q = 1; q < r; ++q) {
+        int a = q >> 2, b = q & 3;
+        if (a) x[q] = cmul(x[q], A[a]);
+        if (b) x[q] = cmul(x[q], B[b]);
+    }
 }
 
 #define SO_TABLE_PASS_MAX 1024   /* a pass uses exact table twiddles iff (L/r)*(r-1) <= this */
@@ -166,21 +189,22 @@ static void fft_dif(cpx* d, int N, const int* radices, int np, const float* tab)
         int use_table = (M * (r - 1) <= SO_TABLE_PASS_MAX);
         for (int base = 0; base < N; base += L) {
             for (int j = 0; j < M; ++j) {
-                cpx x[16], w[16];
+                cpx x[32], w[32];
                 for (int m = 0; m < r; ++m) x[m] = d[base + j + m * M];
-                if (r == 16) dft16(x); else if (r == 8) dft8(x); else if (r == 4) dft4(x); else dft2(x);
+                if (r == 32) dft32(x); else if (r == 16) dft16(x); else if (r == 8) dft8(x); else if (r == 4) dft4(x); else dft2(x);
                 if (M > 1) {
                     if (use_table) {
                         for (int q = 1; q < r; ++q) {
                             int k = j * q * step;
                             w[q].re = tab[2 * k]; w[q].im = tab[2 * k + 1];
                         }
+                        for (int q = 1; q < r; ++q) x[q] = cmul(x[q], w[q]);
                     } else {
                         int k = j * step;
-                        w[1].re = tab[2 * k]; w[1].im = tab[2 * k + 1];
-                        if (r > 2) tw_chain(w, r);
+                        cpx w1 = {tab[2 * k], tab[2 * k + 1]};
+                        if (r > 16) return;                       /* the plan keeps radix-32 passes on tables */
+                        tw_two_level(x, r, w1);
                     }
-                    for (int q = 1; q < r; ++q) x[q] = cmul(x[q], w[q]);
                 }
                 for (int q = 0; q < r; ++q) d[base + j + q * M] = x[q];
             }
@@ -210,14 +234,14 @@ static inline uint8_t quantise(float P, const float* T) {
 }
 
 /* Window (first-pass form): w[j + m*M0] = 0.5 - 0.5*cos(theta_j + 2*pi*m/r0) evaluated from
- * Wtab[j] and the unit16 constants, DESIGN.md 4.1. */
+ * Wtab[j] and the unit32 constants, DESIGN.md 4.1. */
 static void apply_window(cpx* d, int N, int r0, const float* tab) {
     int M0 = N / r0;
     for (int j = 0; j < M0; ++j) {
         float c = tab[2 * j], dd = tab[2 * j + 1];       /* cos(theta_j), -sin(theta_j) */
         for (int m = 0; m < r0; ++m) {
             float C, S;
-            unit16(m * (16 / r0), &C, &S);
+            unit32(m * (32 / r0), &C, &S);
             float t = dd * S;
             float cm = fmaf(c, C, t);                    /* cos(theta_j + phi_m) */
             float w = fmaf(-0.5f, cm, 0.5f);

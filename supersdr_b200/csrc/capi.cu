@@ -193,7 +193,7 @@ int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, d
     for (int k = 1; k < 256; ++k) h->h_thr[k] = (float)(ref * std::pow(10.0, ((double)k - 0.5 - 255.0 - cal_db) / 10.0));
     h->h_thr[256] = std::numeric_limits<float>::infinity();
     h->est_c1 = (float)(10.0 * std::log10(2.0));
-    h->est_c0 = (float)(-10.0 * std::log10(ref) + cal_db + 255.0 + 0.5);
+    h->est_c0 = (float)(-10.0 * std::log10(ref) + cal_db + 255.0);
     int rc = SSDR_OK;
     auto fail = [&](int code) { ssdr_wf_destroy(h); return code; };
     if ((rc = dev_alloc(&h->d_wtab, 2 * (size_t)nfft))) return fail(rc);

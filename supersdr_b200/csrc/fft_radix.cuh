@@ -1,8 +1,12 @@
-// Register-resident radix-2/4/8/16 DIF butterflies, DESIGN.md section 4.2.
+// Register-resident radix-2/4/8/16/32 DIF butterflies on packed float2 arithmetic, DESIGN.md 4.2.
 //
-// Every line is one IEEE float32 operation in a fixed order (the translation unit is compiled with
-// -fmad=false; the only fused multiply-adds are the explicit __fmaf_rn below), so the results are
-// bit-identical to the scalar statement in oracle/c/ssdr_oracle.c.
+// A complex value is one 64-bit register pair and every complex add / subtract / multiply is
+// issued as sm_100 packed-fp32 instructions (FADD2 / FMUL2 / FFMA2: two IEEE float32 operations per
+// lane per issue slot, with the swap / negate / broadcast operand modifiers doing the "multiply by
+// -i", the conjugations and the real-by-complex products for free).  Each packed instruction is
+// exactly the two scalar float32 operations the spec states, in the stated order, so the results are
+// bit-identical to the scalar statement in oracle/c/ssdr_oracle.c.  The translation unit is compiled
+// with -fmad=false: the only fused multiply-adds are the explicit ones written here.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -14,31 +18,65 @@ constexpr float kA = 0.92387953251128674f;  // cos(pi/8)
 constexpr float kB = 0.70710678118654752f;  // sqrt(1/2)
 constexpr float kC = 0.38268343236508977f;  // sin(pi/8)
 
-SSDR_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-SSDR_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// (u.re + i u.im)(w.re + i w.im): re = fma(u.re, w.re, -(u.im*w.im)), im = fma(u.re, w.im, u.im*w.re)
-SSDR_DEV float2 cmul(float2 u, float2 w) {
-    float t0 = u.y * w.y;
-    float t1 = u.y * w.x;
-    return make_float2(__fmaf_rn(u.x, w.x, -t0), __fmaf_rn(u.x, w.y, t1));
+// cos(2 pi r / 32), r = 0..8 (first octant + the two axis values); the rest follows by symmetry.
+__device__ constexpr float kQ32[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                                       0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f,
+                                       0.19509032201612825f, 0.0f};
+
+// cos / sin (2 pi m / 32); m is a compile-time constant after unrolling.
+SSDR_DEV constexpr float unit32_cos(int m) {
+    const int mm = m & 31, quad = mm >> 3, r = mm & 7;
+    return quad == 0 ? kQ32[r] : quad == 1 ? -kQ32[8 - r] : quad == 2 ? -kQ32[r] : kQ32[8 - r];
 }
-SSDR_DEV float2 mul_mi(float2 u) { return make_float2(u.y, -u.x); }                              // * (-i)
-SSDR_DEV float2 mul_w8(float2 u) { return make_float2((u.x + u.y) * kB, (u.y - u.x) * kB); }      // * B(1-i)
-SSDR_DEV float2 mul_w83(float2 u) { return make_float2((u.y - u.x) * kB, (u.x + u.y) * (-kB)); }  // * -B(1+i)
+SSDR_DEV constexpr float unit32_sin(int m) {
+    const int mm = m & 31, quad = mm >> 3, r = mm & 7;
+    return quad == 0 ? kQ32[8 - r] : quad == 1 ? kQ32[r] : quad == 2 ? -kQ32[8 - r] : -kQ32[r];
+}
+
+SSDR_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+SSDR_DEV float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// (u.re + i u.im)(w.re + i w.im): re = fma(u.re, w.re, -(u.im*w.im)), im = fma(u.re, w.im, u.im*w.re)
+// Written so that the swap sits on the FMUL2 operand and the half negation on the FFMA2 addend: both
+// are operand modifiers, so a complex multiply is exactly two instructions.
+SSDR_DEV float2 cmul(float2 u, float2 w) {
+    const float2 t = __fmul2_rn(make_float2(u.y, u.y), make_float2(w.y, w.x));      // {im*w.im, im*w.re}
+    return __ffma2_rn(make_float2(u.x, u.x), w, make_float2(-t.x, t.y));
+}
+SSDR_DEV float2 mul_mi(float2 u) { return make_float2(u.y, -u.x); }                      // * (-i), exact
+SSDR_DEV float2 mul_w8(float2 u) {                                                       // * B(1-i)
+    const float2 s = __fadd2_rn(u, make_float2(u.y, -u.x));                              // {re+im, im-re}
+    return __fmul2_rn(s, make_float2(kB, kB));
+}
+SSDR_DEV float2 mul_w83(float2 u) {                                                      // * -B(1+i)
+    const float2 s = __fadd2_rn(make_float2(u.y, u.x), make_float2(-u.x, u.y));          // {im-re, re+im}
+    return __fmul2_rn(s, make_float2(kB, -kB));
+}
 
 SSDR_DEV void dft2(float2& x0, float2& x1) {
-    float2 a = x0, b = x1;
+    const float2 a = x0, b = x1;
     x0 = cadd(a, b);
     x1 = csub(a, b);
 }
 
 SSDR_DEV void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
-    float2 a = cadd(x0, x2), b = csub(x0, x2);
-    float2 c = cadd(x1, x3), d = mul_mi(csub(x1, x3));
+    const float2 a = cadd(x0, x2), b = csub(x0, x2);
+    const float2 c = cadd(x1, x3), e = csub(x1, x3);
     x0 = cadd(a, c);
     x2 = csub(a, c);
-    x1 = cadd(b, d);
-    x3 = csub(b, d);
+    x1 = __fadd2_rn(b, make_float2(e.y, -e.x));    // b + (-i) e
+    x3 = __fadd2_rn(b, make_float2(-e.y, e.x));    // b - (-i) e
+}
+
+// natural order in, natural order out
+SSDR_DEV void dft8(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4, float2& x5, float2& x6, float2& x7) {
+    dft2(x0, x4); dft2(x1, x5); dft2(x2, x6); dft2(x3, x7);
+    x5 = mul_w8(x5);
+    x6 = mul_mi(x6);
+    x7 = mul_w83(x7);
+    dft4(x0, x1, x2, x3);   // outputs q = 0, 2, 4, 6
+    dft4(x4, x5, x6, x7);   // outputs q = 1, 3, 5, 7
+    const float2 y1 = x4, y2 = x1, y3 = x5, y4 = x2, y5 = x6, y6 = x3;
+    x1 = y1; x2 = y2; x3 = y3; x4 = y4; x5 = y5; x6 = y6;
 }
 
 // Natural-order in, natural-order out: x[q] = sum_m x[m] W_R^(m q).
@@ -52,21 +90,7 @@ template <>
 SSDR_DEV void dft<4>(float2 (&x)[4]) { dft4(x[0], x[1], x[2], x[3]); }
 
 template <>
-SSDR_DEV void dft<8>(float2 (&x)[8]) {
-    // stage 1: pairs (m0, m0+4) -> u[p][m0]; kept in x[m0] (p=0) and x[m0+4] (p=1)
-#pragma unroll
-    for (int m0 = 0; m0 < 4; ++m0) dft2(x[m0], x[m0 + 4]);
-    x[5] = mul_w8(x[5]);
-    x[6] = mul_mi(x[6]);
-    x[7] = mul_w83(x[7]);
-    dft4(x[0], x[1], x[2], x[3]);  // p = 0 -> outputs q = 0,2,4,6 in x[0..3]
-    dft4(x[4], x[5], x[6], x[7]);  // p = 1 -> outputs q = 1,3,5,7 in x[4..7]
-    float2 y[8];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) { y[2 * s] = x[s]; y[2 * s + 1] = x[4 + s]; }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) x[q] = y[q];
-}
+SSDR_DEV void dft<8>(float2 (&x)[8]) { dft8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]); }
 
 template <>
 SSDR_DEV void dft<16>(float2 (&x)[16]) {
@@ -90,41 +114,59 @@ SSDR_DEV void dft<16>(float2 (&x)[16]) {
     for (int q = 0; q < 16; ++q) x[q] = y[q];
 }
 
-// Twiddle powers w[2..R-1] from w[1]: fixed minimum-depth chain, DESIGN.md section 4.4.
-template <int R>
-SSDR_DEV void tw_chain(float2 (&w)[R]) {
-    if constexpr (R > 2) {
-        w[2] = cmul(w[1], w[1]);
-        w[3] = cmul(w[2], w[1]);
-    }
-    if constexpr (R > 4) {
-        w[4] = cmul(w[2], w[2]);
-        w[5] = cmul(w[4], w[1]);
-        w[6] = cmul(w[3], w[3]);
-        w[7] = cmul(w[4], w[3]);
-    }
-    if constexpr (R > 8) {
-        w[8] = cmul(w[4], w[4]);
-        w[9] = cmul(w[8], w[1]);
-        w[10] = cmul(w[5], w[5]);
-        w[11] = cmul(w[8], w[3]);
-        w[12] = cmul(w[6], w[6]);
-        w[13] = cmul(w[8], w[5]);
-        w[14] = cmul(w[7], w[7]);
-        w[15] = cmul(w[8], w[7]);
-    }
+template <>
+SSDR_DEV void dft<32>(float2 (&x)[32]) {
+    // 32 = 4 x 8, m = m0 + 8 m1.  stage 1: radix-4 across m1; result p lives in x[m0 + 8p]
+#pragma unroll
+    for (int m0 = 0; m0 < 8; ++m0) dft4(x[m0], x[m0 + 8], x[m0 + 16], x[m0 + 24]);
+    // internal twiddles W32^(m0*p); exponent 8 is the exact rotation by -i
+#pragma unroll
+    for (int p = 1; p < 4; ++p)
+#pragma unroll
+        for (int m0 = 1; m0 < 8; ++m0) {
+            // W32^e = (-i)^(e / 8) W32^(e % 8): the quarter turns are exact swaps / negations (operand
+            // modifiers of the consuming add), so only seven distinct constants are live.  Bit-identical
+            // to multiplying by the full-circle constant because the unit32 table is built by symmetry.
+            const int e = m0 * p, r = e & 7, k = e >> 3;
+            float2 v = x[m0 + 8 * p];
+            if (r) v = cmul(v, make_float2(unit32_cos(r), -unit32_sin(r)));
+            if (k == 1) v = mul_mi(v);
+            else if (k == 2) v = make_float2(-v.x, -v.y);
+            x[m0 + 8 * p] = v;
+        }
+    // stage 2: radix-8 across m0 for each p; output s lives in x[8p + s] -> q = p + 4s
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        dft8(x[8 * p], x[8 * p + 1], x[8 * p + 2], x[8 * p + 3], x[8 * p + 4], x[8 * p + 5], x[8 * p + 6], x[8 * p + 7]);
+    float2 y[32];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) y[p + 4 * s] = x[8 * p + s];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) x[q] = y[q];
 }
 
-// cos/sin(2 pi m / 16) from {1, A, B, C, 0} by symmetry; m is a compile-time constant after unrolling.
-SSDR_DEV void unit16(int m, float& c, float& s) {
-    const float q[5] = {1.0f, kA, kB, kC, 0.0f};
-    int mm = m & 15, quad = mm >> 2, r = mm & 3;
-    float cr = q[r], sr = q[4 - r];
-    switch (quad) {
-        case 0: c = cr; s = sr; break;
-        case 1: c = -sr; s = cr; break;
-        case 2: c = -cr; s = -sr; break;
-        default: c = sr; s = -cr; break;
+// Twiddles of a "chain" pass: output q = 4a + b is multiplied by W^(j q) as
+// (x * A[a]) * B[b] with B[1] = w1 = W^j, B[2] = w1 w1, B[3] = B[2] w1, A[1] = B[2] B[2], A[2] = A[1] A[1],
+// A[3] = A[2] A[1]: six live twiddles instead of R - 1, the same number of complex multiplies.
+template <int R>
+SSDR_DEV void tw_two_level(float2 (&x)[R], float2 w1) {
+    static_assert(R <= 16, "chain passes have radix <= 16 (the plan keeps radix-32 passes on tables)");
+    if constexpr (R == 2) {
+        x[1] = cmul(x[1], w1);
+    } else {
+        float2 B[4], A[4];
+        B[1] = w1;
+        B[2] = cmul(w1, w1);
+        B[3] = cmul(B[2], w1);
+        if constexpr (R > 4) A[1] = cmul(B[2], B[2]);
+        if constexpr (R > 8) { A[2] = cmul(A[1], A[1]); A[3] = cmul(A[2], A[1]); }
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+            if (q >> 2) x[q] = cmul(x[q], A[q >> 2]);
+            if (q & 3) x[q] = cmul(x[q], B[q & 3]);
+        }
     }
 }
 

@@ -7,11 +7,15 @@
 // kiwi_waterfall.spectrum_db2col (:787-813).  Arithmetic spec: DESIGN.md section 4; bit-exact CPU
 // statement: oracle/c/ssdr_oracle.c.
 //
-// Layout: one frame group of G = N/EPT threads owns one channel at a time and walks its n_avg
-// frames; FPC groups share a CTA for small N.  The frame lives in shared memory (XOR-swizzled
-// float2[N]); every pass is in place, so one barrier per pass; the per-bin byte sums live in
-// shared memory as uint16 in FFT *position* order (digit-reversed), and are permuted to bin order
-// only once per channel when the row is written.
+// Layout: a frame group of G = N/32 threads owns one channel at a time and
+// walks its n_avg frames; every thread handles 32 points of every pass.  The plan is one first pass
+// of radix N/32^k (reads HBM with coalesced 8-byte loads, applies the window, writes shared memory)
+// followed by k <= 2 radix-32 passes, so a 16384-point frame makes only TWO round trips through
+// shared memory.  The frame lives in shared memory as float2[N + N/32] (one pad element per 32:
+// every pass reads and writes with immediate offsets from one per-thread base and is bank-conflict
+// free).  The per-bin byte sums over the n_avg frames never leave registers (16 packed uint16 pairs
+// per thread); the colour stage selects the order statistics from those registers and transposes the
+// finished row through the (then idle) frame buffer so that HBM sees only coalesced row stores.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -29,18 +33,16 @@ namespace ssdr {
 // ---------------------------------------------------------------------------------------------
 struct PlanC {
     int np;
-    int r[5];
+    int r[4];
 };
 constexpr PlanC make_plan(int lg) {
-    PlanC p{0, {0, 0, 0, 0, 0}};
-    int rem = lg;
-    while (rem >= 6 || rem == 4) { p.r[p.np++] = 16; rem -= 4; }
-    if (rem == 5) { p.r[p.np++] = 8; p.r[p.np++] = 4; }
-    else if (rem == 3) p.r[p.np++] = 8;
-    else if (rem == 2) p.r[p.np++] = 4;
+    PlanC p{0, {0, 0, 0, 0}};
+    int k = lg / 5, r = lg - 5 * k;
+    if (r == 0) { r = 5; k -= 1; }
+    p.r[p.np++] = 1 << r;
+    for (int i = 0; i < k; ++i) p.r[p.np++] = 32;
     return p;
 }
-constexpr int kTablePassMax = 1024;   // a pass uses exact table twiddles iff (L/R)*(R-1) <= this
 
 constexpr int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -48,33 +50,27 @@ template <int LG>
 struct Cfg {
     static constexpr int N = 1 << LG;
     static constexpr PlanC plan = make_plan(LG);
-    static constexpr int NP = plan.np;
-    static constexpr int EPT = (LG >= 13) ? 32 : 16;      // elements per thread
-    static constexpr int G = N / EPT;                     // threads per frame group
+    static constexpr int NP = plan.np;                    // 2 (N <= 1024) or 3
+    static constexpr int R0 = plan.r[0];
+    static constexpr int M0 = N / R0;                     // 32 (NP == 2) or 1024 (NP == 3)
+    static constexpr int G = N / 32;                      // threads per frame group
     static constexpr int THREADS = (G >= 256) ? G : 256;
     static constexpr int FPC = THREADS / G;               // frame groups per CTA
-    static constexpr int R0 = plan.r[0];
-    static constexpr int RL = plan.r[plan.np - 1];        // radix of the last pass
-    static constexpr int M0 = N / R0;
-    static constexpr int NCHUNK = N / RL;                 // accumulator chunks (RL uint16 each)
-    static constexpr int CSH = ilog2(M0 / RL);            // chunk >> CSH == first-pass digit q0
-    static constexpr int CMASK = (1 << (CSH < 4 ? CSH : 4)) - 1;   // swizzle only bits below the q0 field
-    // sub-transform length before pass p
-    static constexpr int radix(int p) { return make_plan(LG).r[p]; }   // usable with a runtime index in device code
-    static constexpr int Lof(int p) { int L = N; for (int i = 0; i < p; ++i) L /= radix(i); return L; }
-    static constexpr bool table_pass(int p) { int L = Lof(p), R = radix(p); return (L / R) * (R - 1) <= kTablePassMax; }
-    static constexpr int table_off(int p) {               // float2 offset of pass p's table
-        int off = 0;
-        for (int i = 0; i < p; ++i) { int L = Lof(i), R = radix(i); if (table_pass(i) && L / R > 1) off += (L / R) * (R - 1); }
-        return off;
-    }
-    static constexpr int TABLE_ELEMS = table_off(plan.np);
+    static constexpr int NB0 = 32 / R0;                   // first-pass butterflies per thread
+    static constexpr int PADN = N + N / 32;               // padded frame, float2 elements
+    static constexpr int TW0 = (M0 == 32) ? 32 * (R0 - 1) : 0;   // first-pass twiddle table (NP == 2)
+    static constexpr int TW1 = (NP == 3) ? 32 * 31 : 0;          // middle-pass twiddle table
+    static constexpr int SWZ = (NP == 3) ? ilog2(R0) : -1;       // staging swizzle shift (colour stage)
+    static constexpr int MIN_CTAS = (LG >= 14) ? 1 : 2;
+    static_assert(NP == 2 || NP == 3, "supported sizes: 64 .. 16384");
+    static_assert(M0 == 32 || M0 == 1024, "first pass leaves 32 or 1024 sub-transforms");
     // dynamic shared memory layout (bytes)
     static constexpr size_t SM_DATA = 0;
-    static constexpr size_t SM_ACC = SM_DATA + (size_t)FPC * N * sizeof(float2);
-    static constexpr size_t SM_TW = SM_ACC + (size_t)FPC * N * sizeof(uint16_t);
-    static constexpr size_t SM_THR = SM_TW + (size_t)TABLE_ELEMS * sizeof(float2);
-    static constexpr size_t SM_RED = SM_THR + 260 * sizeof(float);
+    static constexpr size_t SM_TW0 = SM_DATA + (size_t)FPC * PADN * sizeof(float2);
+    static constexpr size_t SM_TW1 = SM_TW0 + (size_t)TW0 * sizeof(float2);
+    static constexpr size_t SM_ACC = SM_TW1 + (size_t)TW1 * sizeof(float2);        // byte sums, thread-private uint4[4][THREADS]
+    static constexpr size_t SM_W1 = SM_ACC + (size_t)THREADS * 16 * sizeof(unsigned);   // wtab[j] of this thread's butterflies
+    static constexpr size_t SM_RED = SM_W1 + (size_t)THREADS * NB0 * sizeof(float2);
     static constexpr size_t SM_BYTES = SM_RED + (size_t)FPC * 8 * sizeof(int);
 };
 
@@ -91,10 +87,9 @@ struct WfKernelParams {
     int batch, n_avg;
     int p_lo;
     float p_gamma;
-    float est_c1, est_c0;           // byte estimate = floor(log2(P) * c1 + c0)
+    float est_c1, est_c0;           // byte value ~= log2(P) * c1 + c0   (rounded to nearest = the byte)
+    int key_bits;                   // bits needed for 255 * n_avg (selection iterations)
 };
-
-SSDR_DEV int swz(int a) { return a ^ ((a >> 4) & 15); }
 
 // ---- sample load (K6 fused): complex64 or Kiwi big-endian int16 pairs (kiwi/client.py:449-453) --
 template <int FMT>
@@ -109,109 +104,132 @@ SSDR_DEV float2 load_iq(const void* base, size_t idx) {
     }
 }
 
-// ---- |X|^2 -> Kiwi byte: count thresholds (exact), starting from a log2 estimate -----------------
-SSDR_DEV int quantise(float P, const float* thr, float c1, float c0) {
-    float est = __fmaf_rn(__log2f(P), c1, c0);          // -inf for P == 0, NaN never (P >= 0)
-    int k = (int)fminf(fmaxf(est, 0.0f), 255.0f);
-    while (k < 255 && P >= thr[k + 1]) ++k;
-    while (k > 0 && P < thr[k]) --k;
-    return k;
+// Ask the memory system to bring [p, p + bytes) into L2 (one bulk request, no destination).
+SSDR_DEV void prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// ---- |X|^2 -> Kiwi byte ------------------------------------------------------------------------
+// Spec: byte = largest k with P >= T[k].  Fast path: v = log2(P) c1 + c0 estimates
+// the un-rounded byte value to ~1e-4; its nearest integer IS the byte unless v lies within kQEps of
+// a rounding boundary, and only then the thresholds are consulted (exact, rare).
+constexpr float kQMagic = 12582912.0f;    // 1.5 * 2^23: (v + magic) rounds v to nearest in the low mantissa bits
+constexpr float kQEps = 2.5e-4f;
+
+SSDR_DEV float lg2_ftz(float x) {          // MUFU.LG2; a subnormal power is far below T[1], so flushing it to 0 is exact
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __noinline__ unsigned quantise_exact(float P, float v, const float* thr) {
+    int k = __float2int_rn(v);             // v is already clamped to [-0.25, 255.25]
+    while (k < 255 && P >= __ldg(thr + k + 1)) ++k;
+    while (k > 0 && P < __ldg(thr + k)) --k;
+    return (unsigned)k;
+}
+
+// two bins -> byte0 | byte1 << 16
+SSDR_DEV unsigned quantise_pair(float2 a, float2 b, const WfKernelParams& kp) {
+    const float t0 = a.y * a.y, t1 = b.y * b.y;
+    const float P0 = __fmaf_rn(a.x, a.x, t0), P1 = __fmaf_rn(b.x, b.x, t1);
+    float2 v = __ffma2_rn(make_float2(lg2_ftz(P0), lg2_ftz(P1)), make_float2(kp.est_c1, kp.est_c1),
+                          make_float2(kp.est_c0, kp.est_c0));
+    v.x = fminf(fmaxf(v.x, -0.25f), 255.25f);           // P == 0 -> -inf -> byte 0; NaN -> 0 like the oracle
+    v.y = fminf(fmaxf(v.y, -0.25f), 255.25f);
+    const float2 m = __fadd2_rn(v, make_float2(kQMagic, kQMagic));
+    const float2 nf = __fadd2_rn(m, make_float2(-kQMagic, -kQMagic));
+    const float2 dd = __fadd2_rn(v, make_float2(-nf.x, -nf.y));
+    unsigned k0 = __float_as_uint(m.x), k1 = __float_as_uint(m.y);     // low 16 bits = nearest integer
+    if (fmaxf(fabsf(dd.x), fabsf(dd.y)) > 0.5f - kQEps) {              // rare: within kQEps of a rounding boundary
+        k0 = quantise_exact(P0, v.x, kp.thr);
+        k1 = quantise_exact(P1, v.y, kp.thr);
+    }
+    return __byte_perm(k0, k1, 0x5410);
 }
 
 // ---------------------------------------------------------------------------------------------
-// one FFT pass (in place in shared memory; the first pass reads global memory)
+// FFT passes.  Element at logical position p of the frame lives at d[p + (p >> 5)].
 // ---------------------------------------------------------------------------------------------
-template <class C, int P, int FMT, bool WINDOW>
-SSDR_DEV void fft_pass(float2* d, uint16_t* acc, const float2* tws, const float* thr, int t,
-                       const void* src, size_t src_off, const WfKernelParams& kp, bool first_frame) {
-    constexpr int N = C::N, R = C::plan.r[P], L = C::Lof(P), M = L / R, G = C::G;
-    constexpr bool FIRST = (P == 0), LAST = (P == C::NP - 1);
-    constexpr bool TABLE = C::table_pass(P);
-    constexpr int NB = (N / R) / G;   // butterflies per thread
-    static_assert(NB >= 1, "group too large for this radix");
-    const float2* tw = tws + C::table_off(P);
-#pragma unroll 1
-    for (int i = 0; i < NB; ++i) {
-        const int u = t + i * G;
-        const int j = u & (M - 1);
-        const int base = (u / M) * L;
-        float2 x[R];
-        float2 w[R];
-        if constexpr (FIRST) {
+// First pass, part 1: the R0 samples of first-pass butterfly i of this thread -> registers (coalesced
+// 8-byte loads).  Butterfly 0 is loaded before the barrier that frees the frame buffer, so its latency
+// hides behind the other warps; the others are in flight while the preceding butterfly computes.
+template <class C, int FMT>
+SSDR_DEV void first_load(float2 (&x)[C::R0], int i, int t, const void* src, size_t off) {
 #pragma unroll
-            for (int m = 0; m < R; ++m) x[m] = load_iq<FMT>(src, src_off + (size_t)(j + m * M));
-            if constexpr (WINDOW || !TABLE) w[1] = __ldg(kp.wtab + j);
-            if constexpr (WINDOW) {
-                const float c = w[1].x, dd = w[1].y;
+    for (int m = 0; m < C::R0; ++m) x[m] = load_iq<FMT>(src, off + (size_t)(t + i * C::G + m * C::M0));
+}
+
+// First pass, part 2: window, radix-R0 butterflies, twiddles, scatter into the frame buffer.
+template <class C, bool WINDOW>
+SSDR_DEV void first_compute(float2 (&x)[C::R0], int i, float2* d, const float2* tw0, int t, float2 w1) {
+    constexpr int R = C::R0, M = C::M0, G = C::G;
+    constexpr bool TABLE = (M == 32);
+    const int j = t + i * G;
+    if constexpr (WINDOW) {
+        // w[j + m M] = 0.5 - 0.5 cos(theta_j + 2 pi m / R) from wtab[j] and the unit32 constants
+        const float2 cc = make_float2(w1.x, w1.x), dd = make_float2(w1.y, w1.y);
 #pragma unroll
-                for (int m = 0; m < R; ++m) {
-                    float Cm, Sm;
-                    unit16(m * (16 / R), Cm, Sm);
-                    float tt = dd * Sm;
-                    float cm = __fmaf_rn(c, Cm, tt);
-                    float wv = __fmaf_rn(-0.5f, cm, 0.5f);
-                    x[m].x = x[m].x * wv;
-                    x[m].y = x[m].y * wv;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < R; ++m) x[m] = d[swz(base + j + m * M)];
+        for (int m = 0; m < R; m += 2) {
+            const int e0 = m * (32 / R), e1 = (m + 1) * (32 / R);
+            const float2 tt = __fmul2_rn(dd, make_float2(unit32_sin(e0), unit32_sin(e1)));
+            const float2 cm = __ffma2_rn(cc, make_float2(unit32_cos(e0), unit32_cos(e1)), tt);
+            const float2 wv = __ffma2_rn(make_float2(-0.5f, -0.5f), cm, make_float2(0.5f, 0.5f));
+            x[m] = __fmul2_rn(x[m], make_float2(wv.x, wv.x));
+            x[m + 1] = __fmul2_rn(x[m + 1], make_float2(wv.y, wv.y));
         }
-        dft<R>(x);
-        if constexpr (M > 1) {
-            if constexpr (TABLE) {
+    }
+    dft<R>(x);
+    if constexpr (TABLE) {
 #pragma unroll
-                for (int q = 1; q < R; ++q) w[q] = tw[(q - 1) * M + j];
-            } else {
-                if constexpr (!FIRST) w[1] = __ldg(kp.wtab + j * (N / L));
-                tw_chain<R>(w);
-            }
+        for (int q = 1; q < R; ++q) x[q] = cmul(x[q], tw0[(q - 1) * 32 + j]);
+    } else {
+        tw_two_level<R>(x, w1);
+    }
+    float2* o = TABLE ? d + j : d + j + (j >> 5);
 #pragma unroll
-            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], w[q]);
-        }
-        if constexpr (!LAST) {
+    for (int q = 0; q < R; ++q) o[q * (M + M / 32)] = x[q];
+}
+
+// radix-32 pass over sub-transforms of length 1024 (NP == 3 only): table twiddles W_1024^(j q)
+template <class C>
+SSDR_DEV void pass_mid(float2* d, const float2* tw1, int t) {
+    const int j = t & 31;
+    float2* p = d + (t >> 5) * (1024 + 32) + j;
+    float2 x[32];
 #pragma unroll
-            for (int q = 0; q < R; ++q) d[swz(base + j + q * M)] = x[q];
-        } else {
-            // epilogue: positions u*R + q.  Power -> byte -> accumulate uint16 sums (position order).
-            unsigned pk[R / 2];
+    for (int m = 0; m < 32; ++m) x[m] = p[33 * m];
+    dft<32>(x);
 #pragma unroll
-            for (int q = 0; q < R; q += 2) {
-                float t0 = x[q].y * x[q].y;
-                float P0 = __fmaf_rn(x[q].x, x[q].x, t0);
-                float t1 = x[q + 1].y * x[q + 1].y;
-                float P1 = __fmaf_rn(x[q + 1].x, x[q + 1].x, t1);
-                unsigned b0 = (unsigned)quantise(P0, thr, kp.est_c1, kp.est_c0);
-                unsigned b1 = (unsigned)quantise(P1, thr, kp.est_c1, kp.est_c0);
-                pk[q / 2] = b0 | (b1 << 16);
-            }
-            const int cs = u ^ ((u >> C::CSH) & C::CMASK);
-            unsigned* a32 = reinterpret_cast<unsigned*>(acc + (size_t)cs * R);
-            if (!first_frame) {
+    for (int q = 1; q < 32; ++q) x[q] = cmul(x[q], tw1[(q - 1) * 32 + j]);
 #pragma unroll
-                for (int q = 0; q < R / 2; ++q) pk[q] += a32[q];   // two uint16 lanes, no carry (<= 25500)
-            }
+    for (int q = 0; q < 32; ++q) p[33 * q] = x[q];
+}
+
+// last radix-32 pass (sub-transform length 32, no twiddles) + power + byte + accumulate
+// The byte sums over the n_avg frames live in a thread-private uint4[4] column of shared memory (two
+// uint16 lanes per word, no carry: <= 25500), touched with 128-bit accesses only.
+template <class C>
+SSDR_DEV void pass_last(const float2* d, int t, uint4* accs, bool first_frame, const WfKernelParams& kp) {
+    const float2* p = d + 33 * t;
+    float2 x[32];
 #pragma unroll
-            for (int q = 0; q < R / 2; ++q) a32[q] = pk[q];
-        }
+    for (int m = 0; m < 32; ++m) x[m] = p[m];
+    dft<32>(x);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 a = make_uint4(0u, 0u, 0u, 0u);
+        if (!first_frame) a = accs[c * C::THREADS];
+        a.x += quantise_pair(x[8 * c], x[8 * c + 1], kp);
+        a.y += quantise_pair(x[8 * c + 2], x[8 * c + 3], kp);
+        a.z += quantise_pair(x[8 * c + 4], x[8 * c + 5], kp);
+        a.w += quantise_pair(x[8 * c + 6], x[8 * c + 7], kp);
+        accs[c * C::THREADS] = a;
     }
 }
 
-template <class C, int P, int FMT, bool WINDOW>
-SSDR_DEV void fft_all_passes(float2* d, uint16_t* acc, const float2* tws, const float* thr, int t,
-                             const void* src, size_t src_off, const WfKernelParams& kp, bool first_frame,
-                             bool active) {
-    if constexpr (P < C::NP) {
-        if (P == 0) __syncthreads();          // previous frame's last pass has finished reading d
-        if (active) fft_pass<C, P, FMT, WINDOW>(d, acc, tws, thr, t, src, src_off, kp, first_frame);
-        if (P < C::NP - 1) __syncthreads();
-        fft_all_passes<C, P + 1, FMT, WINDOW>(d, acc, tws, thr, t, src, src_off, kp, first_frame, active);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// group reductions (a frame group is G threads: a half warp, a warp, or several warps)
+// group synchronisation: a frame group is G threads = part of a warp, a warp, several warps or the CTA
 // ---------------------------------------------------------------------------------------------
 template <int G>
 SSDR_DEV unsigned group_mask(int lane) {
@@ -219,135 +237,123 @@ SSDR_DEV unsigned group_mask(int lane) {
     else return ((1u << G) - 1u) << (lane & ~(G - 1));
 }
 
-// Colour stage for one channel, executed by its frame group.  `red` = 8 ints of scratch per group.
-// keys live in acc (uint16 sums) in chunk order; CHUNK_ID maps the k-order index idx to the chunk.
-template <class C, bool FFT_ORDER>
-SSDR_DEV void colour_stage(uint16_t* acc, int* red, int t, int ch, bool active, const WfKernelParams& kp) {
-    constexpr int N = C::N, G = C::G, RL = C::RL, NCH = C::NCHUNK;
-    constexpr int CPT = NCH / G;      // chunks per thread
+template <class C>
+SSDR_DEV void group_sync(int slot) {
+    if constexpr (C::G <= 32) __syncwarp(group_mask<C::G>(threadIdx.x & 31));
+    else if constexpr (C::FPC == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(C::G) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// colour stage: order statistics from the register-resident sums, then the row through a transpose
+// ---------------------------------------------------------------------------------------------
+// Thread t of a group holds the sums of bins k = kbase(t) + G q, q = 0..31, as acc[q/2] halves
+// (FFT entry) or k = 32 t + q (colorrow entry, LINEAR).  Output index o = k ^ N/2 (FFT) or k.
+// Groups are independent: every barrier below is group-scoped.
+template <class C, bool LINEAR>
+SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsigned (&acc)[16], const WfKernelParams& kp) {
+    constexpr int N = C::N, G = C::G;
     const int lane = threadIdx.x & 31;
     const unsigned gmask = group_mask<G>(lane);
-    const bool leader = (G >= 32) ? (lane == 0) : ((lane & (G - 1)) == 0);
+    const bool leader = (lane == 0);                    // used only when G > 32 (whole warps)
 
-    // chunk (position order, swizzled) holding bins k = idx + NCH*q, q = 0..RL-1
-    auto chunk_of = [](int idx) -> int {
-        if constexpr (!FFT_ORDER) {
-            return idx;
-        } else {
-            int c = 0, rem = idx, Mi = N;
-#pragma unroll
-            for (int p = 0; p < C::NP - 1; ++p) {
-                const int R = C::radix(p);
-                Mi /= R;
-                int q = rem & (R - 1);
-                rem >>= ilog2(R);
-                c += q * (Mi / RL);
-            }
-            return c ^ ((c >> C::CSH) & C::CMASK);
-        }
-    };
+    const ssdr_wf_display_t dp = kp.disp[ch];
 
-    ssdr_wf_display_t dp;
-    if (active) dp = kp.disp[ch];
-    else { dp.zoom = 0; dp.auto_scale = 0; dp.delta_low_db = 0; dp.delta_high_db = 0; dp.low_clip_db = 0.f; dp.dynamic_range = 40.f; }
-
-    // wf_db[0] = wf_db[1] (utils_supersdr.py:791): output bin o = k ^ N/2 (FFT order) or o = k.
-    __syncthreads();
-    if (active && t == 0) {
-        // red[4] keeps the raw sum of bin 0: kiwi_waterfall.spectrum itself is not patched
-        if constexpr (FFT_ORDER) {
-            // o = 0 <-> k = N/2: idx 0, q = RL/2;  o = 1 <-> k = N/2 + 1: idx 1, q = RL/2
-            red[4] = acc[(size_t)chunk_of(0) * RL + RL / 2];
-            acc[(size_t)chunk_of(0) * RL + RL / 2] = acc[(size_t)chunk_of(1) * RL + RL / 2];
-        } else {
-            red[4] = acc[0];
-            acc[0] = acc[1];   // plain order: chunk 0 elements 0 and 1 (RL >= 2)
-        }
+    // wf_db[0] = wf_db[1] (utils_supersdr.py:791).  Output index o of (t, q):
+    //   FFT order:  o = kbase(t) + G (q ^ 16), kbase = (t >> 5) + R0 (t & 31)  (NP == 3)  or  t  (NP == 2)
+    //   linear:     o = 32 t + q
+    // o == 0 is (t = 0, q = 16) / (t = 0, q = 0); o == 1 is (t = tB, q = 16) / (t = 0, q = 1).
+    constexpr int tB = LINEAR ? 0 : (C::NP == 3 ? 32 : 1);
+    constexpr int q0 = LINEAR ? 0 : 16, q1 = LINEAR ? 1 : 16;
+    auto key_at = [&](int q) -> unsigned { return (q & 1) ? (acc[q >> 1] >> 16) : (acc[q >> 1] & 0xffffu); };
+    if (t == tB) red[5] = (int)key_at(q1);
+    if (t == 0) { red[0] = 0; red[1] = 0; red[2] = 0; red[3] = 0; red[4] = 0x7fffffff; }
+    group_sync<C>(slot);
+    unsigned raw0 = 0;
+    if (t == 0) {
+        raw0 = key_at(q0);          // kiwi_waterfall.spectrum[0] itself is not patched
+        const unsigned v1 = (unsigned)red[5];
+        if (q0 & 1) acc[q0 >> 1] = (acc[q0 >> 1] & 0x0000ffffu) | (v1 << 16);
+        else acc[q0 >> 1] = (acc[q0 >> 1] & 0xffff0000u) | v1;
     }
-    if (leader && active) { red[0] = 0; red[1] = 0; red[2] = 0x7fffffff; red[3] = 0; }
-    __syncthreads();
 
-    // keys of this thread: CPT chunks x RL
-    unsigned keys[CPT * RL / 2];
-    int kmax = 0;
-#pragma unroll
-    for (int i = 0; i < CPT; ++i) {
-        const int idx = t + i * G;
-        const unsigned* a32 = reinterpret_cast<const unsigned*>(acc + (size_t)chunk_of(idx) * RL);
-#pragma unroll
-        for (int q = 0; q < RL / 2; ++q) {
-            unsigned v = active ? a32[q] : 0u;
-            keys[i * (RL / 2) + q] = v;
-            kmax = max(kmax, (int)max(v & 0xffffu, v >> 16));
-        }
-    }
     float low_clip = dp.low_clip_db, high_clip = 0.f, dyn = dp.dynamic_range;
     const float fn = (float)kp.n_avg, z3 = (float)(3 * dp.zoom);
     auto wfdb = [&](float s) { return ((__fdiv_rn(s, fn) - 255.0f) - 13.0f) + z3; };
 
-    // ---- max and the two order statistics (ranks p_lo, p_lo + 1) by counting bisection ----------
-    kmax = __reduce_max_sync(gmask, kmax);
-    if (leader && active) atomicMax(&red[3], kmax);
-    __syncthreads();
-    const int vmax = red[3];
-    int lo = 0, hi = vmax;
-    const int want = kp.p_lo + 1;                 // smallest v with count(keys <= v) >= want
-    int cnt_lo = 0;
-    // fixed trip count (uniform across groups sharing the CTA): 15 bits cover 255 * 100
-#pragma unroll 1
-    for (int it = 0; it < 15; ++it) {
-        const int mid = (lo + hi) >> 1;
-        int c = 0;
-#pragma unroll
-        for (int i = 0; i < CPT * RL / 2; ++i) {
-            c += ((int)(keys[i] & 0xffffu) <= mid) + ((int)(keys[i] >> 16) <= mid);
+    auto group_sum = [&](int v, int rslot) -> int {
+        v = __reduce_add_sync(gmask, v);
+        if constexpr (G <= 32) return v;
+        else {
+            if (leader) atomicAdd(&red[rslot], v);
+            group_sync<C>(slot);
+            return red[rslot];
         }
-        c = __reduce_add_sync(gmask, c);
-        int* slot = &red[it & 1];
-        if (leader && active) atomicAdd(slot, c);
-        __syncthreads();
-        const int total = *slot;
-        if (total >= want) hi = mid; else lo = mid + 1;
-        if (leader && active) red[(it + 1) & 1] = 0;   // the other slot is free after this barrier
-        __syncthreads();
+    };
+
+    // ---- max ---------------------------------------------------------------------------------
+    int kmax = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) kmax = max(kmax, (int)max(acc[i] & 0xffffu, acc[i] >> 16));
+    kmax = __reduce_max_sync(gmask, kmax);
+    if constexpr (G > 32) {
+        if (leader) atomicMax(&red[3], kmax);
+        group_sync<C>(slot);
+        kmax = red[3];
     }
-    const int v_lo = hi;                           // == lo
-    {   // count(keys <= v_lo) and min{key > v_lo}
+    const int vmax = kmax;
+
+    if (dp.auto_scale) {          // group-uniform
+        // ---- rank p_lo (0-based) by bisection on the key bits: smallest v with count(keys <= v) >= p_lo + 1.
+        // Packed count: keys < 2^15, so (mid + 0x8000 - key) has bit 15 set iff key <= mid, per 16-bit half.
+        const int want = kp.p_lo + 1;
+        int lo = 0, hi = (1 << kp.key_bits) - 1;
+#pragma unroll 1
+        for (int it = 0; it < kp.key_bits; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const unsigned M = ((unsigned)mid | 0x8000u) * 0x10001u;
+            unsigned c = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c += ((M - acc[i]) & 0x80008000u) >> 15;
+            const int total = group_sum((int)((c & 0xffffu) + (c >> 16)), it % 3);
+            if (total >= want) hi = mid; else lo = mid + 1;
+            if constexpr (G > 32) { if (t == 0) red[(it + 2) % 3] = 0; }   // read by everyone before the previous barrier
+        }
+        const int v_lo = hi;
+        // count(keys <= v_lo) and min{key > v_lo}
         int c = 0, mn = 0x7fffffff;
 #pragma unroll
-        for (int i = 0; i < CPT * RL / 2; ++i) {
-            int a = (int)(keys[i] & 0xffffu), b = (int)(keys[i] >> 16);
+        for (int i = 0; i < 16; ++i) {
+            const int a = (int)(acc[i] & 0xffffu), b = (int)(acc[i] >> 16);
             c += (a <= v_lo) + (b <= v_lo);
             if (a > v_lo) mn = min(mn, a);
             if (b > v_lo) mn = min(mn, b);
         }
-        c = __reduce_add_sync(gmask, c);
         mn = __reduce_min_sync(gmask, mn);
-        // both slots were zeroed: red[(15)&1] by the last iteration, and red[(14)&1]... reset here
-        __syncthreads();
-        if (leader && active) { red[0] = 0; }
-        __syncthreads();
-        if (leader && active) { atomicAdd(&red[0], c); atomicMin(&red[2], mn); }
-        __syncthreads();
-        cnt_lo = red[0];
-        const int v_hi = (cnt_lo >= want + 1 || red[2] == 0x7fffffff) ? v_lo : red[2];
-        if (dp.auto_scale) {
-            // numpy _lerp in float32
-            const float a = wfdb((float)v_lo), b = wfdb((float)v_hi), g = kp.p_gamma;
-            const float dba = b - a;
-            float p;
-            if (g >= 0.5f) { float tt = 1.0f - g; tt = dba * tt; p = b - tt; }
-            else { float tt = dba * g; p = a + tt; }
-            low_clip = p;
-            high_clip = wfdb((float)vmax);
-            const float dd = high_clip - low_clip;
-            dyn = dd > 40.0f ? dd : 40.0f;
+        if constexpr (G > 32) {
+            group_sync<C>(slot);                               // all reads of the bisection slots are done
+            if (t == 0) red[0] = 0;
+            group_sync<C>(slot);
+            if (leader) atomicMin(&red[4], mn);
         }
+        const int cnt_lo = group_sum(c, 0);
+        if constexpr (G > 32) mn = red[4];
+        const int v_hi = (cnt_lo >= want + 1 || mn == 0x7fffffff) ? v_lo : mn;
+        // numpy _lerp in float32
+        const float a = wfdb((float)v_lo), b = wfdb((float)v_hi), g = kp.p_gamma;
+        const float dba = b - a;
+        float p;
+        if (g >= 0.5f) { float tt = 1.0f - g; tt = dba * tt; p = b - tt; }
+        else { float tt = dba * g; p = a + tt; }
+        low_clip = p;
+        high_clip = wfdb((float)vmax);
+        const float dd = high_clip - low_clip;
+        dyn = dd > 40.0f ? dd : 40.0f;
     }
     const float low = low_clip + (float)dp.delta_low_db;
     const float nf = dyn + (float)dp.delta_high_db;
     const float den = nf - (float)dp.delta_low_db;
-    if (active && t == 0) {
+    if (t == 0) {
         if (dp.auto_scale) { kp.disp[ch].low_clip_db = low_clip; kp.disp[ch].dynamic_range = dyn; }
         if (kp.scalars) {
             ssdr_wf_scalars_t s;
@@ -356,80 +362,137 @@ SSDR_DEV void colour_stage(uint16_t* acc, int* red, int t, int ch, bool active, 
             kp.scalars[ch] = s;
         }
     }
-    // ---- colour row: permute to bin order, coalesced byte / float stores ------------------------
-    if (active) {
-        const size_t row = (size_t)ch * N;
+
+    // ---- the row: colour value per bin, transposed to bin order through shared memory ---------------
+    auto out_index = [&](int q) -> int {
+        if constexpr (LINEAR) return 32 * t + q;
+        else {
+            const int kb = (C::NP == 3) ? ((t >> 5) + C::R0 * (t & 31)) : t;
+            return kb + G * (q ^ 16);
+        }
+    };
+    auto sidx = [](int o) -> int {
+        if constexpr (LINEAR) return o + (o >> 5);                       // thread-contiguous writes: pad, not swizzle
+        else if constexpr (C::SWZ >= 0) return o ^ ((o >> C::SWZ) & 31);
+        else return o;
+    };
+    const size_t row = (size_t)ch * N;
+    group_sync<C>(slot);                                                 // every warp of the group is past its last FFT pass
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-            const int idx = t + i * G;
+    for (int q = 0; q < 32; ++q) {
+        const float s = (float)key_at(q);
+        const float m = __fdiv_rn(s, fn);
+        const float w = ((m - 255.0f) - 13.0f) + z3;
+        float c = __fdiv_rn(w - low, den);
+        c = fminf(fmaxf(c, 0.0f), 1.0f);
+        c = c * 254.0f;
+        c = fminf(fmaxf(c, 0.0f), 255.0f);
+        stage[sidx(out_index(q))] = c;
+    }
+    group_sync<C>(slot);
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+        const int o = t + i * G;
+        const float c = stage[sidx(o)];
+        if (kp.colour) kp.colour[row + o] = c;
+        if (kp.pixels) kp.pixels[row + o] = (uint8_t)__float2int_rn(c);
+    }
+    if (kp.spectrum) {                                                    // kiwi_waterfall.spectrum (optional output)
+        group_sync<C>(slot);
 #pragma unroll
-            for (int q = 0; q < RL; ++q) {
-                const unsigned pair = keys[i * (RL / 2) + (q >> 1)];
-                const float s = (float)((q & 1) ? (pair >> 16) : (pair & 0xffffu));
-                const int k = FFT_ORDER ? (idx + NCH * q) : (idx * RL + q);
-                const int o = FFT_ORDER ? (k ^ (N / 2)) : k;
-                const float m = __fdiv_rn(s, fn);
-                const float w = ((m - 255.0f) - 13.0f) + z3;
-                float c = __fdiv_rn(w - low, den);
-                c = fminf(fmaxf(c, 0.0f), 1.0f);
-                c = c * 254.0f;
-                c = fminf(fmaxf(c, 0.0f), 255.0f);
-                if (kp.spectrum) kp.spectrum[row + o] = (o == 0) ? __fdiv_rn((float)red[4], fn) : m;
-                if (kp.colour) kp.colour[row + o] = c;
-                if (kp.pixels) kp.pixels[row + o] = (uint8_t)__float2int_rn(c);
-            }
+        for (int q = 0; q < 32; ++q) {
+            const float s = (t == 0 && q == q0) ? (float)raw0 : (float)key_at(q);
+            stage[sidx(out_index(q))] = __fdiv_rn(s, fn);
+        }
+        group_sync<C>(slot);
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int o = t + i * G;
+            kp.spectrum[row + o] = stage[sidx(o)];
         }
     }
+    // the caller's next barrier (before the frame buffer is written again) orders these reads
 }
 
 // ---------------------------------------------------------------------------------------------
 // the fused waterfall kernel
 // ---------------------------------------------------------------------------------------------
 template <int LG, int FMT, bool WINDOW>
-__global__ void __launch_bounds__(Cfg<LG>::THREADS, (LG >= 13) ? 1 : 2)
+__global__ void __launch_bounds__(Cfg<LG>::THREADS, Cfg<LG>::MIN_CTAS)
 wf_fft_kernel(const WfKernelParams kp) {
     using C = Cfg<LG>;
     constexpr int N = C::N, G = C::G, FPC = C::FPC;
     extern __shared__ __align__(16) unsigned char smem[];
     float2* data = reinterpret_cast<float2*>(smem + C::SM_DATA);
-    uint16_t* accs = reinterpret_cast<uint16_t*>(smem + C::SM_ACC);
-    float2* tws = reinterpret_cast<float2*>(smem + C::SM_TW);
-    float* thr = reinterpret_cast<float*>(smem + C::SM_THR);
+    float2* tw0 = reinterpret_cast<float2*>(smem + C::SM_TW0);
+    float2* tw1 = reinterpret_cast<float2*>(smem + C::SM_TW1);
+    uint4* accs = reinterpret_cast<uint4*>(smem + C::SM_ACC) + threadIdx.x;
     int* reds = reinterpret_cast<int*>(smem + C::SM_RED);
 
     const int slot = threadIdx.x / G, t = threadIdx.x % G;
-    float2* d = data + (size_t)slot * N;
-    uint16_t* acc = accs + (size_t)slot * N;
+    float2* d = data + (size_t)slot * C::PADN;
     int* red = reds + slot * 8;
 
-    // one-time tables: thresholds and the exact-table twiddles of the small passes
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) thr[i] = kp.thr[i];
-    {
-        int L = N;
-#pragma unroll
-        for (int p = 0; p < C::NP; ++p) {
-            const int R = C::radix(p), M = L / R;
-            if (C::table_pass(p) && M > 1) {
-                float2* tw = tws + C::table_off(p);
-                for (int e = threadIdx.x; e < M * (R - 1); e += blockDim.x) {
-                    int q = e / M + 1, j = e - (q - 1) * M;
-                    tw[e] = kp.wtab[j * q * (N / L)];
-                }
-            }
-            L = M;
-        }
-    }
+    // one-time tables: twiddles of the table passes W_L^(j q), j < 32
+    for (int e = threadIdx.x; e < C::TW0; e += blockDim.x) { const int q = e / 32 + 1, j = e & 31; tw0[e] = kp.wtab[j * q]; }
+    for (int e = threadIdx.x; e < C::TW1; e += blockDim.x) { const int q = e / 32 + 1, j = e & 31; tw1[e] = kp.wtab[j * q * (N / 1024)]; }
     __syncthreads();
 
-    const int n_groups = (kp.batch + FPC - 1) / FPC;
-    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const int ch = g * FPC + slot;
-        const bool active = ch < kp.batch;
+    // (cos, -sin)(2 pi j / N) of this thread's first-pass butterflies (window + first twiddle level):
+    // loop invariant, parked in a thread-private shared-memory column (short, fixed latency)
+    float2* w1s = reinterpret_cast<float2*>(smem + C::SM_W1) + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < C::NB0; ++i) w1s[i * C::THREADS] = __ldg(kp.wtab + t + i * G);
+    auto w1_of = [&](int i) -> float2 { return w1s[i * C::THREADS]; };
+
+    constexpr unsigned sample_bytes = (FMT == SSDR_IQ_CF32) ? 8u : 4u;
+    const int ch_stride = (int)gridDim.x * FPC;
+    for (int ch = blockIdx.x * FPC + slot; ch < kp.batch; ch += ch_stride) {
+        float2 x0[C::R0];
+        size_t off = (size_t)ch * kp.n_avg * N;
+        first_load<C, FMT>(x0, 0, t, kp.iq, off);
+#pragma unroll 1
         for (int f = 0; f < kp.n_avg; ++f) {
-            const size_t off = ((size_t)ch * kp.n_avg + f) * N;
-            fft_all_passes<C, 0, FMT, WINDOW>(d, acc, tws, thr, t, kp.iq, off, kp, f == 0, active);
+            // the frame after next (or the first frame of this group's next channel) -> L2
+            if (t == 0) {
+                const bool last = (f + 1 == kp.n_avg);
+                const size_t nxt = last ? (size_t)(ch + ch_stride) * kp.n_avg * N : off + N;
+                if (!last || ch + ch_stride < kp.batch)
+                    prefetch_l2(static_cast<const unsigned char*>(kp.iq) + nxt * sample_bytes, (unsigned)N * sample_bytes);
+            }
+            group_sync<C>(slot);              // every thread of the group has finished reading the previous frame (or row)
+            if constexpr (C::NB0 == 1) {
+                first_compute<C, WINDOW>(x0, 0, d, tw0, t, w1_of(0));
+            } else {
+                // software pipeline over this thread's first-pass butterflies: load i + 1 while i computes
+                float2 xa[C::R0], xb[C::R0];
+#pragma unroll
+                for (int m = 0; m < C::R0; ++m) xa[m] = x0[m];
+#pragma unroll
+                for (int i = 0; i < C::NB0; i += 2) {
+                    first_load<C, FMT>(xb, i + 1, t, kp.iq, off);
+                    first_compute<C, WINDOW>(xa, i, d, tw0, t, w1_of(i));
+                    if (i + 2 < C::NB0) first_load<C, FMT>(xa, i + 2, t, kp.iq, off);
+                    first_compute<C, WINDOW>(xb, i + 1, d, tw0, t, w1_of(i + 1));
+                }
+            }
+            group_sync<C>(slot);
+            // from here each warp owns a contiguous 1024-point (NP == 3) / 32-point sub-transform: warp-local
+            if constexpr (C::NP == 3) {
+                pass_mid<C>(d, tw1, t);
+                __syncwarp();
+            }
+            pass_last<C>(d, t, accs, f == 0, kp);
+            off += N;
+            if (f + 1 < kp.n_avg) first_load<C, FMT>(x0, 0, t, kp.iq, off);
         }
-        colour_stage<C, true>(acc, red, t, ch, active, kp);
+        unsigned acc[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint4 a = accs[c * C::THREADS];
+            acc[4 * c] = a.x; acc[4 * c + 1] = a.y; acc[4 * c + 2] = a.z; acc[4 * c + 3] = a.w;
+        }
+        colour_stage<C, false>(reinterpret_cast<float*>(d), red, slot, t, ch, acc, kp);
     }
 }
 
@@ -440,30 +503,31 @@ wf_colorrow_kernel(const WfKernelParams kp) {
     using C = Cfg<LG>;
     constexpr int N = C::N, G = C::G, FPC = C::FPC;
     extern __shared__ __align__(16) unsigned char smem[];
-    uint16_t* accs = reinterpret_cast<uint16_t*>(smem);
-    int* reds = reinterpret_cast<int*>(smem + (size_t)FPC * N * sizeof(uint16_t));
+    float* stages = reinterpret_cast<float*>(smem);
+    int* reds = reinterpret_cast<int*>(smem + (size_t)FPC * C::PADN * sizeof(float));
     const int slot = threadIdx.x / G, t = threadIdx.x % G;
-    uint16_t* acc = accs + (size_t)slot * N;
+    float* stage = stages + (size_t)slot * C::PADN;
     int* red = reds + slot * 8;
-    const int n_groups = (kp.batch + FPC - 1) / FPC;
-    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const int ch = g * FPC + slot;
-        const bool active = ch < kp.batch;
-        __syncthreads();
-        if (active) {
-            // each thread sums 4 adjacent bins per step: coalesced 32-bit loads of the byte lines
-            for (int i = t * 4; i < N; i += G * 4) {
-                unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                for (int f = 0; f < kp.n_avg; ++f) {
-                    unsigned v = __ldcs(reinterpret_cast<const unsigned*>(kp.lines + ((size_t)ch * kp.n_avg + f) * N + i));
-                    s0 += v & 0xff; s1 += (v >> 8) & 0xff; s2 += (v >> 16) & 0xff; s3 += v >> 24;
+    for (int ch = blockIdx.x * FPC + slot; ch < kp.batch; ch += (int)gridDim.x * FPC) {
+        unsigned acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0u;
+        // thread t owns bins 32 t .. 32 t + 31: two 16-byte loads per line
+        for (int f = 0; f < kp.n_avg; ++f) {
+            const uint4* src = reinterpret_cast<const uint4*>(kp.lines + ((size_t)ch * kp.n_avg + f) * N + 32 * t);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint4 v = __ldg(src + h);
+                const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[h * 8 + 2 * k] += __byte_perm(w[k], 0u, 0x4140);       // bytes 0, 1 -> two uint16 lanes
+                    acc[h * 8 + 2 * k + 1] += __byte_perm(w[k], 0u, 0x4342);   // bytes 2, 3
                 }
-                unsigned* a32 = reinterpret_cast<unsigned*>(acc + i);
-                a32[0] = s0 | (s1 << 16);
-                a32[1] = s2 | (s3 << 16);
             }
         }
-        colour_stage<C, false>(acc, red, t, ch, active, kp);
+        group_sync<C>(slot);          // the previous row's transposed reads are done
+        colour_stage<C, true>(stage, red, slot, t, ch, acc, kp);
     }
 }
 
@@ -493,7 +557,7 @@ static int launch_fft(const WfKernelParams& kp, int fmt, int window, cudaStream_
 template <int LG>
 static int launch_colorrow(const WfKernelParams& kp, cudaStream_t st) {
     using C = Cfg<LG>;
-    const size_t smem = (size_t)C::FPC * C::N * sizeof(uint16_t) + (size_t)C::FPC * 8 * sizeof(int);
+    const size_t smem = (size_t)C::FPC * C::PADN * sizeof(float) + (size_t)C::FPC * 8 * sizeof(int);
     SSDR_CUDA(cudaFuncSetAttribute(wf_colorrow_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_groups = (kp.batch + C::FPC - 1) / C::FPC;
     int grid = sm_count() * 4;
@@ -519,6 +583,8 @@ int wf_launch(const WfLaunch& a, cudaStream_t st) {
     kp.pixels = a.pixels; kp.colour = a.colour; kp.spectrum = a.spectrum; kp.scalars = a.scalars;
     kp.lines = a.lines; kp.batch = a.batch; kp.n_avg = a.n_avg; kp.p_lo = a.p_lo; kp.p_gamma = a.p_gamma;
     kp.est_c1 = a.est_c1; kp.est_c0 = a.est_c0;
+    kp.key_bits = 1;
+    while ((1 << kp.key_bits) <= 255 * a.n_avg) ++kp.key_bits;
     const int lg = ilog2(a.nfft);
     if (a.lines) {
         switch (lg) {
