@@ -91,25 +91,50 @@ static inline cpx cmul(cpx u, cpx w) {
     return r;
 }
 static inline cpx mul_mi(cpx u) { cpx r = {u.im, -u.re}; return r; }                 /* * (-i)      */
-static inline cpx mul_w8(cpx u) { cpx r = {(u.re + u.im) * K_B, (u.im - u.re) * K_B}; return r; }   /* * B(1-i)  */
-static inline cpx mul_w83(cpx u) { cpx r = {(u.im - u.re) * K_B, (u.re + u.im) * (-K_B)}; return r; } /* * -B(1+i) */
+/* rotations by odd eighth turns are ordinary complex multiplies by the rounded constants */
+static inline cpx mul_w8(cpx u) { cpx w = {K_B, -K_B}; return cmul(u, w); }      /* * B(1-i)  = W8^1 */
+static inline cpx mul_w83(cpx u) { cpx w = {-K_B, -K_B}; return cmul(u, w); }    /* * -B(1+i) = W8^3 */
 
-static inline void dft2(cpx* x) { cpx a = x[0], b = x[1]; x[0] = cadd(a, b); x[1] = csub(a, b); }
-
-static inline void dft4(cpx* x) {
-    cpx a = cadd(x[0], x[2]), b = csub(x[0], x[2]);
-    cpx c = cadd(x[1], x[3]), d = mul_mi(csub(x[1], x[3]));
-    x[0] = cadd(a, c); x[2] = csub(a, c);
-    x[1] = cadd(b, d); x[3] = csub(b, d);
+/* ---- butterflies, DESIGN.md 4.2 -------------------------------------------------------------
+ * Every radix-r butterfly (natural order in and out) starts with the same first level,
+ *     (x[m], x[m + r/2]) <- (x[m] + x[m + r/2], x[m] - x[m + r/2]),   m < r/2,
+ * followed by dft_rest(r).  The first pass of the transform replaces that level by the windowed
+ * form l1_window(), which fuses the Hann multiply into it. */
+static void l1(cpx* x, int r) {
+    for (int m = 0; m < r / 2; ++m) {
+        cpx a = x[m], b = x[m + r / 2];
+        x[m] = cadd(a, b);
+        x[m + r / 2] = csub(a, b);
+    }
 }
 
-static void dft8(cpx* x) {
-    cpx u[2][4];
-    for (int m0 = 0; m0 < 4; ++m0) {
-        cpx t[2] = {x[m0], x[m0 + 4]};
-        dft2(t);
-        u[0][m0] = t[0]; u[1][m0] = t[1];
+/* x[m] <- x[m] w[m] + x[m+h] w[m+h],  x[m+h] <- x[m] w[m] - x[m+h] w[m+h]  with one rounded product
+ * p = x[m] w[m] and two fused multiply-adds (w real). */
+static void l1_window(cpx* x, int r, const float* w) {
+    int h = r / 2;
+    for (int m = 0; m < h; ++m) {
+        cpx a = x[m], b = x[m + h];
+        float pr = a.re * w[m], pi = a.im * w[m];
+        x[m].re = fmaf(b.re, w[m + h], pr);      x[m].im = fmaf(b.im, w[m + h], pi);
+        x[m + h].re = fmaf(b.re, -w[m + h], pr); x[m + h].im = fmaf(b.im, -w[m + h], pi);
     }
+}
+
+/* second level of a radix-4: in (a, c, b, e) = (x0+x2, x1+x3, x0-x2, x1-x3) at x[0], x[1], x[2], x[3] */
+static inline void dft4_rest(cpx* x0, cpx* x1, cpx* x2, cpx* x3) {
+    cpx a = *x0, c = *x1, b = *x2, d = mul_mi(*x3);
+    *x0 = cadd(a, c); *x2 = csub(a, c);
+    *x1 = cadd(b, d); *x3 = csub(b, d);
+}
+
+static inline void dft4(cpx* x) {
+    l1(x, 4);
+    dft4_rest(&x[0], &x[1], &x[2], &x[3]);
+}
+
+static void dft8_rest(cpx* x) {              /* after l1: x[0..3] sums, x[4..7] differences */
+    cpx u[2][4];
+    for (int m0 = 0; m0 < 4; ++m0) { u[0][m0] = x[m0]; u[1][m0] = x[m0 + 4]; }
     u[1][1] = mul_w8(u[1][1]);
     u[1][2] = mul_mi(u[1][2]);
     u[1][3] = mul_w83(u[1][3]);
@@ -119,12 +144,13 @@ static void dft8(cpx* x) {
     }
 }
 
-static void dft16(cpx* x) {
+static void dft16_rest(cpx* x) {             /* after l1 on pairs (m, m + 8) */
     cpx u[4][4];   /* u[p][m0] */
     const cpx w1 = {K_A, -K_C}, w3 = {K_C, -K_A}, w9 = {-K_A, K_C};
     for (int m0 = 0; m0 < 4; ++m0) {
+        /* radix-4 across (m0, m0+4, m0+8, m0+12): level 1 is done, pairs (m0, m0+8) and (m0+4, m0+12) */
         cpx t[4] = {x[m0], x[m0 + 4], x[m0 + 8], x[m0 + 12]};
-        dft4(t);
+        dft4_rest(&t[0], &t[1], &t[2], &t[3]);
         for (int p = 0; p < 4; ++p) u[p][m0] = t[p];
     }
     /* internal twiddles W16^(m0*p) */
@@ -139,11 +165,11 @@ static void dft16(cpx* x) {
 
 /* 32 = 4 x 8: radix-4 across m1 (m = m0 + 8 m1), twiddle W32^(m0 p), radix-8 across m0; q = p + 4 s.
  * W32^e = (cos, -sin)(2 pi e / 32) from the unit32 constants; e == 8 is the exact rotation by -i. */
-static void dft32(cpx* x) {
+static void dft32_rest(cpx* x) {             /* after l1 on pairs (m, m + 16) */
     cpx u[4][8];   /* u[p][m0] */
     for (int m0 = 0; m0 < 8; ++m0) {
         cpx t[4] = {x[m0], x[m0 + 8], x[m0 + 16], x[m0 + 24]};
-        dft4(t);
+        dft4_rest(&t[0], &t[1], &t[2], &t[3]);
         for (int p = 0; p < 4; ++p) u[p][m0] = t[p];
     }
     for (int p = 1; p < 4; ++p)
@@ -156,9 +182,18 @@ static void dft32(cpx* x) {
             u[p][m0] = cmul(u[p][m0], w);
         }
     for (int p = 0; p < 4; ++p) {
-        dft8(u[p]);
+        l1(u[p], 8);
+        dft8_rest(u[p]);
         for (int s = 0; s < 8; ++s) x[p + 4 * s] = u[p][s];
     }
+}
+
+static void dft_rest(cpx* x, int r) {
+    if (r == 32) dft32_rest(x);
+    else if (r == 16) dft16_rest(x);
+    else if (r == 8) dft8_rest(x);
+    else if (r == 4) dft4_rest(&x[0], &x[1], &x[2], &x[3]);
+    /* r == 2: the first level is the whole butterfly */
 }
 
 /* Twiddles of a "chain" pass: output q = 4a + b of a radix-r butterfly is multiplied
@@ -182,7 +217,7 @@ static void tw_two_level(cpx* x, int r, cpx w1) {
 #define SO_TABLE_PASS_MAX 1024   /* a pass uses exact table twiddles iff (L/r)*(r-1) <= this */
 
 /* In-place mixed-radix DIF FFT on d[0..N); output in digit-reversed order. */
-static void fft_dif(cpx* d, int N, const int* radices, int np, const float* tab) {
+static void fft_dif(cpx* d, int N, const int* radices, int np, const float* tab, int window) {
     int L = N;
     for (int p = 0; p < np; ++p) {
         int r = radices[p], M = L / r, step = N / L;
@@ -191,7 +226,22 @@ static void fft_dif(cpx* d, int N, const int* radices, int np, const float* tab)
             for (int j = 0; j < M; ++j) {
                 cpx x[32], w[32];
                 for (int m = 0; m < r; ++m) x[m] = d[base + j + m * M];
-                if (r == 32) dft32(x); else if (r == 16) dft16(x); else if (r == 8) dft8(x); else if (r == 4) dft4(x); else dft2(x);
+                if (p == 0 && window) {
+                    /* Hann values of the r samples j + m M: 0.5 - 0.5 cos(theta_j + 2 pi m / r)
+                     * from (cos, -sin)(theta_j) = tab[j] and the unit32 constants, fused into the first level */
+                    float wv[32], c = tab[2 * j], dd = tab[2 * j + 1];
+                    for (int m = 0; m < r; ++m) {
+                        float C, S;
+                        unit32(m * (32 / r), &C, &S);
+                        float t = dd * S;
+                        float cm = fmaf(c, C, t);
+                        wv[m] = fmaf(-0.5f, cm, 0.5f);
+                    }
+                    l1_window(x, r, wv);
+                } else {
+                    l1(x, r);
+                }
+                dft_rest(x, r);
                 if (M > 1) {
                     if (use_table) {
                         for (int q = 1; q < r; ++q) {
@@ -233,24 +283,6 @@ static inline uint8_t quantise(float P, const float* T) {
     return (uint8_t)lo;
 }
 
-/* Window (first-pass form): w[j + m*M0] = 0.5 - 0.5*cos(theta_j + 2*pi*m/r0) evaluated from
- * Wtab[j] and the unit32 constants, DESIGN.md 4.1. */
-static void apply_window(cpx* d, int N, int r0, const float* tab) {
-    int M0 = N / r0;
-    for (int j = 0; j < M0; ++j) {
-        float c = tab[2 * j], dd = tab[2 * j + 1];       /* cos(theta_j), -sin(theta_j) */
-        for (int m = 0; m < r0; ++m) {
-            float C, S;
-            unit32(m * (32 / r0), &C, &S);
-            float t = dd * S;
-            float cm = fmaf(c, C, t);                    /* cos(theta_j + phi_m) */
-            float w = fmaf(-0.5f, cm, 0.5f);
-            cpx* e = &d[j + m * M0];
-            e->re = e->re * w; e->im = e->im * w;
-        }
-    }
-}
-
 /* One frame: interleaved float32 IQ[N] -> Kiwi bytes[N], fftshifted (bin 0 = lowest frequency).
  * If spec_out != NULL also returns the raw FFT (natural order) for diagnostics. */
 int so_wf_frame_bytes(const float* iq, int N, int window, double cal_db, uint8_t* bytes, float* spec_out) {
@@ -263,8 +295,7 @@ int so_wf_frame_bytes(const float* iq, int N, int window, double cal_db, uint8_t
     so_twiddle_table(N, tab);
     so_thresholds(N, cal_db, T);
     memcpy(d, iq, sizeof(cpx) * (size_t)N);
-    if (window) apply_window(d, N, radices[0], tab);
-    fft_dif(d, N, radices, np, tab);
+    fft_dif(d, N, radices, np, tab, window);
     for (int pos = 0; pos < N; ++pos) {
         int k = pos_to_bin(pos, N, radices, np);
         float t = d[pos].im * d[pos].im;

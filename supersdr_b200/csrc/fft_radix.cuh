@@ -43,13 +43,36 @@ SSDR_DEV float2 cmul(float2 u, float2 w) {
     return __ffma2_rn(make_float2(u.x, u.x), w, make_float2(-t.x, t.y));
 }
 SSDR_DEV float2 mul_mi(float2 u) { return make_float2(u.y, -u.x); }                      // * (-i), exact
-SSDR_DEV float2 mul_w8(float2 u) {                                                       // * B(1-i)
-    const float2 s = __fadd2_rn(u, make_float2(u.y, -u.x));                              // {re+im, im-re}
-    return __fmul2_rn(s, make_float2(kB, kB));
+// Odd eighth turns are ordinary complex multiplies by the rounded constants.  (A separate scale by B
+// after an add would be an FMUL2 feeding FADD2s, which ptxas contracts into FFMA2 even for mul.rn /
+// add.rn -- one rounding less than the spec.  Every multiply in this file therefore feeds an explicit
+// fused multiply-add addend, where no further contraction is possible.)
+SSDR_DEV float2 mul_w8(float2 u) { return cmul(u, make_float2(kB, -kB)); }               // * B(1-i)  = W8^1
+SSDR_DEV float2 mul_w83(float2 u) { return cmul(u, make_float2(-kB, -kB)); }             // * -B(1+i) = W8^3
+
+// ---- first butterfly level: (x[m], x[m + R/2]) <- (sum, difference), m < R/2 ------------------------
+template <int R>
+SSDR_DEV void l1(float2 (&x)[R]) {
+#pragma unroll
+    for (int m = 0; m < R / 2; ++m) {
+        const float2 a = x[m], b = x[m + R / 2];
+        x[m] = cadd(a, b);
+        x[m + R / 2] = csub(a, b);
+    }
 }
-SSDR_DEV float2 mul_w83(float2 u) {                                                      // * -B(1+i)
-    const float2 s = __fadd2_rn(make_float2(u.y, u.x), make_float2(-u.x, u.y));          // {im-re, re+im}
-    return __fmul2_rn(s, make_float2(kB, -kB));
+
+// Windowed first level (first pass only): with real weights w, one rounded product p = x[m] w[m] and
+// two fused multiply-adds  x[m] <- fma(x[m+h], w[m+h], p),  x[m+h] <- fma(x[m+h], -w[m+h], p).
+template <int R>
+SSDR_DEV void l1_window(float2 (&x)[R], const float (&w)[R]) {
+    constexpr int H = R / 2;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        const float2 b = x[m + H];
+        const float2 p = __fmul2_rn(x[m], make_float2(w[m], w[m]));
+        x[m] = __ffma2_rn(b, make_float2(w[m + H], w[m + H]), p);
+        x[m + H] = __ffma2_rn(b, make_float2(-w[m + H], -w[m + H]), p);
+    }
 }
 
 SSDR_DEV void dft2(float2& x0, float2& x1) {
@@ -58,18 +81,24 @@ SSDR_DEV void dft2(float2& x0, float2& x1) {
     x1 = csub(a, b);
 }
 
-SSDR_DEV void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
-    const float2 a = cadd(x0, x2), b = csub(x0, x2);
-    const float2 c = cadd(x1, x3), e = csub(x1, x3);
+// second level of a radix-4: in (a, c, b, e) = (x0+x2, x1+x3, x0-x2, x1-x3) at (x0, x1, x2, x3)
+SSDR_DEV void dft4_rest(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 a = x0, c = x1, b = x2, e = x3;
     x0 = cadd(a, c);
     x2 = csub(a, c);
     x1 = __fadd2_rn(b, make_float2(e.y, -e.x));    // b + (-i) e
     x3 = __fadd2_rn(b, make_float2(-e.y, e.x));    // b - (-i) e
 }
 
-// natural order in, natural order out
-SSDR_DEV void dft8(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4, float2& x5, float2& x6, float2& x7) {
-    dft2(x0, x4); dft2(x1, x5); dft2(x2, x6); dft2(x3, x7);
+SSDR_DEV void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 a = cadd(x0, x2), b = csub(x0, x2);
+    const float2 c = cadd(x1, x3), e = csub(x1, x3);
+    x0 = a; x1 = c; x2 = b; x3 = e;
+    dft4_rest(x0, x1, x2, x3);
+}
+
+// after the first level: x0..x3 sums, x4..x7 differences; natural order out
+SSDR_DEV void dft8_rest(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4, float2& x5, float2& x6, float2& x7) {
     x5 = mul_w8(x5);
     x6 = mul_mi(x6);
     x7 = mul_w83(x7);
@@ -79,24 +108,24 @@ SSDR_DEV void dft8(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4, f
     x1 = y1; x2 = y2; x3 = y3; x4 = y4; x5 = y5; x6 = y6;
 }
 
-// Natural-order in, natural-order out: x[q] = sum_m x[m] W_R^(m q).
+// Remainder of a radix-R butterfly after its first level; natural order out: x[q] = sum_m x[m] W_R^(m q).
 template <int R>
-SSDR_DEV void dft(float2 (&x)[R]);
+SSDR_DEV void dft_rest(float2 (&x)[R]);
 
 template <>
-SSDR_DEV void dft<2>(float2 (&x)[2]) { dft2(x[0], x[1]); }
+SSDR_DEV void dft_rest<2>(float2 (&x)[2]) {}
 
 template <>
-SSDR_DEV void dft<4>(float2 (&x)[4]) { dft4(x[0], x[1], x[2], x[3]); }
+SSDR_DEV void dft_rest<4>(float2 (&x)[4]) { dft4_rest(x[0], x[1], x[2], x[3]); }
 
 template <>
-SSDR_DEV void dft<8>(float2 (&x)[8]) { dft8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]); }
+SSDR_DEV void dft_rest<8>(float2 (&x)[8]) { dft8_rest(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]); }
 
 template <>
-SSDR_DEV void dft<16>(float2 (&x)[16]) {
-    // stage 1: for each m0, radix-4 across (m0, m0+4, m0+8, m0+12); result p lives in x[m0 + 4p]
+SSDR_DEV void dft_rest<16>(float2 (&x)[16]) {
+    // radix-4 across (m0, m0+4, m0+8, m0+12) with its first level (pairs m, m + 8) done; result p in x[m0 + 4p]
 #pragma unroll
-    for (int m0 = 0; m0 < 4; ++m0) dft4(x[m0], x[m0 + 4], x[m0 + 8], x[m0 + 12]);
+    for (int m0 = 0; m0 < 4; ++m0) dft4_rest(x[m0], x[m0 + 4], x[m0 + 8], x[m0 + 12]);
     // internal twiddles W16^(m0*p), u[p][m0] = x[m0 + 4p]
     const float2 w1 = make_float2(kA, -kC), w3 = make_float2(kC, -kA), w9 = make_float2(-kA, kC);
     x[5] = cmul(x[5], w1);   x[6] = mul_w8(x[6]);    x[7] = cmul(x[7], w3);
@@ -115,11 +144,11 @@ SSDR_DEV void dft<16>(float2 (&x)[16]) {
 }
 
 template <>
-SSDR_DEV void dft<32>(float2 (&x)[32]) {
-    // 32 = 4 x 8, m = m0 + 8 m1.  stage 1: radix-4 across m1; result p lives in x[m0 + 8p]
+SSDR_DEV void dft_rest<32>(float2 (&x)[32]) {
+    // 32 = 4 x 8, m = m0 + 8 m1.  radix-4 across m1 with its first level (pairs m, m + 16) done; result p in x[m0 + 8p]
 #pragma unroll
-    for (int m0 = 0; m0 < 8; ++m0) dft4(x[m0], x[m0 + 8], x[m0 + 16], x[m0 + 24]);
-    // internal twiddles W32^(m0*p); exponent 8 is the exact rotation by -i
+    for (int m0 = 0; m0 < 8; ++m0) dft4_rest(x[m0], x[m0 + 8], x[m0 + 16], x[m0 + 24]);
+    // internal twiddles W32^(m0*p)
 #pragma unroll
     for (int p = 1; p < 4; ++p)
 #pragma unroll
@@ -136,8 +165,10 @@ SSDR_DEV void dft<32>(float2 (&x)[32]) {
         }
     // stage 2: radix-8 across m0 for each p; output s lives in x[8p + s] -> q = p + 4s
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
-        dft8(x[8 * p], x[8 * p + 1], x[8 * p + 2], x[8 * p + 3], x[8 * p + 4], x[8 * p + 5], x[8 * p + 6], x[8 * p + 7]);
+    for (int p = 0; p < 4; ++p) {
+        dft2(x[8 * p], x[8 * p + 4]); dft2(x[8 * p + 1], x[8 * p + 5]); dft2(x[8 * p + 2], x[8 * p + 6]); dft2(x[8 * p + 3], x[8 * p + 7]);
+        dft8_rest(x[8 * p], x[8 * p + 1], x[8 * p + 2], x[8 * p + 3], x[8 * p + 4], x[8 * p + 5], x[8 * p + 6], x[8 * p + 7]);
+    }
     float2 y[32];
 #pragma unroll
     for (int p = 0; p < 4; ++p)
@@ -145,6 +176,12 @@ SSDR_DEV void dft<32>(float2 (&x)[32]) {
         for (int s = 0; s < 8; ++s) y[p + 4 * s] = x[8 * p + s];
 #pragma unroll
     for (int q = 0; q < 32; ++q) x[q] = y[q];
+}
+
+template <int R>
+SSDR_DEV void dft(float2 (&x)[R]) {
+    l1<R>(x);
+    dft_rest<R>(x);
 }
 
 // Twiddles of a "chain" pass: output q = 4a + b is multiplied by W^(j q) as

@@ -167,19 +167,24 @@ SSDR_DEV void first_compute(float2 (&x)[C::R0], int i, float2* d, const float2* 
     constexpr bool TABLE = (M == 32);
     const int j = t + i * G;
     if constexpr (WINDOW) {
-        // w[j + m M] = 0.5 - 0.5 cos(theta_j + 2 pi m / R) from wtab[j] and the unit32 constants
+        // w[j + m M] = 0.5 - 0.5 cos(theta_j + 2 pi m / R) from wtab[j] and the unit32 constants,
+        // fused into the first butterfly level
+        float wv[R];
         const float2 cc = make_float2(w1.x, w1.x), dd = make_float2(w1.y, w1.y);
 #pragma unroll
         for (int m = 0; m < R; m += 2) {
             const int e0 = m * (32 / R), e1 = (m + 1) * (32 / R);
             const float2 tt = __fmul2_rn(dd, make_float2(unit32_sin(e0), unit32_sin(e1)));
             const float2 cm = __ffma2_rn(cc, make_float2(unit32_cos(e0), unit32_cos(e1)), tt);
-            const float2 wv = __ffma2_rn(make_float2(-0.5f, -0.5f), cm, make_float2(0.5f, 0.5f));
-            x[m] = __fmul2_rn(x[m], make_float2(wv.x, wv.x));
-            x[m + 1] = __fmul2_rn(x[m + 1], make_float2(wv.y, wv.y));
+            const float2 w2 = __ffma2_rn(make_float2(-0.5f, -0.5f), cm, make_float2(0.5f, 0.5f));
+            wv[m] = w2.x;
+            wv[m + 1] = w2.y;
         }
+        l1_window<R>(x, wv);
+    } else {
+        l1<R>(x);
     }
-    dft<R>(x);
+    dft_rest<R>(x);
     if constexpr (TABLE) {
 #pragma unroll
         for (int q = 1; q < R; ++q) x[q] = cmul(x[q], tw0[(q - 1) * 32 + j]);

@@ -44,8 +44,10 @@ def test_kiwi_waterfall_dropin(ssdr):
         assert np.array_equal(wf.spectrum, spec) and np.array_equal(wf.wf_color, col)
         assert np.float32(wf.wf_min_db) == st.wf_min_db and np.float32(wf.wf_max_db) == st.wf_max_db
         rows.append(col)
-    # scroll buffer semantics utils:893-897: 3-line delay, newest on top
-    assert np.array_equal(wf.wf_data[0], rows[2].astype(np.float64)) and np.array_equal(wf.wf_data[2], rows[0])
+    # scroll buffer semantics utils:893-897: a 3-deep delay deque (maxlen 3: the very first row falls off
+    # its far end on the 4th line), scrolling starts with the 4th line, newest on top
+    assert np.array_equal(wf.wf_data[0], rows[3].astype(np.float64)) and np.array_equal(wf.wf_data[1], rows[2])
+    assert np.array_equal(wf.wf_data[2], rows[1]) and not wf.wf_data[3].any()
     assert src.keepalives == 24
     assert not wf.run_once() and wf.terminate            # stream ended
     assert wf.change_passband(10, -20) == (40, 2980)     # USB defaults utils:859-862

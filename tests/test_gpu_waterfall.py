@@ -40,6 +40,32 @@ def test_waterfall_bit_exact_vs_c_oracle(ssdr, N, B, n):
     bank.close()
 
 
+@pytest.mark.parametrize("N,window", [(256, True), (512, False), (1024, True), (1024, False), (2048, True),
+                                      (4096, True), (8192, False), (16384, True), (16384, False)])
+def test_waterfall_rounding_noise_is_bit_exact(ssdr, N, window):
+    """Adversarial for last-bit differences: one strong tone on an EXACT bin (optionally a second weak
+    one) and no noise.  Every other bin then holds pure float32 rounding noise, which is reproduced only
+    if every operation (and every fused / unfused rounding) happens exactly as the spec states."""
+    B, n = 12, 2
+    rng = np.random.default_rng(N)
+    t = np.arange(n * N)
+    iq = np.empty((B, n, N), np.complex64)
+    for b in range(B):
+        k1, k2 = rng.integers(0, N, 2)
+        x = 0.5 * np.exp(2j * np.pi * (k1 * t / N + rng.uniform()))
+        if b % 3 == 1:
+            x = x + 1e-3 * np.exp(2j * np.pi * (k2 * t / N + rng.uniform()))
+        if b % 3 == 2:
+            x = np.rint(x * 32768) / 32768                       # integer counts, as a real int16 stream
+        iq[b] = (x * 32768).astype(np.complex64).reshape(n, N)
+    bank = ssdr.WaterfallBank(N, B, n, window=window)
+    res = bank.process(iq)
+    ref = c_oracle.wf_rows(iq, window=window, threads=8)
+    assert np.array_equal(res["spectrum"], ref["spectrum"])
+    assert np.array_equal(res["pixels"], ref["pixels"])
+    bank.close()
+
+
 def test_config1_single_1024_frame_golden_and_float64(ssdr):
     """BASELINE config 1: one 1024-pt frame.  Golden fixture + boundary-aware check vs float64."""
     g = np.load(os.path.join(GOLD, "tier_u_waterfall.npz"))
