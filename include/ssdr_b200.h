@@ -119,6 +119,8 @@ int ssdr_wf_set_display(ssdr_wf_t h, int first_channel, int count, const ssdr_wf
 /* Spec tables the handle uses (for parity tests): twiddles float32[2*nfft], thresholds float32[256],
  * radix plan (returns number of passes). */
 int ssdr_wf_get_tables(ssdr_wf_t h, float* twiddles, float* thresholds, int* radices);
+/* First half of the periodic Hann window the handle uses, float32[nfft/2]. */
+int ssdr_wf_get_window(ssdr_wf_t h, float* window_half);
 
 /* One row per channel from HOST IQ [batch][n_avg][nfft]: H2D copy (pipelined in channel chunks
  * on the handle's streams), kernel, D2H of the requested outputs (NULL = not wanted):

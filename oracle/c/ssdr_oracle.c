@@ -70,6 +70,12 @@ void so_twiddle_table(int N, float* tab) {
     }
 }
 
+/* First half of the periodic Hann window, w[n] = float(0.5 - 0.5 cos(2 pi n / N)), n < N/2 */
+void so_window_table(int N, float* win) {
+    for (int n = 0; n < N / 2; ++n)
+        win[n] = (float)(0.5 - 0.5 * cos(2.0 * SO_PI * (double)n / (double)N));
+}
+
 /* byte >= k  <=>  P >= T[k], k = 1..255;  T[0] = 0 */
 void so_thresholds(int N, double cal_db, float* T) {
     double ref = ((double)N * SO_FS * 0.5);
@@ -108,15 +114,18 @@ static void l1(cpx* x, int r) {
     }
 }
 
-/* x[m] <- x[m] w[m] + x[m+h] w[m+h],  x[m+h] <- x[m] w[m] - x[m+h] w[m+h]  with one rounded product
- * p = x[m] w[m] and two fused multiply-adds (w real). */
+/* Windowed first level (first pass of the transform only).  The pair (x[m], x[m+h]) are the samples
+ * n and n + N/2 of the frame; the periodic Hann window satisfies w[n + N/2] = 1 - w[n], so with w = w[n]
+ *     x[m]   <- x[m] w + x[m+h] (1 - w) = fma(x[m] - x[m+h], w,  x[m+h])
+ *     x[m+h] <- x[m] w - x[m+h] (1 - w) = fma(x[m] + x[m+h], w, -x[m+h])
+ * (one rounded add / subtract and one fused multiply-add per output). */
 static void l1_window(cpx* x, int r, const float* w) {
     int h = r / 2;
     for (int m = 0; m < h; ++m) {
         cpx a = x[m], b = x[m + h];
-        float pr = a.re * w[m], pi = a.im * w[m];
-        x[m].re = fmaf(b.re, w[m + h], pr);      x[m].im = fmaf(b.im, w[m + h], pi);
-        x[m + h].re = fmaf(b.re, -w[m + h], pr); x[m + h].im = fmaf(b.im, -w[m + h], pi);
+        float dr = a.re - b.re, di = a.im - b.im, sr = a.re + b.re, si = a.im + b.im;
+        x[m].re = fmaf(dr, w[m], b.re);      x[m].im = fmaf(di, w[m], b.im);
+        x[m + h].re = fmaf(sr, w[m], -b.re); x[m + h].im = fmaf(si, w[m], -b.im);
     }
 }
 
@@ -217,7 +226,8 @@ static void tw_two_level(cpx* x, int r, cpx w1) {
 #define SO_TABLE_PASS_MAX 1024   /* a pass uses exact table twiddles iff (L/r)*(r-1) <= this */
 
 /* In-place mixed-radix DIF FFT on d[0..N); output in digit-reversed order. */
-static void fft_dif(cpx* d, int N, const int* radices, int np, const float* tab, int window) {
+static void fft_dif(cpx* d, int N, const int* radices, int np, const float* tab, const float* win) {
+    int window = (win != NULL);
     int L = N;
     for (int p = 0; p < np; ++p) {
         int r = radices[p], M = L / r, step = N / L;
@@ -227,16 +237,9 @@ static void fft_dif(cpx* d, int N, const int* radices, int np, const float* tab,
                 cpx x[32], w[32];
                 for (int m = 0; m < r; ++m) x[m] = d[base + j + m * M];
                 if (p == 0 && window) {
-                    /* Hann values of the r samples j + m M: 0.5 - 0.5 cos(theta_j + 2 pi m / r)
-                     * from (cos, -sin)(theta_j) = tab[j] and the unit32 constants, fused into the first level */
-                    float wv[32], c = tab[2 * j], dd = tab[2 * j + 1];
-                    for (int m = 0; m < r; ++m) {
-                        float C, S;
-                        unit32(m * (32 / r), &C, &S);
-                        float t = dd * S;
-                        float cm = fmaf(c, C, t);
-                        wv[m] = fmaf(-0.5f, cm, 0.5f);
-                    }
+                    /* Hann values of the first r/2 samples j + m M (all < N/2) from the window table */
+                    float wv[16];
+                    for (int m = 0; m < r / 2; ++m) wv[m] = win[j + m * M];
                     l1_window(x, r, wv);
                 } else {
                     l1(x, r);
@@ -291,11 +294,13 @@ int so_wf_frame_bytes(const float* iq, int N, int window, double cal_db, uint8_t
     if (np < 0) return -1;
     float* tab = (float*)malloc(sizeof(float) * 2 * (size_t)N);
     cpx* d = (cpx*)malloc(sizeof(cpx) * (size_t)N);
+    float* win = (float*)malloc(sizeof(float) * (size_t)(N / 2));
     float T[256];
     so_twiddle_table(N, tab);
+    so_window_table(N, win);
     so_thresholds(N, cal_db, T);
     memcpy(d, iq, sizeof(cpx) * (size_t)N);
-    fft_dif(d, N, radices, np, tab, window);
+    fft_dif(d, N, radices, np, tab, window ? win : NULL);
     for (int pos = 0; pos < N; ++pos) {
         int k = pos_to_bin(pos, N, radices, np);
         float t = d[pos].im * d[pos].im;
@@ -303,8 +308,24 @@ int so_wf_frame_bytes(const float* iq, int N, int window, double cal_db, uint8_t
         bytes[(k + N / 2) & (N - 1)] = quantise(P, T);
         if (spec_out) { spec_out[2 * k] = d[pos].re; spec_out[2 * k + 1] = d[pos].im; }
     }
-    free(d); free(tab);
+    free(d); free(tab); free(win);
     return 0;
+}
+
+/* The kernel divides by loop-invariant divisors with Markstein's sequence (r = RN(1/b); q0 = RN(a r);
+ * e = fma(-q0, b, a); q = fma(e, r, q0)); this restates it so that tests can compare it with IEEE division.
+ * Returns the number of (a[i], b) pairs whose result differs from a[i] / b. */
+int so_markstein_mismatches(const float* a, int n, float b) {
+    volatile float r = 1.0f / b;
+    int bad = 0;
+    for (int i = 0; i < n; ++i) {
+        float q0 = a[i] * r;
+        float e = fmaf(-q0, b, a[i]);
+        float q = fmaf(e, r, q0);
+        float ref = a[i] / b;
+        if (memcmp(&q, &ref, sizeof(float)) != 0) ++bad;
+    }
+    return bad;
 }
 
 /* ---- Tier-P tail in strict float32 (restates oracle/tier_p.py; utils_supersdr.py:787-813) --- */

@@ -43,6 +43,8 @@ def lib():
                                     C.c_void_p, C.c_void_p]
         _lib.so_twiddle_table.argtypes = [C.c_int, C.c_void_p]
         _lib.so_thresholds.argtypes = [C.c_int, C.c_double, C.c_void_p]
+        _lib.so_window_table.argtypes = [C.c_int, C.c_void_p]
+        _lib.so_markstein_mismatches.argtypes = [C.c_void_p, C.c_int, C.c_float]
         _lib.so_play_buffer.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p,
                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.so_colour_row.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ColourT),
@@ -66,6 +68,17 @@ def twiddle_table(N):
     t = np.empty(2 * N, np.float32)
     lib().so_twiddle_table(N, _p(t))
     return t.view(np.complex64)
+
+
+def window_table(N):
+    w = np.empty(N // 2, np.float32)
+    lib().so_window_table(N, _p(w))
+    return w
+
+
+def markstein_mismatches(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return lib().so_markstein_mismatches(_p(a), a.size, float(np.float32(b)))
 
 
 def thresholds(N, cal_db):

@@ -67,6 +67,7 @@ _PROTOS = {
     "ssdr_wf_destroy": (_i, [_vp]),
     "ssdr_wf_set_display": (_i, [_vp, _i, _i, C.POINTER(WfDisplay)]),
     "ssdr_wf_get_tables": (_i, [_vp, _vp, _vp, C.POINTER(_i)]),
+    "ssdr_wf_get_window": (_i, [_vp, _vp]),
     "ssdr_wf_process": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "ssdr_wf_process_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "ssdr_wf_colorrow_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -60,8 +60,9 @@ struct ssdr_wf {
     float p_gamma = 0.f;
     double cal_db = 0.0;
     float est_c1 = 0.f, est_c0 = 0.f;
-    std::vector<float> h_wtab, h_thr;
+    std::vector<float> h_wtab, h_thr, h_win;
     float* d_wtab = nullptr;
+    float* d_win = nullptr;
     float* d_thr = nullptr;
     ssdr_wf_display_t* d_disp = nullptr;
     cudaStream_t compute = nullptr, copy = nullptr;
@@ -186,6 +187,9 @@ int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, d
         h->h_wtab[2 * k] = (float)std::cos(a);
         h->h_wtab[2 * k + 1] = (float)(-std::sin(a));
     }
+    h->h_win.resize((size_t)nfft / 2);          // first half of the periodic Hann window
+    for (int n = 0; n < nfft / 2; ++n)
+        h->h_win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * 3.14159265358979323846 * (double)n / (double)nfft));
     h->h_thr.resize(257);
     double ref = (double)nfft * 32768.0 * 0.5;
     ref = ref * ref;
@@ -198,9 +202,11 @@ int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, d
     auto fail = [&](int code) { ssdr_wf_destroy(h); return code; };
     if ((rc = dev_alloc(&h->d_wtab, 2 * (size_t)nfft))) return fail(rc);
     if ((rc = dev_alloc(&h->d_thr, 257))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_win, (size_t)nfft / 2))) return fail(rc);
     if ((rc = dev_alloc(&h->d_disp, (size_t)batch))) return fail(rc);
     if ((rc = dev_alloc(&h->d_sc, (size_t)batch))) return fail(rc);
     if (cudaMemcpy(h->d_wtab, h->h_wtab.data(), sizeof(float) * 2 * nfft, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->d_win, h->h_win.data(), sizeof(float) * (nfft / 2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->d_thr, h->h_thr.data(), sizeof(float) * 257, cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("table upload failed");
         return fail(SSDR_E_CUDA);
@@ -223,7 +229,7 @@ int ssdr_wf_destroy(ssdr_wf_t h) {
     if (!h) return SSDR_OK;
     if (h->compute) cudaStreamSynchronize(h->compute);
     if (h->copy) cudaStreamSynchronize(h->copy);
-    cudaFree(h->d_wtab); cudaFree(h->d_thr); cudaFree(h->d_disp); cudaFree(h->d_in[0]); cudaFree(h->d_in[1]);
+    cudaFree(h->d_wtab); cudaFree(h->d_win); cudaFree(h->d_thr); cudaFree(h->d_disp); cudaFree(h->d_in[0]); cudaFree(h->d_in[1]);
     cudaFree(h->d_px); cudaFree(h->d_col); cudaFree(h->d_spec); cudaFree(h->d_sc);
     for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -252,9 +258,15 @@ int ssdr_wf_get_tables(ssdr_wf_t h, float* twiddles, float* thresholds, int* rad
     return np;
 }
 
+int ssdr_wf_get_window(ssdr_wf_t h, float* window_half) {
+    SSDR_ARG(h && window_half, "null argument");
+    std::memcpy(window_half, h->h_win.data(), sizeof(float) * (size_t)(h->nfft / 2));
+    return SSDR_OK;
+}
+
 static WfLaunch wf_base(ssdr_wf_t h) {
     WfLaunch a;
-    a.wtab = h->d_wtab; a.thr = h->d_thr; a.nfft = h->nfft; a.n_avg = h->n_avg; a.window = h->window;
+    a.wtab = h->d_wtab; a.win = h->d_win; a.thr = h->d_thr; a.nfft = h->nfft; a.n_avg = h->n_avg; a.window = h->window;
     a.p_lo = h->p_lo; a.p_gamma = h->p_gamma; a.est_c1 = h->est_c1; a.est_c0 = h->est_c0;
     return a;
 }

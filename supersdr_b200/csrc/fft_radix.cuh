@@ -61,17 +61,20 @@ SSDR_DEV void l1(float2 (&x)[R]) {
     }
 }
 
-// Windowed first level (first pass only): with real weights w, one rounded product p = x[m] w[m] and
-// two fused multiply-adds  x[m] <- fma(x[m+h], w[m+h], p),  x[m+h] <- fma(x[m+h], -w[m+h], p).
+// Windowed first level (first pass only).  The pair (x[m], x[m+H]) are the samples n and n + N/2 of the
+// frame and the periodic Hann window satisfies w[n + N/2] = 1 - w[n], so with w = w[n]
+//     x[m]   <- fma(x[m] - x[m+H], w,  x[m+H])   ( = x[m] w + x[m+H] (1 - w) )
+//     x[m+H] <- fma(x[m] + x[m+H], w, -x[m+H])   ( = x[m] w - x[m+H] (1 - w) )
 template <int R>
-SSDR_DEV void l1_window(float2 (&x)[R], const float (&w)[R]) {
+SSDR_DEV void l1_window(float2 (&x)[R], const float (&w)[R / 2]) {
     constexpr int H = R / 2;
 #pragma unroll
     for (int m = 0; m < H; ++m) {
-        const float2 b = x[m + H];
-        const float2 p = __fmul2_rn(x[m], make_float2(w[m], w[m]));
-        x[m] = __ffma2_rn(b, make_float2(w[m + H], w[m + H]), p);
-        x[m + H] = __ffma2_rn(b, make_float2(-w[m + H], -w[m + H]), p);
+        const float2 a = x[m], b = x[m + H];
+        const float2 d = csub(a, b), s = cadd(a, b);
+        const float2 ww = make_float2(w[m], w[m]);
+        x[m] = __ffma2_rn(d, ww, b);
+        x[m + H] = __ffma2_rn(s, ww, make_float2(-b.x, -b.y));
     }
 }
 

@@ -13,6 +13,7 @@ struct WfLaunch {
     int iq_format = SSDR_IQ_CF32;
     const uint8_t* lines = nullptr;    // device, colorrow entry (iq ignored)
     const float* wtab = nullptr;       // device, 2*nfft floats
+    const float* win = nullptr;        // device, nfft/2 floats (first half of the Hann window)
     const float* thr = nullptr;        // device, 257 floats
     ssdr_wf_display_t* disp = nullptr; // device, [batch]
     uint8_t* pixels = nullptr;

@@ -20,6 +20,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -70,13 +71,15 @@ struct Cfg {
     static constexpr size_t SM_TW1 = SM_TW0 + (size_t)TW0 * sizeof(float2);
     static constexpr size_t SM_ACC = SM_TW1 + (size_t)TW1 * sizeof(float2);        // byte sums, thread-private uint4[4][THREADS]
     static constexpr size_t SM_W1 = SM_ACC + (size_t)THREADS * 16 * sizeof(unsigned);   // wtab[j] of this thread's butterflies
-    static constexpr size_t SM_RED = SM_W1 + (size_t)THREADS * NB0 * sizeof(float2);
+    static constexpr size_t SM_WIN = SM_W1 + (size_t)THREADS * NB0 * sizeof(float2);     // first half of the Hann window, N/2 floats
+    static constexpr size_t SM_RED = SM_WIN + (size_t)(N / 2) * sizeof(float);
     static constexpr size_t SM_BYTES = SM_RED + (size_t)FPC * 8 * sizeof(int);
 };
 
 struct WfKernelParams {
     const void* iq;                 // [batch][n_avg][N] samples
     const float2* wtab;             // master twiddle table, N entries
+    const float* win;               // first half of the periodic Hann window, N/2 entries
     const float* thr;               // 257 thresholds (thr[256] = +inf)
     ssdr_wf_display_t* disp;        // [batch], low_clip_db/dynamic_range updated when auto_scale
     uint8_t* pixels;                // [batch][N] or null
@@ -162,24 +165,16 @@ SSDR_DEV void first_load(float2 (&x)[C::R0], int i, int t, const void* src, size
 
 // First pass, part 2: window, radix-R0 butterflies, twiddles, scatter into the frame buffer.
 template <class C, bool WINDOW>
-SSDR_DEV void first_compute(float2 (&x)[C::R0], int i, float2* d, const float2* tw0, int t, float2 w1) {
+SSDR_DEV void first_compute(float2 (&x)[C::R0], int i, float2* d, const float2* tw0, const float* win, int t, float2 w1) {
     constexpr int R = C::R0, M = C::M0, G = C::G;
     constexpr bool TABLE = (M == 32);
     const int j = t + i * G;
     if constexpr (WINDOW) {
-        // w[j + m M] = 0.5 - 0.5 cos(theta_j + 2 pi m / R) from wtab[j] and the unit32 constants,
-        // fused into the first butterfly level
-        float wv[R];
-        const float2 cc = make_float2(w1.x, w1.x), dd = make_float2(w1.y, w1.y);
+        // Hann values of the samples j + m M, m < R/2 (all < N/2), from the shared-memory table; the other half
+        // of the butterfly uses w[n + N/2] = 1 - w[n], folded into the first level
+        float wv[R / 2];
 #pragma unroll
-        for (int m = 0; m < R; m += 2) {
-            const int e0 = m * (32 / R), e1 = (m + 1) * (32 / R);
-            const float2 tt = __fmul2_rn(dd, make_float2(unit32_sin(e0), unit32_sin(e1)));
-            const float2 cm = __ffma2_rn(cc, make_float2(unit32_cos(e0), unit32_cos(e1)), tt);
-            const float2 w2 = __ffma2_rn(make_float2(-0.5f, -0.5f), cm, make_float2(0.5f, 0.5f));
-            wv[m] = w2.x;
-            wv[m + 1] = w2.y;
-        }
+        for (int m = 0; m < R / 2; ++m) wv[m] = win[j + m * M];
         l1_window<R>(x, wv);
     } else {
         l1<R>(x);
@@ -250,6 +245,36 @@ SSDR_DEV void group_sync(int slot) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// IEEE-754 round-to-nearest division a / b by a loop-invariant divisor (Markstein): with r = RN(1/b),
+// q0 = RN(a r), e = a - q0 b (exact, one fma), q = RN(q0 + e r) is the correctly rounded quotient provided
+// b is normal, its significand is not all ones and nothing under/overflows -- div_ok() checks the divisor,
+// the dividends here (|a| < 2^9 or 0) are safe.  tests/test_oracle_tier_p.py checks the sequence against
+// IEEE division on the CPU (every sum / n_avg pair, random colour quotients).
+// ---------------------------------------------------------------------------------------------
+struct Divisor {
+    float b, r;
+    bool ok;
+};
+SSDR_DEV Divisor make_divisor(float b) {
+    Divisor d;
+    d.b = b;
+    d.r = __frcp_rn(b);
+    const unsigned u = __float_as_uint(b), ex = (u >> 23) & 0xffu;
+    d.ok = (ex >= 64u && ex <= 190u) && ((u & 0x7fffffu) != 0x7fffffu);
+    return d;
+}
+template <bool FAST>
+SSDR_DEV float div_rn(float a, const Divisor& d) {
+    if constexpr (FAST) {
+        const float q0 = __fmul_rn(a, d.r);
+        const float e = __fmaf_rn(-q0, d.b, a);
+        return __fmaf_rn(e, d.r, q0);
+    } else {
+        return __fdiv_rn(a, d.b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // colour stage: order statistics from the register-resident sums, then the row through a transpose
 // ---------------------------------------------------------------------------------------------
 // Thread t of a group holds the sums of bins k = kbase(t) + G q, q = 0..31, as acc[q/2] halves
@@ -284,7 +309,8 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
 
     float low_clip = dp.low_clip_db, high_clip = 0.f, dyn = dp.dynamic_range;
     const float fn = (float)kp.n_avg, z3 = (float)(3 * dp.zoom);
-    auto wfdb = [&](float s) { return ((__fdiv_rn(s, fn) - 255.0f) - 13.0f) + z3; };
+    const Divisor dfn = make_divisor(fn);               // n_avg = 1..100: always a valid Markstein divisor
+    auto wfdb = [&](float s) { return ((div_rn<true>(s, dfn) - 255.0f) - 13.0f) + z3; };
 
     auto group_sum = [&](int v, int rslot) -> int {
         v = __reduce_add_sync(gmask, v);
@@ -383,17 +409,21 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
     };
     const size_t row = (size_t)ch * N;
     group_sync<C>(slot);                                                 // every warp of the group is past its last FFT pass
+    const Divisor dden = make_divisor(den);
+    auto emit_row = [&](auto fast) {
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
-        const float s = (float)key_at(q);
-        const float m = __fdiv_rn(s, fn);
-        const float w = ((m - 255.0f) - 13.0f) + z3;
-        float c = __fdiv_rn(w - low, den);
-        c = fminf(fmaxf(c, 0.0f), 1.0f);
-        c = c * 254.0f;
-        c = fminf(fmaxf(c, 0.0f), 255.0f);
-        stage[sidx(out_index(q))] = c;
-    }
+        for (int q = 0; q < 32; ++q) {
+            const float s = (float)key_at(q);
+            const float m = div_rn<true>(s, dfn);
+            const float w = ((m - 255.0f) - 13.0f) + z3;
+            float c = div_rn<decltype(fast)::value>(w - low, dden);
+            c = fminf(fmaxf(c, 0.0f), 1.0f);
+            c = c * 254.0f;
+            c = fminf(fmaxf(c, 0.0f), 255.0f);
+            stage[sidx(out_index(q))] = c;
+        }
+    };
+    if (dden.ok) emit_row(std::true_type{}); else emit_row(std::false_type{});     // group-uniform
     group_sync<C>(slot);
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
@@ -407,7 +437,7 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
             const float s = (t == 0 && q == q0) ? (float)raw0 : (float)key_at(q);
-            stage[sidx(out_index(q))] = __fdiv_rn(s, fn);
+            stage[sidx(out_index(q))] = div_rn<true>(s, dfn);
         }
         group_sync<C>(slot);
 #pragma unroll 4
@@ -441,6 +471,10 @@ wf_fft_kernel(const WfKernelParams kp) {
     // one-time tables: twiddles of the table passes W_L^(j q), j < 32
     for (int e = threadIdx.x; e < C::TW0; e += blockDim.x) { const int q = e / 32 + 1, j = e & 31; tw0[e] = kp.wtab[j * q]; }
     for (int e = threadIdx.x; e < C::TW1; e += blockDim.x) { const int q = e / 32 + 1, j = e & 31; tw1[e] = kp.wtab[j * q * (N / 1024)]; }
+    float* win = reinterpret_cast<float*>(smem + C::SM_WIN);
+    if constexpr (WINDOW) {
+        for (int e = threadIdx.x; e < N / 2; e += blockDim.x) win[e] = kp.win[e];
+    }
     __syncthreads();
 
     // (cos, -sin)(2 pi j / N) of this thread's first-pass butterflies (window + first twiddle level):
@@ -467,7 +501,7 @@ wf_fft_kernel(const WfKernelParams kp) {
             }
             group_sync<C>(slot);              // every thread of the group has finished reading the previous frame (or row)
             if constexpr (C::NB0 == 1) {
-                first_compute<C, WINDOW>(x0, 0, d, tw0, t, w1_of(0));
+                first_compute<C, WINDOW>(x0, 0, d, tw0, win, t, w1_of(0));
             } else {
                 // software pipeline over this thread's first-pass butterflies: load i + 1 while i computes
                 float2 xa[C::R0], xb[C::R0];
@@ -476,9 +510,9 @@ wf_fft_kernel(const WfKernelParams kp) {
 #pragma unroll
                 for (int i = 0; i < C::NB0; i += 2) {
                     first_load<C, FMT>(xb, i + 1, t, kp.iq, off);
-                    first_compute<C, WINDOW>(xa, i, d, tw0, t, w1_of(i));
+                    first_compute<C, WINDOW>(xa, i, d, tw0, win, t, w1_of(i));
                     if (i + 2 < C::NB0) first_load<C, FMT>(xa, i + 2, t, kp.iq, off);
-                    first_compute<C, WINDOW>(xb, i + 1, d, tw0, t, w1_of(i + 1));
+                    first_compute<C, WINDOW>(xb, i + 1, d, tw0, win, t, w1_of(i + 1));
                 }
             }
             group_sync<C>(slot);
@@ -584,7 +618,7 @@ int wf_plan(int nfft, int* radices) {
 int wf_launch(const WfLaunch& a, cudaStream_t st) {
     WfKernelParams kp;
     std::memset(&kp, 0, sizeof(kp));
-    kp.iq = a.iq; kp.wtab = reinterpret_cast<const float2*>(a.wtab); kp.thr = a.thr; kp.disp = a.disp;
+    kp.iq = a.iq; kp.wtab = reinterpret_cast<const float2*>(a.wtab); kp.win = a.win; kp.thr = a.thr; kp.disp = a.disp;
     kp.pixels = a.pixels; kp.colour = a.colour; kp.spectrum = a.spectrum; kp.scalars = a.scalars;
     kp.lines = a.lines; kp.batch = a.batch; kp.n_avg = a.n_avg; kp.p_lo = a.p_lo; kp.p_gamma = a.p_gamma;
     kp.est_c1 = a.est_c1; kp.est_c0 = a.est_c0;

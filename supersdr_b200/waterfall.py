@@ -69,6 +69,12 @@ class WaterfallBank:
         n = check(lib.ssdr_wf_get_tables(self._h, ptr(tw), ptr(th), r))
         return tw.view(np.complex64), th, [r[i] for i in range(n)]
 
+    def window_table(self):
+        """First half of the periodic Hann window the kernel uses, float32[nfft / 2]."""
+        w = np.empty(self.nfft // 2, np.float32)
+        check(lib.ssdr_wf_get_window(self._h, ptr(w)))
+        return w
+
     # -- host-buffer API ----------------------------------------------------------------------
     def _outputs(self, want_colour, want_spectrum, out):
         B, N = self.batch, self.nfft

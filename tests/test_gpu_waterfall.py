@@ -22,6 +22,7 @@ def test_spec_tables_equal_oracle(ssdr):
         assert plan == c_oracle.fft_plan(N)
         assert np.array_equal(tw.view(np.float32), c_oracle.twiddle_table(N).view(np.float32))
         assert np.array_equal(thr, c_oracle.thresholds(N, -10.0))
+        assert np.array_equal(b.window_table(), c_oracle.window_table(N))
         b.close()
 
 

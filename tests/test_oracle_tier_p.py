@@ -111,3 +111,21 @@ def test_restatement_matches_imported_reference_live():
         assert np.array_equal(col, wf.wf_color)
     f = m.filtering(6000, 48000)
     assert np.array_equal(f.h, tier_p.fir_design(6000, 48000))
+
+
+def test_markstein_division_equals_ieee():
+    """The kernel's division by loop-invariant divisors (csrc/wf_kernels.cu div_rn) is IEEE-exact:
+    every byte sum / n_avg pair the waterfall can produce, and random colour quotients
+    (w - low) / den in the ranges spectrum_db2col produces (utils_supersdr.py:793-809)."""
+    for n in range(1, 101):
+        a = np.arange(0, 255 * n + 1, dtype=np.float32)
+        assert c_oracle.markstein_mismatches(a, n) == 0
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        den = np.float32(rng.uniform(1.0, 400.0))
+        if (den.view(np.uint32) & 0x7fffff) == 0x7fffff:
+            continue
+        a = rng.uniform(-400.0, 400.0, 20000).astype(np.float32)
+        a[:100] = (rng.integers(-2000, 2000, 100) / np.float32(10.0)).astype(np.float32)
+        a[100] = 0.0
+        assert c_oracle.markstein_mismatches(a, den) == 0
