@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-demod", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="developer runs: skip the host-buffer arm")
     ap.add_argument("--channels", type=int, default=B_PER_GPU, help="channels per GPU (default: the BASELINE config)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -223,22 +224,28 @@ def main():
     value = world * n_samples / ms_step / 1e3          # Msamples/s, whole job
 
     # ---- end-to-end arm: pinned host IQ -> H2D -> kernel -> D2H pixels, every step ----------------------
-    host_iq = S.PinnedArray((B, N_AVG, NFFT), np.complex64)
-    S._lib.check(S.lib.ssdr_memcpy_d2h(S._lib.ptr(host_iq.array), iq_dev.ptr, n_samples * 8))
-    host_px = S.PinnedArray((B, NFFT), np.uint8)
-    host_sc = np.empty(B, S._lib.SCALARS_DTYPE)
-    out = {"pixels": host_px.array, "scalars": host_sc}
-    e2e_steps = max(2, min(args.steps, 5))
-    bank.process(host_iq.array, want_colour=False, want_spectrum=False, out=out)   # warm-up (allocates staging)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        bank.process(host_iq.array, want_colour=False, want_spectrum=False, out=out)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    e2e = None
+    checksum = None
+    if not args.no_e2e:
+        host_iq = S.PinnedArray((B, N_AVG, NFFT), np.complex64)
+        S._lib.check(S.lib.ssdr_memcpy_d2h(S._lib.ptr(host_iq.array), iq_dev.ptr, n_samples * 8))
+        host_px = S.PinnedArray((B, NFFT), np.uint8)
+        host_sc = np.empty(B, S._lib.SCALARS_DTYPE)
+        out = {"pixels": host_px.array, "scalars": host_sc}
+        e2e_steps = max(2, min(args.steps, 5))
+        bank.process(host_iq.array, want_colour=False, want_spectrum=False, out=out)   # warm-up (allocates staging)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            bank.process(host_iq.array, want_colour=False, want_spectrum=False, out=out)
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        checksum = int(host_px.array[::257].astype(np.uint64).sum())
+        e2e = {"value": world * n_samples * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": n_samples * 8, "d2h_bytes_per_step": B * NFFT + host_sc.nbytes, "steps": e2e_steps,
+               "api": "WaterfallBank.process -> ssdr_wf_process (pinned host buffers)"}
+        host_iq.free(); host_px.free()
     clk = clocks.stop()
-    e2e_value = world * n_samples * e2e_steps / e2e_s / 1e6
-    checksum = int(host_px.array[::257].astype(np.uint64).sum())
 
     # ---- demodulator (BASELINE config 3) as a secondary line -------------------------------------------
     demod = None
@@ -278,9 +285,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "wf_fft_kernel<14>",
                      "algorithmic_bytes_per_launch": alg_bytes},
-        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": n_samples * 8,
-                "d2h_bytes_per_step": B * NFFT + host_sc.nbytes, "steps": e2e_steps,
-                "api": "WaterfallBank.process -> ssdr_wf_process (pinned host buffers)"},
+        "e2e": e2e,
         "gpu_launches": launches, "clocks": clk,
     }
     if demod:
@@ -291,7 +296,7 @@ def main():
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line))
-    bank.close(); iq_dev.free(); px_dev.free(); host_iq.free(); host_px.free()
+    bank.close(); iq_dev.free(); px_dev.free()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssdr_b200.so")
+# SSDR_B200_LIB: developer override used by scripts/exp_variants.sh to time experimental builds of the same ABI
+LIB_PATH = os.environ.get("SSDR_B200_LIB") or os.path.join(_HERE, "libssdr_b200.so")
 
 SSDR_IQ_CF32, SSDR_IQ_S16BE = 0, 1
 MODE_AM, MODE_USB, MODE_LSB, MODE_CW, MODE_NBFM = 0, 1, 2, 3, 4

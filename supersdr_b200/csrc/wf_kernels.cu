@@ -27,6 +27,12 @@
 #include "fft_radix.cuh"
 #include "wf_host.h"
 
+// Developer timing experiments (scripts/exp_variants.sh): SSDR_EXP is a bit mask that removes one phase of the
+// kernel at a time to measure its marginal cost.  Results are WRONG when any bit is set; the product build has 0.
+#ifndef SSDR_EXP
+#define SSDR_EXP 0
+#endif
+
 namespace ssdr {
 
 // ---------------------------------------------------------------------------------------------
@@ -117,7 +123,8 @@ SSDR_DEV void prefetch_l2(const void* p, unsigned bytes) {
 // the un-rounded byte value to ~1e-4; its nearest integer IS the byte unless v lies within kQEps of
 // a rounding boundary, and only then the thresholds are consulted (exact, rare).
 constexpr float kQMagic = 12582912.0f;    // 1.5 * 2^23: (v + magic) rounds v to nearest in the low mantissa bits
-constexpr float kQEps = 2.5e-4f;
+constexpr unsigned kQMagicBits = 0x4b400000u;
+constexpr float kQEps = 1.25e-4f;         // estimate error <= 8.7e-5: lg2.approx 2^-22 relative (|log2 P| <= 100) x c1, fma rounding, c0/c1 rounding
 
 SSDR_DEV float lg2_ftz(float x) {          // MUFU.LG2; a subnormal power is far below T[1], so flushing it to 0 is exact
     float y;
@@ -125,30 +132,62 @@ SSDR_DEV float lg2_ftz(float x) {          // MUFU.LG2; a subnormal power is far
     return y;
 }
 
-__device__ __noinline__ unsigned quantise_exact(float P, float v, const float* thr) {
-    int k = __float2int_rn(v);             // v is already clamped to [-0.25, 255.25]
-    while (k < 255 && P >= __ldg(thr + k + 1)) ++k;
-    while (k > 0 && P < __ldg(thr + k)) --k;
-    return (unsigned)k;
+// exact bytes of two bins (byte0 | byte1 << 16) from the thresholds, starting at the estimates
+__device__ __noinline__ unsigned quantise_pair_exact(float P0, float P1, float v0, float v1, const float* thr) {
+    unsigned k[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float P = i ? P1 : P0;
+        const float v = fminf(fmaxf(i ? v1 : v0, 0.0f), 255.0f);      // P == 0 -> -inf -> 0; NaN -> 0 like the oracle
+        int kk = __float2int_rn(v);
+        while (kk < 255 && P >= __ldg(thr + kk + 1)) ++kk;
+        while (kk > 0 && P < __ldg(thr + kk)) --kk;
+        k[i] = (unsigned)kk;
+    }
+    return k[0] | k[1] << 16;
 }
 
-// two bins -> byte0 | byte1 << 16
-SSDR_DEV unsigned quantise_pair(float2 a, float2 b, const WfKernelParams& kp) {
-    const float t0 = a.y * a.y, t1 = b.y * b.y;
-    const float P0 = __fmaf_rn(a.x, a.x, t0), P1 = __fmaf_rn(b.x, b.x, t1);
-    float2 v = __ffma2_rn(make_float2(lg2_ftz(P0), lg2_ftz(P1)), make_float2(kp.est_c1, kp.est_c1),
-                          make_float2(kp.est_c0, kp.est_c0));
-    v.x = fminf(fmaxf(v.x, -0.25f), 255.25f);           // P == 0 -> -inf -> byte 0; NaN -> 0 like the oracle
-    v.y = fminf(fmaxf(v.y, -0.25f), 255.25f);
-    const float2 m = __fadd2_rn(v, make_float2(kQMagic, kQMagic));
-    const float2 nf = __fadd2_rn(m, make_float2(-kQMagic, -kQMagic));
-    const float2 dd = __fadd2_rn(v, make_float2(-nf.x, -nf.y));
-    unsigned k0 = __float_as_uint(m.x), k1 = __float_as_uint(m.y);     // low 16 bits = nearest integer
-    if (fmaxf(fabsf(dd.x), fabsf(dd.y)) > 0.5f - kQEps) {              // rare: within kQEps of a rounding boundary
-        k0 = quantise_exact(P0, v.x, kp.thr);
-        k1 = quantise_exact(P1, v.y, kp.thr);
+// Eight bins -> four words byte0 | byte1 << 16.  The eight estimates are in flight together (instruction-level
+// parallelism across the MUFU latency) and ONE test covers all of them: some |v - rint(v)| within kQEps of a
+// rounding boundary, or some v + magic outside [magic, magic + 255] (estimate out of range, infinite or NaN:
+// no clamps on the fast path).  Only then the thresholds are consulted (exact, rare).
+SSDR_DEV uint4 quantise8(const float2* x, const WfKernelParams& kp) {
+    float P[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float t = x[i].y * x[i].y;
+        P[i] = __fmaf_rn(x[i].x, x[i].x, t);
     }
-    return __byte_perm(k0, k1, 0x5410);
+    float2 v[4], m[4];
+    float worst = 0.0f;
+    unsigned range = 0u;
+    const float2 c1 = make_float2(kp.est_c1, kp.est_c1), c0 = make_float2(kp.est_c0, kp.est_c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[i] = __ffma2_rn(make_float2(lg2_ftz(P[2 * i]), lg2_ftz(P[2 * i + 1])), c1, c0);
+        m[i] = __fadd2_rn(v[i], make_float2(kQMagic, kQMagic));
+        const float2 nf = __fadd2_rn(m[i], make_float2(-kQMagic, -kQMagic));
+        const float2 dd = __fadd2_rn(v[i], make_float2(-nf.x, -nf.y));
+        worst = fmaxf(worst, fmaxf(fabsf(dd.x), fabsf(dd.y)));
+        range |= (__float_as_uint(m[i].x) ^ kQMagicBits) | (__float_as_uint(m[i].y) ^ kQMagicBits);   // < 256 iff both in range
+    }
+    uint4 r;                                              // low 16 bits of m = nearest integer
+    r.x = __byte_perm(__float_as_uint(m[0].x), __float_as_uint(m[0].y), 0x5410);
+    r.y = __byte_perm(__float_as_uint(m[1].x), __float_as_uint(m[1].y), 0x5410);
+    r.z = __byte_perm(__float_as_uint(m[2].x), __float_as_uint(m[2].y), 0x5410);
+    r.w = __byte_perm(__float_as_uint(m[3].x), __float_as_uint(m[3].y), 0x5410);
+    if (worst > 0.5f - kQEps || range >= 256u) {
+        unsigned* rw = &r.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 nf = __fadd2_rn(m[i], make_float2(-kQMagic, -kQMagic));
+            const float2 dd = __fadd2_rn(v[i], make_float2(-nf.x, -nf.y));
+            const unsigned rg = (__float_as_uint(m[i].x) ^ kQMagicBits) | (__float_as_uint(m[i].y) ^ kQMagicBits);
+            if (!(fmaxf(fabsf(dd.x), fabsf(dd.y)) <= 0.5f - kQEps) || rg >= 256u)
+                rw[i] = quantise_pair_exact(P[2 * i], P[2 * i + 1], v[i].x, v[i].y, kp.thr);
+        }
+    }
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -160,7 +199,11 @@ SSDR_DEV unsigned quantise_pair(float2 a, float2 b, const WfKernelParams& kp) {
 template <class C, int FMT>
 SSDR_DEV void first_load(float2 (&x)[C::R0], int i, int t, const void* src, size_t off) {
 #pragma unroll
+#if SSDR_EXP & 32
+    for (int m = 0; m < C::R0; ++m) x[m] = make_float2((float)(t + m), (float)(i - m) + (float)off);
+#else
     for (int m = 0; m < C::R0; ++m) x[m] = load_iq<FMT>(src, off + (size_t)(t + i * C::G + m * C::M0));
+#endif
 }
 
 // First pass, part 2: window, radix-R0 butterflies, twiddles, scatter into the frame buffer.
@@ -169,6 +212,14 @@ SSDR_DEV void first_compute(float2 (&x)[C::R0], int i, float2* d, const float2* 
     constexpr int R = C::R0, M = C::M0, G = C::G;
     constexpr bool TABLE = (M == 32);
     const int j = t + i * G;
+#if SSDR_EXP & 256
+    {
+        float2* o = TABLE ? d + j : d + j + (j >> 5);
+#pragma unroll
+        for (int q = 0; q < R; ++q) o[q * (M + M / 32)] = x[q];
+        return;
+    }
+#endif
     if constexpr (WINDOW) {
         // Hann values of the samples j + m M, m < R/2 (all < N/2), from the shared-memory table; the other half
         // of the butterfly uses w[n + N/2] = 1 - w[n], folded into the first level
@@ -199,7 +250,9 @@ SSDR_DEV void pass_mid(float2* d, const float2* tw1, int t) {
     float2 x[32];
 #pragma unroll
     for (int m = 0; m < 32; ++m) x[m] = p[33 * m];
+#if !(SSDR_EXP & 8)
     dft<32>(x);
+#endif
 #pragma unroll
     for (int q = 1; q < 32; ++q) x[q] = cmul(x[q], tw1[(q - 1) * 32 + j]);
 #pragma unroll
@@ -215,15 +268,22 @@ SSDR_DEV void pass_last(const float2* d, int t, uint4* accs, bool first_frame, c
     float2 x[32];
 #pragma unroll
     for (int m = 0; m < 32; ++m) x[m] = p[m];
+#if !(SSDR_EXP & 4)
     dft<32>(x);
+#endif
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         uint4 a = make_uint4(0u, 0u, 0u, 0u);
         if (!first_frame) a = accs[c * C::THREADS];
-        a.x += quantise_pair(x[8 * c], x[8 * c + 1], kp);
-        a.y += quantise_pair(x[8 * c + 2], x[8 * c + 3], kp);
-        a.z += quantise_pair(x[8 * c + 4], x[8 * c + 5], kp);
-        a.w += quantise_pair(x[8 * c + 6], x[8 * c + 7], kp);
+#if SSDR_EXP & 1
+        a.x += (__float_as_uint(x[8 * c].x) ^ __float_as_uint(x[8 * c + 1].y)) & 0xffu;
+        a.y += (__float_as_uint(x[8 * c + 2].x) ^ __float_as_uint(x[8 * c + 3].y)) & 0xffu;
+        a.z += (__float_as_uint(x[8 * c + 4].x) ^ __float_as_uint(x[8 * c + 5].y)) & 0xffu;
+        a.w += (__float_as_uint(x[8 * c + 6].x) ^ __float_as_uint(x[8 * c + 7].y)) & 0xffu;
+#else
+        const uint4 k8 = quantise8(x + 8 * c, kp);
+        a.x += k8.x; a.y += k8.y; a.z += k8.z; a.w += k8.w;
+#endif
         accs[c * C::THREADS] = a;
     }
 }
@@ -499,7 +559,9 @@ wf_fft_kernel(const WfKernelParams kp) {
                 if (!last || ch + ch_stride < kp.batch)
                     prefetch_l2(static_cast<const unsigned char*>(kp.iq) + nxt * sample_bytes, (unsigned)N * sample_bytes);
             }
+#if !(SSDR_EXP & 64)
             group_sync<C>(slot);              // every thread of the group has finished reading the previous frame (or row)
+#endif
             if constexpr (C::NB0 == 1) {
                 first_compute<C, WINDOW>(x0, 0, d, tw0, win, t, w1_of(0));
             } else {
@@ -515,12 +577,16 @@ wf_fft_kernel(const WfKernelParams kp) {
                     first_compute<C, WINDOW>(xb, i + 1, d, tw0, win, t, w1_of(i + 1));
                 }
             }
+#if !(SSDR_EXP & 128)
             group_sync<C>(slot);
+#endif
             // from here each warp owns a contiguous 1024-point (NP == 3) / 32-point sub-transform: warp-local
+#if !(SSDR_EXP & 16)
             if constexpr (C::NP == 3) {
                 pass_mid<C>(d, tw1, t);
                 __syncwarp();
             }
+#endif
             pass_last<C>(d, t, accs, f == 0, kp);
             off += N;
             if (f + 1 < kp.n_avg) first_load<C, FMT>(x0, 0, t, kp.iq, off);
@@ -531,7 +597,11 @@ wf_fft_kernel(const WfKernelParams kp) {
             const uint4 a = accs[c * C::THREADS];
             acc[4 * c] = a.x; acc[4 * c + 1] = a.y; acc[4 * c + 2] = a.z; acc[4 * c + 3] = a.w;
         }
+#if SSDR_EXP & 2
+        if (acc[0] == 0x12345678u) kp.pixels[ch] = (uint8_t)acc[1];
+#else
         colour_stage<C, false>(reinterpret_cast<float*>(d), red, slot, t, ch, acc, kp);
+#endif
     }
 }
 
