@@ -91,9 +91,9 @@ static inline cpx csub(cpx a, cpx b) { cpx r = {a.re - b.re, a.im - b.im}; retur
 static inline cpx cmul(cpx u, cpx w) {
     cpx r;
     float t0 = u.im * w.im;
-    float t1 = u.im * w.re;
+    float t1 = u.re * w.im;
     r.re = fmaf(u.re, w.re, -t0);
-    r.im = fmaf(u.re, w.im, t1);
+    r.im = fmaf(u.im, w.re, t1);
     return r;
 }
 static inline cpx mul_mi(cpx u) { cpx r = {u.im, -u.re}; return r; }                 /* * (-i)      */
@@ -173,7 +173,7 @@ static void dft16_rest(cpx* x) {             /* after l1 on pairs (m, m + 8) */
 }
 
 /* 32 = 4 x 8: radix-4 across m1 (m = m0 + 8 m1), twiddle W32^(m0 p), radix-8 across m0; q = p + 4 s.
- * W32^e = (cos, -sin)(2 pi e / 32) from the unit32 constants; e == 8 is the exact rotation by -i. */
+ * W32^e is applied as W32^(e mod 8) (unit32 constants) followed by (e div 8) exact quarter turns. */
 static void dft32_rest(cpx* x) {             /* after l1 on pairs (m, m + 16) */
     cpx u[4][8];   /* u[p][m0] */
     for (int m0 = 0; m0 < 8; ++m0) {
@@ -183,12 +183,19 @@ static void dft32_rest(cpx* x) {             /* after l1 on pairs (m, m + 16) */
     }
     for (int p = 1; p < 4; ++p)
         for (int m0 = 1; m0 < 8; ++m0) {
-            int e = m0 * p;
-            if (e == 8) { u[p][m0] = mul_mi(u[p][m0]); continue; }
-            float c, s;
-            unit32(e, &c, &s);
-            cpx w = {c, -s};
-            u[p][m0] = cmul(u[p][m0], w);
+            /* W32^e = (-i)^(e div 8) W32^(e mod 8): a complex multiply by the first-quadrant constant
+             * (skipped when e mod 8 == 0) followed by exact quarter turns. */
+            int e = m0 * p, r = e & 7, k = e >> 3;
+            cpx v = u[p][m0];
+            if (r) {
+                float c, s;
+                unit32(r, &c, &s);
+                cpx w = {c, -s};
+                v = cmul(v, w);
+            }
+            if (k == 1) v = mul_mi(v);
+            else if (k == 2) { v.re = -v.re; v.im = -v.im; }
+            u[p][m0] = v;
         }
     for (int p = 0; p < 4; ++p) {
         l1(u[p], 8);

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/../supersdr_b200/csrc"
 mkdir -p ../../build/exp
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC"
 for m in "$@"; do
-  nvcc $FLAGS -fmad=false -DSSDR_EXP=$m -c wf_kernels.cu -o ../../build/exp/wf_$m.o &
+  nvcc $FLAGS -fmad=false -DSSDR_EXP=$m $EXTRA -c wf_kernels.cu -o ../../build/exp/wf_$m.o &
 done
 wait
 for m in "$@"; do

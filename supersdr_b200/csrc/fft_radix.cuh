@@ -35,12 +35,14 @@ SSDR_DEV constexpr float unit32_sin(int m) {
 
 SSDR_DEV float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 SSDR_DEV float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
-// (u.re + i u.im)(w.re + i w.im): re = fma(u.re, w.re, -(u.im*w.im)), im = fma(u.re, w.im, u.im*w.re)
-// Written so that the swap sits on the FMUL2 operand and the half negation on the FFMA2 addend: both
-// are operand modifiers, so a complex multiply is exactly two instructions.
+// (u.re + i u.im)(w.re + i w.im):  re = fma(u.re, w.re, -(u.im * w.im)),  im = fma(u.im, w.re, u.re * w.im).
+// Written so that both instructions take the twiddle as a BROADCAST scalar (w.im for the FMUL2, w.re for the
+// FFMA2): a compile-time twiddle is then a 32-bit immediate / a single register instead of a 64-bit register
+// pair that has to be materialised, and a table twiddle is used straight from the pair it was loaded into.
+// The swap of u sits on the FMUL2 operand and the half negation on the FFMA2 addend (operand modifiers).
 SSDR_DEV float2 cmul(float2 u, float2 w) {
-    const float2 t = __fmul2_rn(make_float2(u.y, u.y), make_float2(w.y, w.x));      // {im*w.im, im*w.re}
-    return __ffma2_rn(make_float2(u.x, u.x), w, make_float2(-t.x, t.y));
+    const float2 t = __fmul2_rn(make_float2(u.y, u.x), make_float2(w.y, w.y));      // {im*w.im, re*w.im}
+    return __ffma2_rn(u, make_float2(w.x, w.x), make_float2(-t.x, t.y));
 }
 SSDR_DEV float2 mul_mi(float2 u) { return make_float2(u.y, -u.x); }                      // * (-i), exact
 // Odd eighth turns are ordinary complex multiplies by the rounded constants.  (A separate scale by B
