@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""BASELINE config 5: FFT size sweep x batch sweep on one GPU (device-resident IQ, n_avg = 1 unless --n-avg):
+achieved algorithmic HBM GB/s (B*n*N*8 in + B*N out) vs the measured copy peak.  Prints one JSON line per point.
+    python scripts/sweep.py [--sizes 256,...,16384] [--batches 1,64,4096,65536] [--n-avg 1] [--fmt cf32|s16be]"""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import supersdr_b200 as S
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="256,512,1024,2048,4096,8192,16384")
+    ap.add_argument("--batches", default="1,16,256,4096,65536")
+    ap.add_argument("--n-avg", type=int, default=1)
+    ap.add_argument("--fmt", default="cf32", choices=["cf32", "s16be"])
+    ap.add_argument("--max-bytes", type=float, default=8e9)
+    ap.add_argument("--iters", type=int, default=10)
+    a = ap.parse_args()
+    S.init(0)
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    fmt = S.SSDR_IQ_CF32 if a.fmt == "cf32" else S.SSDR_IQ_S16BE
+    sb = 8 if a.fmt == "cf32" else 4
+    for N in [int(x) for x in a.sizes.split(",")]:
+        for B in [int(x) for x in a.batches.split(",")]:
+            in_bytes = B * a.n_avg * N * sb
+            if in_bytes > a.max_bytes:
+                continue
+            iq = S.DeviceBuffer(in_bytes)
+            px = S.DeviceBuffer(B * N)
+            S._lib.check(S.lib.ssdr_synth_iq_dev(iq.ptr, fmt, B, a.n_avg, N, 77))
+            bank = S.WaterfallBank(N, B, a.n_avg)
+            for _ in range(3):
+                bank.time_dev(iq.ptr, fmt, px.ptr, 1)
+            # inputs smaller than L2 (126 MB) are cache-resident between iterations: flagged in the output
+            ms = bank.time_dev(iq.ptr, fmt, px.ptr, a.iters) / a.iters
+            alg = in_bytes + B * N
+            print(json.dumps({"nfft": N, "batch": B, "n_avg": a.n_avg, "fmt": a.fmt, "ms": round(ms, 5),
+                              "msamples_per_s": round(B * a.n_avg * N / ms / 1e3, 1), "gbs": round(alg / ms / 1e6, 1),
+                              "frac_of_measured_hbm": round(alg / ms / 1e6 / peak, 4),
+                              "l2_resident": in_bytes < 126e6}), flush=True)
+            bank.close(); iq.free(); px.free()
+
+
+if __name__ == "__main__":
+    main()

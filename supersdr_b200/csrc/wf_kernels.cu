@@ -616,225 +616,6 @@ wf_fft_kernel(const WfKernelParams kp) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// 16384-point frames: split-butterfly kernel
-//
-// A 16384-point frame fills the shared memory of an SM, so only one frame per SM can be in flight and a
-// single 16-warp frame group runs its phases (HBM loads, shared-memory traffic, butterflies) in lock
-// step.  Here the CTA is TWO independent groups of 8 warps.  Both read every frame; group g computes
-// only the first-pass outputs q = g (mod 2) -- the radix-16 butterfly is 4 x 4 and its outputs p = q mod 4
-// in {0, 2} depend only on the (windowed) sums x[m] + x[m + 8], those in {1, 3} only on the differences,
-// so the two halves share no arithmetic -- and then owns those eight 1024-point sub-transforms (one per
-// warp) through the remaining two warp-local passes.  Same operations, same order, same results as the
-// single-group plan; what changes is that each group has its own barrier pair and its own half of the
-// frame buffer, so one group's memory phases overlap the other's arithmetic.  The price is that every
-// input sample crosses L2 -> SM twice (HBM traffic is unchanged: the second reader hits L2).
-// Layout: region r of group g (sub-transform q = 2r + g) holds element e at r * 1088 + e + 2 (e >> 5):
-// two pad elements per 32 keep every pass conflict-free AND make the last pass's 32 consecutive elements
-// per thread 16-byte aligned (128-bit loads).
-// ---------------------------------------------------------------------------------------------
-struct C16 {
-    static constexpr int N = 16384, G = 512, THREADS = 512, FPC = 1, NP = 3, R0 = 16, M0 = 1024;
-    static constexpr int GT = 256;                          // threads per group
-    static constexpr int RS = 1024 + 64;                    // region stride, float2
-    static constexpr int GS = 8 * RS;                       // group buffer, float2
-    static constexpr int SWZ = 4;
-    static constexpr size_t SM_DATA = 0;
-    static constexpr size_t SM_TW1 = SM_DATA + (size_t)2 * GS * sizeof(float2);
-    static constexpr size_t SM_ACC = SM_TW1 + (size_t)32 * 31 * sizeof(float2);
-    static constexpr size_t SM_WIN = SM_ACC + (size_t)THREADS * 16 * sizeof(unsigned);
-    static constexpr size_t SM_W1 = SM_WIN + (size_t)(N / 2) * sizeof(float);
-    static constexpr size_t SM_RED = SM_W1 + (size_t)M0 * sizeof(float2);
-    static constexpr size_t SM_BYTES = SM_RED + 8 * sizeof(int);
-};
-
-SSDR_DEV void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(C16::GT) : "memory"); }
-
-template <int FMT>
-SSDR_DEV void load16(float2 (&x)[16], int j, const void* src, size_t off) {
-#pragma unroll
-    for (int m = 0; m < 16; ++m) x[m] = load_iq<FMT>(src, off + (size_t)(j + m * 1024));
-}
-
-// Half of first-pass butterfly j for group GRP: x[0..15] in, the eight outputs q = p + 4 s, p = GRP + 2 pi,
-// left in x[4 pi + s] (pi = 0, 1; s = 0..3), already multiplied by the chain twiddles W^(j q).
-template <int GRP, bool WINDOW>
-SSDR_DEV void half_butterfly(float2 (&x)[16], int j, const float* win, const float2* w1tab) {
-    float2 h[8];
-    // first level: windowed sums (GRP 0) or differences (GRP 1) of the pairs (m, m + 8)
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const float2 a = x[m], b = x[m + 8];
-        if constexpr (WINDOW) {
-            const float w = win[j + m * 1024];
-            const float2 ww = make_float2(w, w);
-            if constexpr (GRP == 0) h[m] = __ffma2_rn(csub(a, b), ww, b);
-            else h[m] = __ffma2_rn(cadd(a, b), ww, make_float2(-b.x, -b.y));
-        } else {
-            h[m] = (GRP == 0) ? cadd(a, b) : csub(a, b);
-        }
-    }
-    // second level of the radix-4 across (m0, m0 + 4): rows p = GRP and p = GRP + 2, u[pi][m0] -> x[4 pi + m0]
-#pragma unroll
-    for (int m0 = 0; m0 < 4; ++m0) {
-        const float2 a = h[m0], c = h[m0 + 4];
-        if constexpr (GRP == 0) {
-            x[m0] = cadd(a, c);                                        // p = 0
-            x[4 + m0] = csub(a, c);                                    // p = 2
-        } else {
-            x[m0] = __fadd2_rn(a, make_float2(c.y, -c.x));             // p = 1: b + (-i) e
-            x[4 + m0] = __fadd2_rn(a, make_float2(-c.y, c.x));         // p = 3: b - (-i) e
-        }
-    }
-    // internal twiddles W16^(m0 p)
-    if constexpr (GRP == 0) {
-        x[5] = mul_w8(x[5]); x[6] = mul_mi(x[6]); x[7] = mul_w83(x[7]);
-    } else {
-        const float2 w1 = make_float2(kA, -kC), w3 = make_float2(kC, -kA), w9 = make_float2(-kA, kC);
-        x[1] = cmul(x[1], w1); x[2] = mul_w8(x[2]);  x[3] = cmul(x[3], w3);
-        x[5] = cmul(x[5], w3); x[6] = mul_w83(x[6]); x[7] = cmul(x[7], w9);
-    }
-    // radix-4 across m0 for both rows: output s in x[4 pi + s]
-    dft4(x[0], x[1], x[2], x[3]);
-    dft4(x[4], x[5], x[6], x[7]);
-    // chain twiddles: q = 4 s + p  ->  (x A[s]) B[p]
-    const float2 wj = w1tab[j];
-    const float2 B2 = cmul(wj, wj);
-    float2 B3 = B2;
-    if constexpr (GRP == 1) B3 = cmul(B2, wj);
-    const float2 A1 = cmul(B2, B2), A2 = cmul(A1, A1), A3 = cmul(A2, A1);
-#pragma unroll
-    for (int pi = 0; pi < 2; ++pi) {
-        x[4 * pi + 1] = cmul(x[4 * pi + 1], A1);
-        x[4 * pi + 2] = cmul(x[4 * pi + 2], A2);
-        x[4 * pi + 3] = cmul(x[4 * pi + 3], A3);
-    }
-    if constexpr (GRP == 0) {
-#pragma unroll
-        for (int sidx = 0; sidx < 4; ++sidx) x[4 + sidx] = cmul(x[4 + sidx], B2);          // p = 2
-    } else {
-#pragma unroll
-        for (int sidx = 0; sidx < 4; ++sidx) {
-            x[sidx] = cmul(x[sidx], wj);                                                  // p = 1
-            x[4 + sidx] = cmul(x[4 + sidx], B3);                                          // p = 3
-        }
-    }
-}
-
-// outputs of half-butterfly j -> the group's regions: q = p + 4 s lives in region (q - g) / 2 = pi + 2 s
-SSDR_DEV void store_half(const float2 (&x)[16], int j, float2* dg) {
-    float2* o = dg + j + 2 * (j >> 5);
-#pragma unroll
-    for (int pi = 0; pi < 2; ++pi)
-#pragma unroll
-        for (int sidx = 0; sidx < 4; ++sidx) o[(pi + 2 * sidx) * C16::RS] = x[4 * pi + sidx];
-}
-
-template <int GRP, int FMT, bool WINDOW>
-SSDR_DEV void frames16k(const WfKernelParams& kp, int ch, int ch_next, float2* dg, const float2* tw1, const float* win,
-                        const float2* w1tab, uint4* accs, int tl) {
-    constexpr int N = C16::N;
-    constexpr unsigned sample_bytes = (FMT == SSDR_IQ_CF32) ? 8u : 4u;
-    const int lane = tl & 31;
-    float2* region = dg + (tl >> 5) * C16::RS;
-    size_t off = (size_t)ch * kp.n_avg * N;
-    float2 xa[16], xb[16];
-    load16<FMT>(xa, tl, kp.iq, off);
-#pragma unroll 1
-    for (int f = 0; f < kp.n_avg; ++f) {
-        if (GRP == 0 && tl == 0) {            // the frame after next (or the first frame of the next channel) -> L2
-            const bool last = (f + 1 == kp.n_avg);
-            const size_t nxt = last ? (size_t)ch_next * kp.n_avg * N : off + N;
-            if (!last || ch_next < kp.batch)
-                prefetch_l2(static_cast<const unsigned char*>(kp.iq) + nxt * sample_bytes, (unsigned)N * sample_bytes);
-        }
-        // first pass: four half-butterflies j = tl + 256 i, loads one ahead; the first one is computed before
-        // the barrier that frees the frame buffer
-        half_butterfly<GRP, WINDOW>(xa, tl, win, w1tab);
-        load16<FMT>(xb, tl + 256, kp.iq, off);
-        group_bar(GRP);                       // every warp of the group has finished reading the previous frame
-        store_half(xa, tl, dg);
-        half_butterfly<GRP, WINDOW>(xb, tl + 256, win, w1tab);
-        load16<FMT>(xa, tl + 512, kp.iq, off);
-        store_half(xb, tl + 256, dg);
-        half_butterfly<GRP, WINDOW>(xa, tl + 512, win, w1tab);
-        load16<FMT>(xb, tl + 768, kp.iq, off);
-        store_half(xa, tl + 512, dg);
-        half_butterfly<GRP, WINDOW>(xb, tl + 768, win, w1tab);
-        store_half(xb, tl + 768, dg);
-        off += N;
-        if (f + 1 < kp.n_avg) load16<FMT>(xa, tl, kp.iq, off);
-        group_bar(GRP);
-        // warp-local from here: this warp's 1024-point sub-transform
-        {
-            float2* p = region + lane;
-            float2 x[32];
-#pragma unroll
-            for (int m = 0; m < 32; ++m) x[m] = p[34 * m];
-            dft<32>(x);
-#pragma unroll
-            for (int q = 1; q < 32; ++q) x[q] = cmul(x[q], tw1[(q - 1) * 32 + lane]);
-#pragma unroll
-            for (int q = 0; q < 32; ++q) p[34 * q] = x[q];
-        }
-        __syncwarp();
-        {
-            const float4* p = reinterpret_cast<const float4*>(region + 34 * lane);
-            float2 x[32];
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const float4 v = p[m];
-                x[2 * m] = make_float2(v.x, v.y);
-                x[2 * m + 1] = make_float2(v.z, v.w);
-            }
-            dft<32>(x);
-            last_epilogue<C16::THREADS>(x, accs, f == 0, kp);
-        }
-    }
-}
-
-template <int FMT, bool WINDOW>
-__global__ void __launch_bounds__(C16::THREADS, 1)
-wf_fft16k_kernel(const WfKernelParams kp) {
-    using C = C16;
-    constexpr int N = C::N;
-    extern __shared__ __align__(16) unsigned char smem[];
-    float2* data = reinterpret_cast<float2*>(smem + C::SM_DATA);
-    float2* tw1 = reinterpret_cast<float2*>(smem + C::SM_TW1);
-    uint4* accs = reinterpret_cast<uint4*>(smem + C::SM_ACC) + threadIdx.x;
-    float* win = reinterpret_cast<float*>(smem + C::SM_WIN);
-    float2* w1tab = reinterpret_cast<float2*>(smem + C::SM_W1);
-    int* red = reinterpret_cast<int*>(smem + C::SM_RED);
-
-    for (int e = threadIdx.x; e < 32 * 31; e += blockDim.x) { const int q = e / 32 + 1, j = e & 31; tw1[e] = kp.wtab[j * q * (N / 1024)]; }
-    for (int e = threadIdx.x; e < C::M0; e += blockDim.x) w1tab[e] = kp.wtab[e];
-    if constexpr (WINDOW) {
-        for (int e = threadIdx.x; e < N / 2; e += blockDim.x) win[e] = kp.win[e];
-    }
-    __syncthreads();
-
-    const int t = threadIdx.x, g = t >> 8, tl = t & 255;
-    float2* dg = data + (size_t)g * C::GS;
-    // bins of this thread: k = q1 + 16 lane + 512 q3, q1 = 2 (warp in group) + g
-    const int kb = (2 * (tl >> 5) + g) + 16 * (tl & 31);
-    for (int ch = blockIdx.x; ch < kp.batch; ch += (int)gridDim.x) {
-#ifdef SSDR_SKEW
-        if (g == 1) { const long long t0 = clock64(); while (clock64() - t0 < SSDR_SKEW) { } }
-#endif
-        if (g == 0) frames16k<0, FMT, WINDOW>(kp, ch, ch + (int)gridDim.x, dg, tw1, win, w1tab, accs, tl);
-        else frames16k<1, FMT, WINDOW>(kp, ch, ch + (int)gridDim.x, dg, tw1, win, w1tab, accs, tl);
-        unsigned acc[16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const uint4 a = accs[c * C::THREADS];
-            acc[4 * c] = a.x; acc[4 * c + 1] = a.y; acc[4 * c + 2] = a.z; acc[4 * c + 3] = a.w;
-        }
-        __syncthreads();                      // both groups are past their last pass: the frame buffers become the row stage
-        colour_stage<C, false>(reinterpret_cast<float*>(data), red, 0, t, ch, acc, kp, kb, 256);
-        __syncthreads();                      // the stage has been read before the next channel's first pass writes
-    }
-}
-
 // Tier-P entry: finished uint8 lines in, same colour stage (no FFT).  utils_supersdr.py:783-813,881-886
 template <int LG>
 __global__ void __launch_bounds__(Cfg<LG>::THREADS)
@@ -893,20 +674,6 @@ static int launch_fft(const WfKernelParams& kp, int fmt, int window, cudaStream_
     return window ? launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, false>);
 }
 
-static int launch_fft16k(const WfKernelParams& kp, int fmt, int window, cudaStream_t st) {
-    auto launch = [&](auto kern) -> int {
-        SSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C16::SM_BYTES));
-        int grid = sm_count();
-        if (grid > kp.batch) grid = kp.batch;
-        kern<<<grid, C16::THREADS, C16::SM_BYTES, st>>>(kp);
-        count_launch();
-        SSDR_CUDA(cudaGetLastError());
-        return SSDR_OK;
-    };
-    if (fmt == SSDR_IQ_CF32) return window ? launch(wf_fft16k_kernel<SSDR_IQ_CF32, true>) : launch(wf_fft16k_kernel<SSDR_IQ_CF32, false>);
-    return window ? launch(wf_fft16k_kernel<SSDR_IQ_S16BE, true>) : launch(wf_fft16k_kernel<SSDR_IQ_S16BE, false>);
-}
-
 template <int LG>
 static int launch_colorrow(const WfKernelParams& kp, cudaStream_t st) {
     using C = Cfg<LG>;
@@ -957,7 +724,7 @@ int wf_launch(const WfLaunch& a, cudaStream_t st) {
             case 11: return launch_fft<11>(kp, a.iq_format, a.window, st);
             case 12: return launch_fft<12>(kp, a.iq_format, a.window, st);
             case 13: return launch_fft<13>(kp, a.iq_format, a.window, st);
-            case 14: return (SSDR_EXP & 512) ? launch_fft<14>(kp, a.iq_format, a.window, st) : launch_fft16k(kp, a.iq_format, a.window, st);
+            case 14: return launch_fft<14>(kp, a.iq_format, a.window, st);
         }
     }
     set_error("unsupported nfft %d", a.nfft);
