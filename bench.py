@@ -247,22 +247,52 @@ def main():
         host_iq.free(); host_px.free()
     clk = clocks.stop()
 
-    # ---- demodulator (BASELINE config 3) as a secondary line -------------------------------------------
+    # ---- demodulator (BASELINE configs 3 and 4) as secondary lines ---------------------------------------
     demod = None
     if not args.no_demod:
-        dq = S.DeviceBuffer(DEMOD_B * DEMOD_S * 8)
-        dout = S.DeviceBuffer(DEMOD_B * DEMOD_S * 4)
-        S._lib.check(S.lib.ssdr_synth_iq_dev(dq.ptr, S.SSDR_IQ_CF32, DEMOD_B, 1, DEMOD_S, 99 + rank))
-        db = S.DemodBank(DEMOD_B, DEMOD_S)
-        db.set_all(mode="usb", lc=300, hc=2700)
-        for _ in range(3):
-            db.time_dev(dq.ptr, S.SSDR_IQ_CF32, DEMOD_S, dout.ptr, None, 1)
-        dms = max_over_ranks(db.time_dev(dq.ptr, S.SSDR_IQ_CF32, DEMOD_S, dout.ptr, None, 5) / 5)
-        ns = DEMOD_B * DEMOD_S
-        demod = {"workload": "config[2]: batch=4096 ch/GPU USB demod @12 kHz, 127-tap FIR, 64 frames/call",
-                 "value": world * ns / dms / 1e3, "unit": "Msamples/s", "ms_per_step": dms,
-                 "hbm_gbs": ns * 12 / dms / 1e6, "fp32_tflops": ns * (4 * 127 + 30) / dms / 1e9}
-        db.close(); dq.free(); dout.free()
+        from supersdr_b200.sound import demod_params
+        demod = {}
+
+        def demod_case(key, workload, B, ns_ch, params):
+            dq = S.DeviceBuffer(B * ns_ch * 8)
+            dout = S.DeviceBuffer(B * ns_ch * 4)
+            S._lib.check(S.lib.ssdr_synth_iq_dev(dq.ptr, S.SSDR_IQ_CF32, B, 1, ns_ch, 99 + rank))
+            db = S.DemodBank(B, ns_ch)
+            db.set_params(0, params)
+            for _ in range(3):
+                db.time_dev(dq.ptr, S.SSDR_IQ_CF32, ns_ch, dout.ptr, None, 1)
+            barrier()
+            dms = max_over_ranks(db.time_dev(dq.ptr, S.SSDR_IQ_CF32, ns_ch, dout.ptr, None, 5) / 5)
+            ns = B * ns_ch
+            d = {"workload": workload, "value": world * ns / dms / 1e3, "unit": "Msamples/s", "ms_per_step": dms,
+                 "hbm_gbs": ns * 12 / dms / 1e6, "fp32_tflops": ns * (4 * 127 + 30) / dms / 1e9,
+                 "bound": "fp32 pipe (direct-form 127-tap FIR: 4*127+~30 flop/sample); HBM bound would be 12 B/sample"}
+            if not args.no_e2e:
+                hq = S.PinnedArray((B, ns_ch), np.complex64)
+                ho = S.PinnedArray((B, ns_ch), np.float32)
+                S._lib.check(S.lib.ssdr_memcpy_d2h(S._lib.ptr(hq.array), dq.ptr, ns * 8))
+                db.reset()
+                o = {"pcm_f32": ho.array}
+                db.process(hq.array, want_f32=True, want_i16=False, want_rssi=True, out=o)     # warm-up (allocates staging)
+                barrier()
+                t1 = time.perf_counter()
+                n_e2e = 3
+                for _ in range(n_e2e):
+                    db.process(hq.array, want_f32=True, want_i16=False, want_rssi=True, out=o)
+                es = max_over_ranks(time.perf_counter() - t1)
+                d["e2e"] = {"value": world * ns * n_e2e / es / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": ns * 8,
+                            "d2h_bytes_per_step": ns * 4 + ns // 512 * 4, "steps": n_e2e,
+                            "api": "DemodBank.process -> ssdr_demod_process (pinned host IQ in, pinned float32 PCM out)"}
+                hq.free(); ho.free()
+            db.close(); dq.free(); dout.free()
+            demod[key] = d
+
+        usb = demod_params("usb", 300, 2700)
+        demod_case("config3_usb", "config[2]: batch=4096 ch/GPU USB demod @12 kHz, 2.4 kHz pass-band (300..2700 Hz), "
+                   "127-tap FIR, 64 frames/call", DEMOD_B, DEMOD_S, [usb] * DEMOD_B)
+        modes = [demod_params(m) for m in ("am", "lsb", "usb", "cw", "nbfm")]
+        demod_case("config4_mixed", "config[3]: 65536 ch / 8 GPUs = 8192 ch/GPU, modes ch%5 -> AM/LSB/USB/CW/NBFM "
+                   "(reference pass-bands), 32 frames/call", 8192, 512 * 32, [modes[c % 5] for c in range(8192)])
 
     peak, peak_src = peaks()
     alg_bytes = B * N_AVG * NFFT * 8 + B * NFFT

@@ -83,11 +83,13 @@ struct ssdr_demod {
     DemodState* d_state = nullptr;
     float2* d_hist = nullptr;
     float* d_taps = nullptr;
-    cudaStream_t compute = nullptr;
+    cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_read[2] = {nullptr, nullptr}, ev_done = nullptr;
     double am_pow16[5];
-    void* d_in = nullptr;
+    void* d_in = nullptr;          // two chunk slots of in_bytes / 2 each
     size_t in_bytes = 0;
+    int chunk_ch = 0;
     float* d_f32 = nullptr;
     int16_t* d_i16 = nullptr;
     float* d_rssi = nullptr;
@@ -402,8 +404,14 @@ int ssdr_demod_create(ssdr_demod_t* out, int batch, int max_samples) {
     if ((rc = dev_alloc(&h->d_state, (size_t)batch))) return fail(rc);
     if ((rc = dev_alloc(&h->d_hist, (size_t)batch * (SSDR_FIR_TAPS - 1)))) return fail(rc);
     if ((rc = dev_alloc(&h->d_taps, (size_t)batch * SSDR_FIR_TAPS))) return fail(rc);
-    if (cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(SSDR_E_CUDA); }
+    if (cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(SSDR_E_CUDA); }
     if (cudaEventCreate(&h->ev_t0) != cudaSuccess || cudaEventCreate(&h->ev_t1) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_read[i], cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
+    if (cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
     cudaMemset(h->d_chan, 0, sizeof(DemodChan) * (size_t)batch);
     cudaMemset(h->d_taps, 0, sizeof(float) * (size_t)batch * SSDR_FIR_TAPS);
     *out = h;
@@ -414,11 +422,17 @@ int ssdr_demod_create(ssdr_demod_t* out, int batch, int max_samples) {
 int ssdr_demod_destroy(ssdr_demod_t h) {
     if (!h) return SSDR_OK;
     if (h->compute) cudaStreamSynchronize(h->compute);
+    if (h->copy_in) cudaStreamSynchronize(h->copy_in);
+    if (h->copy_out) cudaStreamSynchronize(h->copy_out);
     cudaFree(h->d_chan); cudaFree(h->d_state); cudaFree(h->d_hist); cudaFree(h->d_taps);
     cudaFree(h->d_in); cudaFree(h->d_f32); cudaFree(h->d_i16); cudaFree(h->d_rssi);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_read[i]) cudaEventDestroy(h->ev_read[i]); }
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->compute) cudaStreamDestroy(h->compute);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     delete h;
     return SSDR_OK;
 }
@@ -464,41 +478,68 @@ int ssdr_demod_set(ssdr_demod_t h, int first, int count, const ssdr_demod_params
     return SSDR_OK;
 }
 
+static int demod_launch_block(ssdr_demod_t h, const void* iq_dev, int iq_format, int n_samples, int pitch,
+                              float* pcm_f32_dev, int16_t* pcm_i16_dev, float* rssi_dev) {
+    DemodLaunch a;
+    a.iq = iq_dev; a.iq_format = iq_format; a.chan = h->d_chan; a.state = h->d_state; a.hist = h->d_hist; a.taps = h->d_taps;
+    a.pcm_f32 = pcm_f32_dev; a.pcm_i16 = pcm_i16_dev; a.rssi = rssi_dev; a.batch = h->batch; a.n_samples = n_samples; a.pitch = pitch;
+    for (int s = 0; s < 5; ++s) a.am_pow16[s] = h->am_pow16[s];
+    return demod_launch(a, h->compute);
+}
+
 int ssdr_demod_process_dev(ssdr_demod_t h, const void* iq_dev, int iq_format, int n_samples, float* pcm_f32_dev,
                            int16_t* pcm_i16_dev, float* rssi_dev) {
     SSDR_ARG(h && iq_dev, "null argument");
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
     SSDR_ARG(n_samples > 0 && n_samples % SSDR_FRAME == 0, "n_samples %d must be a positive multiple of %d", n_samples, SSDR_FRAME);
-    DemodLaunch a;
-    a.iq = iq_dev; a.iq_format = iq_format; a.chan = h->d_chan; a.state = h->d_state; a.hist = h->d_hist; a.taps = h->d_taps;
-    a.pcm_f32 = pcm_f32_dev; a.pcm_i16 = pcm_i16_dev; a.rssi = rssi_dev; a.batch = h->batch; a.n_samples = n_samples;
-    for (int s = 0; s < 5; ++s) a.am_pow16[s] = h->am_pow16[s];
-    return demod_launch(a, h->compute);
+    return demod_launch_block(h, iq_dev, iq_format, n_samples, n_samples, pcm_f32_dev, pcm_i16_dev, rssi_dev);
 }
 
+// Host-buffer entry.  The call is cut into TIME blocks (all channels x a few frames): the per-channel streaming state
+// carries from block to block exactly as it does from call to call, every kernel covers the whole batch, and the strided
+// H2D copy of block k+1 (copy-in stream), the kernel of block k (compute stream) and the D2H copies of block k-1
+// (copy-out stream) overlap -- PCIe is full duplex.
 int ssdr_demod_process(ssdr_demod_t h, const void* iq_host, int iq_format, int n_samples, float* pcm_f32, int16_t* pcm_i16,
                        float* rssi_dbm) {
     SSDR_ARG(h && iq_host, "null argument");
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
     SSDR_ARG(n_samples > 0 && n_samples % SSDR_FRAME == 0 && n_samples <= h->max_samples,
              "n_samples %d must be a multiple of %d and <= %d", n_samples, SSDR_FRAME, h->max_samples);
-    const size_t tot = (size_t)h->batch * n_samples, cap = (size_t)h->batch * h->max_samples;
+    const size_t cap = (size_t)h->batch * h->max_samples, sb = iq_sample_bytes(iq_format);
     int rc;
-    if (h->in_bytes < tot * iq_sample_bytes(iq_format)) {
-        cudaFree(h->d_in); h->d_in = nullptr;
+    if (!h->d_in) {
         h->in_bytes = cap * 8;
         if ((rc = dev_alloc(reinterpret_cast<unsigned char**>(&h->d_in), h->in_bytes))) return rc;
     }
     if (pcm_f32 && !h->d_f32 && (rc = dev_alloc(&h->d_f32, cap))) return rc;
     if (pcm_i16 && !h->d_i16 && (rc = dev_alloc(&h->d_i16, cap))) return rc;
     if (rssi_dbm && !h->d_rssi && (rc = dev_alloc(&h->d_rssi, cap / SSDR_FRAME))) return rc;
-    SSDR_CUDA(cudaMemcpyAsync(h->d_in, iq_host, tot * iq_sample_bytes(iq_format), cudaMemcpyHostToDevice, h->compute));
-    if ((rc = ssdr_demod_process_dev(h, h->d_in, iq_format, n_samples, pcm_f32 ? h->d_f32 : nullptr, pcm_i16 ? h->d_i16 : nullptr,
-                                     rssi_dbm ? h->d_rssi : nullptr))) return rc;
-    if (pcm_f32) SSDR_CUDA(cudaMemcpyAsync(pcm_f32, h->d_f32, tot * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
-    if (pcm_i16) SSDR_CUDA(cudaMemcpyAsync(pcm_i16, h->d_i16, tot * sizeof(int16_t), cudaMemcpyDeviceToHost, h->compute));
-    if (rssi_dbm) SSDR_CUDA(cudaMemcpyAsync(rssi_dbm, h->d_rssi, tot / SSDR_FRAME * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
+    // block length: ~64 MiB of input per block, whole frames, at least one frame
+    const int nblk_total = n_samples / SSDR_FRAME;
+    int fpb = (int)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)h->batch * SSDR_FRAME * sb));
+    fpb = std::min(fpb, nblk_total);
+    const size_t pitch_b = (size_t)n_samples;                     // device staging keeps the caller's [batch][n_samples] layout
+    unsigned char* d_iq = static_cast<unsigned char*>(h->d_in);
+    for (int f0 = 0; f0 < nblk_total; f0 += fpb) {
+        const int nf = std::min(fpb, nblk_total - f0);
+        const size_t s0 = (size_t)f0 * SSDR_FRAME, ns = (size_t)nf * SSDR_FRAME;
+        SSDR_CUDA(cudaMemcpy2DAsync(d_iq + s0 * sb, pitch_b * sb, static_cast<const unsigned char*>(iq_host) + s0 * sb, pitch_b * sb,
+                                    ns * sb, (size_t)h->batch, cudaMemcpyHostToDevice, h->copy_in));
+        SSDR_CUDA(cudaEventRecord(h->ev_copied[0], h->copy_in));
+        SSDR_CUDA(cudaStreamWaitEvent(h->compute, h->ev_copied[0], 0));
+        if ((rc = demod_launch_block(h, d_iq + s0 * sb, iq_format, (int)ns, n_samples, pcm_f32 ? h->d_f32 + s0 : nullptr,
+                                     pcm_i16 ? h->d_i16 + s0 : nullptr, rssi_dbm ? h->d_rssi + f0 : nullptr))) return rc;
+        SSDR_CUDA(cudaEventRecord(h->ev_done, h->compute));
+        SSDR_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_done, 0));
+        if (pcm_f32) SSDR_CUDA(cudaMemcpy2DAsync(pcm_f32 + s0, pitch_b * sizeof(float), h->d_f32 + s0, pitch_b * sizeof(float),
+                                                 ns * sizeof(float), (size_t)h->batch, cudaMemcpyDeviceToHost, h->copy_out));
+        if (pcm_i16) SSDR_CUDA(cudaMemcpy2DAsync(pcm_i16 + s0, pitch_b * sizeof(int16_t), h->d_i16 + s0, pitch_b * sizeof(int16_t),
+                                                 ns * sizeof(int16_t), (size_t)h->batch, cudaMemcpyDeviceToHost, h->copy_out));
+    }
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    if (rssi_dbm) SSDR_CUDA(cudaMemcpyAsync(rssi_dbm, h->d_rssi, (size_t)h->batch * nblk_total * sizeof(float), cudaMemcpyDeviceToHost, h->copy_out));
+    SSDR_CUDA(cudaStreamSynchronize(h->copy_out));
+    SSDR_CUDA(cudaStreamSynchronize(h->copy_in));
     return SSDR_OK;
 }
 

@@ -42,6 +42,7 @@ struct DemodKernelParams {
     int16_t* pcm_i16;
     float* rssi;
     int batch, n_samples;
+    int pitch;                // samples between consecutive channels in iq / pcm (>= n_samples); rssi rows are pitch/512 apart
     double am_pow16[5];       // ((1-beta)^16)^(2^s)
 };
 
@@ -56,6 +57,7 @@ struct DemodLaunch {
     int16_t* pcm_i16 = nullptr;
     float* rssi = nullptr;
     int batch = 0, n_samples = 0;
+    int pitch = 0;            // 0 = n_samples (dense)
     double am_pow16[5] = {0, 0, 0, 0, 0};
 };
 

@@ -107,7 +107,7 @@ demod_kernel(const DemodKernelParams kp) {
         __syncwarp();
 
         for (int b = 0; b < nblk; ++b) {
-            const size_t s0 = (size_t)ch * kp.n_samples + (size_t)b * FR;
+            const size_t s0 = (size_t)ch * kp.pitch + (size_t)b * FR;
             // ---- mixer: lane-strided, coalesced --------------------------------------------
 #pragma unroll 4
             for (int r = 0; r < SPL; ++r) {
@@ -164,7 +164,7 @@ demod_kernel(const DemodKernelParams kp) {
             }
             if (kp.rssi && lane == 0) {
                 float mp = fmaxf(psum * (1.0f / FR), 1e-30f);
-                kp.rssi[(size_t)ch * nblk + b] = 10.0f * log10f(mp * (1.0f / (SSDR_FS * SSDR_FS))) + kDemodFsDbm;
+                kp.rssi[(size_t)ch * (kp.pitch / FR) + b] = 10.0f * log10f(mp * (1.0f / (SSDR_FS * SSDR_FS))) + kDemodFsDbm;
             }
             // ---- detector --------------------------------------------------------------------------
             float a[SPL];
@@ -317,7 +317,7 @@ int demod_launch(const DemodLaunch& a, cudaStream_t st) {
     DemodKernelParams kp;
     kp.iq = a.iq; kp.chan = a.chan; kp.state = a.state; kp.hist = a.hist; kp.taps = a.taps;
     kp.pcm_f32 = a.pcm_f32; kp.pcm_i16 = a.pcm_i16; kp.rssi = a.rssi;
-    kp.batch = a.batch; kp.n_samples = a.n_samples;
+    kp.batch = a.batch; kp.n_samples = a.n_samples; kp.pitch = a.pitch ? a.pitch : a.n_samples;
     for (int s = 0; s < 5; ++s) kp.am_pow16[s] = a.am_pow16[s];
     const size_t smem = sizeof(WarpSmem) * WARPS;
     auto kern = (a.iq_format == SSDR_IQ_CF32) ? demod_kernel<SSDR_IQ_CF32> : demod_kernel<SSDR_IQ_S16BE>;

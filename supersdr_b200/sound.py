@@ -82,8 +82,9 @@ class DemodBank:
     def reset(self):
         check(lib.ssdr_demod_reset(self._h))
 
-    def process(self, iq, want_f32=True, want_i16=True, want_rssi=True):
-        """iq: complex64[B, n] or uint8[B, n, 4] wire bytes; n a multiple of 512."""
+    def process(self, iq, want_f32=True, want_i16=True, want_rssi=True, out=None):
+        """iq: complex64[B, n] or uint8[B, n, 4] wire bytes; n a multiple of 512.  ``out`` may hold caller-owned
+        (ideally pinned) result arrays under the keys ``pcm_f32`` / ``pcm_i16`` / ``rssi``."""
         iq = np.asarray(iq)
         if iq.dtype == np.complex64:
             fmt, n = _lib.SSDR_IQ_CF32, iq.shape[-1]
@@ -96,9 +97,20 @@ class DemodBank:
         if not ok:
             raise ValueError("iq shape %s does not match batch %d" % (iq.shape, self.batch))
         iq = np.ascontiguousarray(iq)
-        f32 = np.empty((self.batch, n), np.float32) if want_f32 else None
-        i16 = np.empty((self.batch, n), np.int16) if want_i16 else None
-        rssi = np.empty((self.batch, n // _lib.FRAME), np.float32) if want_rssi else None
+        out = out or {}
+
+        def buf(key, want, shape, dtype):
+            if not want:
+                return None
+            a = out.get(key)
+            if a is None:
+                return np.empty(shape, dtype)
+            if a.shape != shape or a.dtype != dtype or not a.flags.c_contiguous:
+                raise ValueError("out[%r] must be a C-contiguous %s array of shape %s" % (key, np.dtype(dtype).name, shape))
+            return a
+        f32 = buf("pcm_f32", want_f32, (self.batch, n), np.float32)
+        i16 = buf("pcm_i16", want_i16, (self.batch, n), np.int16)
+        rssi = buf("rssi", want_rssi, (self.batch, n // _lib.FRAME), np.float32)
         check(lib.ssdr_demod_process(self._h, ptr(iq), fmt, int(n), ptr(f32), ptr(i16), ptr(rssi)))
         return dict(pcm_f32=f32, pcm_i16=i16, rssi=rssi)
 
