@@ -69,6 +69,11 @@ struct Cfg {
     static constexpr int TW1 = (NP == 3) ? 32 * 31 : 0;          // middle-pass twiddle table
     static constexpr int SWZ = (NP == 3) ? ilog2(R0) : -1;       // staging swizzle shift (colour stage)
     static constexpr int MIN_CTAS = (LG >= 14) ? 1 : 2;
+    static constexpr bool SPLIT = (FPC == 1 && G > 32);     // split-phase frame-buffer hand-off (mbarrier)
+    // Warps of a one-frame-per-SM group start their warp-local passes STAGGER cycles apart per level (4 levels, by
+    // warp / 4): in lock step all sixteen warps hit the shared-memory pipe and then the fp32 pipe together; staggered,
+    // one warp's loads overlap another's butterflies (measured: 2.26 -> 2.09 ms on config 2).
+    static constexpr int STAGGER = (LG == 14) ? 500 : 0;
     static_assert(NP == 2 || NP == 3, "supported sizes: 64 .. 16384");
     static_assert(M0 == 32 || M0 == 1024, "first pass leaves 32 or 1024 sub-transforms");
     // dynamic shared memory layout (bytes)
@@ -76,10 +81,16 @@ struct Cfg {
     static constexpr size_t SM_TW0 = SM_DATA + (size_t)FPC * PADN * sizeof(float2);
     static constexpr size_t SM_TW1 = SM_TW0 + (size_t)TW0 * sizeof(float2);
     static constexpr size_t SM_ACC = SM_TW1 + (size_t)TW1 * sizeof(float2);        // byte sums, thread-private uint4[4][THREADS]
-    static constexpr size_t SM_W1 = SM_ACC + (size_t)THREADS * 16 * sizeof(unsigned);   // wtab[j] of this thread's butterflies
-    static constexpr size_t SM_WIN = SM_W1 + (size_t)THREADS * NB0 * sizeof(float2);     // first half of the Hann window, N/2 floats
+    // W_N^j of the first-pass butterflies (chain passes only): LG 14 parks this thread's two values in a thread-private
+    // shared-memory column, LG 13 keeps its four in registers (the column would cost the second CTA per SM), smaller
+    // sizes share one table of M0 = 1024 entries
+    static constexpr int W1_MODE = (NP == 2) ? 0 : (LG == 14) ? 1 : (LG == 13) ? 2 : 3;
+    static constexpr size_t W1_BYTES = (W1_MODE == 1) ? (size_t)THREADS * NB0 * sizeof(float2) : (W1_MODE == 3) ? (size_t)M0 * sizeof(float2) : 0;
+    static constexpr size_t SM_W1 = SM_ACC + (size_t)THREADS * 16 * sizeof(unsigned);
+    static constexpr size_t SM_WIN = SM_W1 + W1_BYTES;                                   // first half of the Hann window, N/2 floats
     static constexpr size_t SM_RED = SM_WIN + (size_t)(N / 2) * sizeof(float);
-    static constexpr size_t SM_BYTES = SM_RED + (size_t)FPC * 8 * sizeof(int);
+    static constexpr size_t SM_MBAR = SM_RED + (size_t)FPC * 8 * sizeof(int);
+    static constexpr size_t SM_BYTES = SM_MBAR + 8;
 };
 
 struct WfKernelParams {
@@ -206,19 +217,14 @@ SSDR_DEV void first_load(float2 (&x)[C::R0], int i, int t, const void* src, size
 #endif
 }
 
-// First pass, part 2: window, radix-R0 butterflies, twiddles, scatter into the frame buffer.
+// First pass, part 2: window, radix-R0 butterfly and twiddles of butterfly i, in registers.
 template <class C, bool WINDOW>
-SSDR_DEV void first_compute(float2 (&x)[C::R0], int i, float2* d, const float2* tw0, const float* win, int t, float2 w1) {
+SSDR_DEV void first_math(float2 (&x)[C::R0], int i, const float2* tw0, const float* win, int t, float2 w1) {
     constexpr int R = C::R0, M = C::M0, G = C::G;
     constexpr bool TABLE = (M == 32);
     const int j = t + i * G;
 #if SSDR_EXP & 256
-    {
-        float2* o = TABLE ? d + j : d + j + 2 * (j >> 5);
-#pragma unroll
-        for (int q = 0; q < R; ++q) o[q * (M + M / 16)] = x[q];
-        return;
-    }
+    return;
 #endif
     if constexpr (WINDOW) {
         // Hann values of the samples j + m M, m < R/2 (all < N/2), from the shared-memory table; the other half
@@ -237,9 +243,36 @@ SSDR_DEV void first_compute(float2 (&x)[C::R0], int i, float2* d, const float2* 
     } else {
         tw_two_level<R>(x, w1);
     }
-    float2* o = TABLE ? d + j : d + j + 2 * (j >> 5);
+}
+
+// First pass, part 3: scatter the outputs of butterfly i into the frame buffer.
+template <class C>
+SSDR_DEV void first_store(const float2 (&x)[C::R0], int i, float2* d, int t) {
+    constexpr int R = C::R0, M = C::M0;
+    const int j = t + i * C::G;
+    float2* o = (M == 32) ? d + j : d + j + 2 * (j >> 5);
 #pragma unroll
     for (int q = 0; q < R; ++q) o[q * (M + M / 16)] = x[q];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split-phase hand-off of the frame buffer (one-CTA-per-frame sizes: LG 13, 14).  The buffer may be overwritten by
+// the next frame's first pass once every warp has LOADED its last-pass inputs: each warp arrives on an mbarrier
+// right after those loads and only waits just before its first store of the next frame -- after the butterfly,
+// quantiser and the next frame's first HBM loads and first butterfly, which need no shared memory.
+// ---------------------------------------------------------------------------------------------
+SSDR_DEV void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+SSDR_DEV void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+SSDR_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
 // radix-32 pass over sub-transforms of length 1024 (NP == 3 only): table twiddles W_1024^(j q)
@@ -286,7 +319,7 @@ SSDR_DEV void last_epilogue(float2 (&x)[32], uint4* accs, bool first_frame, cons
 
 // last radix-32 pass (sub-transform length 32, no twiddles) + power + byte + accumulate
 template <class C>
-SSDR_DEV void pass_last(const float2* d, int t, uint4* accs, bool first_frame, const WfKernelParams& kp) {
+SSDR_DEV void pass_last(const float2* d, int t, uint4* accs, bool first_frame, const WfKernelParams& kp, unsigned long long* bar) {
     const float4* p = reinterpret_cast<const float4*>(d + 34 * t);       // 272-byte thread stride: 16-byte aligned, conflict-free
     float2 x[32];
 #pragma unroll
@@ -294,6 +327,10 @@ SSDR_DEV void pass_last(const float2* d, int t, uint4* accs, bool first_frame, c
         const float4 v = p[m];
         x[2 * m] = make_float2(v.x, v.y);
         x[2 * m + 1] = make_float2(v.z, v.w);
+    }
+    if constexpr (C::SPLIT) {                 // this warp no longer needs the frame buffer
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
     }
 #if !(SSDR_EXP & 4)
     dft<32>(x);
@@ -549,10 +586,31 @@ wf_fft_kernel(const WfKernelParams kp) {
 
     // (cos, -sin)(2 pi j / N) of this thread's first-pass butterflies (window + first twiddle level):
     // loop invariant, parked in a thread-private shared-memory column (short, fixed latency)
-    float2* w1s = reinterpret_cast<float2*>(smem + C::SM_W1) + threadIdx.x;
+    float2* w1s = reinterpret_cast<float2*>(smem + C::SM_W1);
+    float2 w1r[C::W1_MODE == 2 ? C::NB0 : 1];
+    if constexpr (C::W1_MODE == 1) {
 #pragma unroll
-    for (int i = 0; i < C::NB0; ++i) w1s[i * C::THREADS] = __ldg(kp.wtab + t + i * G);
-    auto w1_of = [&](int i) -> float2 { return w1s[i * C::THREADS]; };
+        for (int i = 0; i < C::NB0; ++i) w1s[threadIdx.x + i * C::THREADS] = __ldg(kp.wtab + t + i * G);
+    } else if constexpr (C::W1_MODE == 2) {
+#pragma unroll
+        for (int i = 0; i < C::NB0; ++i) w1r[i] = __ldg(kp.wtab + t + i * G);
+    } else if constexpr (C::W1_MODE == 3) {
+        for (int e = threadIdx.x; e < C::M0; e += blockDim.x) w1s[e] = kp.wtab[e];
+        __syncthreads();
+    }
+    auto w1_of = [&](int i) -> float2 {
+        if constexpr (C::W1_MODE == 1) return w1s[threadIdx.x + i * C::THREADS];
+        else if constexpr (C::W1_MODE == 2) return w1r[i];
+        else if constexpr (C::W1_MODE == 3) return w1s[t + i * G];
+        else return make_float2(1.f, 0.f);
+    };
+
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + C::SM_MBAR);
+    unsigned frames_done = 0;                 // frames this group has finished (mbarrier phase counter)
+    if constexpr (C::SPLIT) {
+        if (threadIdx.x == 0) mbar_init(bar, G / 32);
+        __syncthreads();
+    }
 
     constexpr unsigned sample_bytes = (FMT == SSDR_IQ_CF32) ? 8u : 4u;
     const int ch_stride = (int)gridDim.x * FPC;
@@ -569,11 +627,20 @@ wf_fft_kernel(const WfKernelParams kp) {
                 if (!last || ch + ch_stride < kp.batch)
                     prefetch_l2(static_cast<const unsigned char*>(kp.iq) + nxt * sample_bytes, (unsigned)N * sample_bytes);
             }
+            // Before the first store of this frame every thread of the group must have finished reading the previous
+            // frame (or row).  SPLIT: the first butterfly (and the loads of the second) come first, then the wait on
+            // the warps' arrivals of the previous frame; the row of the previous channel is covered by the barrier
+            // after the colour stage.  Otherwise: one group barrier.
+            auto buffer_free = [&]() {
 #if !(SSDR_EXP & 64)
-            group_sync<C>(slot);              // every thread of the group has finished reading the previous frame (or row)
+                if constexpr (C::SPLIT) { if (frames_done) mbar_wait(bar, (frames_done - 1) & 1u); }
+                else group_sync<C>(slot);
 #endif
+            };
             if constexpr (C::NB0 == 1) {
-                first_compute<C, WINDOW>(x0, 0, d, tw0, win, t, w1_of(0));
+                first_math<C, WINDOW>(x0, 0, tw0, win, t, w1_of(0));
+                buffer_free();
+                first_store<C>(x0, 0, d, t);
             } else {
                 // software pipeline over this thread's first-pass butterflies: load i + 1 while i computes
                 float2 xa[C::R0], xb[C::R0];
@@ -582,22 +649,30 @@ wf_fft_kernel(const WfKernelParams kp) {
 #pragma unroll
                 for (int i = 0; i < C::NB0; i += 2) {
                     first_load<C, FMT>(xb, i + 1, t, kp.iq, off);
-                    first_compute<C, WINDOW>(xa, i, d, tw0, win, t, w1_of(i));
+                    first_math<C, WINDOW>(xa, i, tw0, win, t, w1_of(i));
+                    if (i == 0) buffer_free();
+                    first_store<C>(xa, i, d, t);
                     if (i + 2 < C::NB0) first_load<C, FMT>(xa, i + 2, t, kp.iq, off);
-                    first_compute<C, WINDOW>(xb, i + 1, d, tw0, win, t, w1_of(i + 1));
+                    first_math<C, WINDOW>(xb, i + 1, tw0, win, t, w1_of(i + 1));
+                    first_store<C>(xb, i + 1, d, t);
                 }
             }
 #if !(SSDR_EXP & 128)
             group_sync<C>(slot);
 #endif
             // from here each warp owns a contiguous 1024-point (NP == 3) / 32-point sub-transform: warp-local
+            if constexpr (C::STAGGER > 0) {
+                const int lvl = (threadIdx.x >> 7) & 3;
+                if (lvl) { const long long c0 = clock64(); while (clock64() - c0 < lvl * C::STAGGER) { } }
+            }
 #if !(SSDR_EXP & 16)
             if constexpr (C::NP == 3) {
                 pass_mid<C>(d, tw1, t);
                 __syncwarp();
             }
 #endif
-            pass_last<C>(d, t, accs, f == 0, kp);
+            pass_last<C>(d, t, accs, f == 0, kp, bar);
+            ++frames_done;
             off += N;
             if (f + 1 < kp.n_avg) first_load<C, FMT>(x0, 0, t, kp.iq, off);
         }
@@ -613,6 +688,7 @@ wf_fft_kernel(const WfKernelParams kp) {
         colour_stage<C, false>(reinterpret_cast<float*>(d), red, slot, t, ch, acc, kp,
                                (C::NP == 3) ? ((t >> 5) + C::R0 * (t & 31)) : t, (C::NP == 3) ? 32 : 1);
 #endif
+        if constexpr (C::SPLIT) group_sync<C>(slot);     // the row stage has been read before the next channel's first store
     }
 }
 

@@ -70,6 +70,32 @@ def test_demod_mixed_modes_and_chunking(ssdr):
     one.close(); cut.close()
 
 
+def test_demod_host_pipeline_time_blocks(ssdr):
+    """A call large enough to be cut into several time blocks by the host pipeline (ssdr_demod_process: > 64 MiB of
+    input) gives, per channel, exactly what one small call gives, into caller-owned output buffers."""
+    modes = ["usb", "am", "nbfm", "cw"]
+    B, n = 640, 512 * 48                                   # 126 MB of complex64 -> 2 blocks
+    src = np.stack([tier_u.synth_demod_iq(m, n, seed=21 + i) for i, m in enumerate(modes)])
+    iq = np.ascontiguousarray(src[np.arange(B) % 4])
+    params = [ssdr.demod_params(modes[b % 4], hang=(b % 4 == 3)) for b in range(B)]
+    big = ssdr.DemodBank(B, n)
+    big.set_params(0, params)
+    out = {"pcm_f32": np.empty((B, n), np.float32), "pcm_i16": np.empty((B, n), np.int16), "rssi": np.empty((B, n // 512), np.float32)}
+    res = big.process(iq, out=out)
+    assert res["pcm_f32"] is out["pcm_f32"] and res["rssi"] is out["rssi"]
+    small = ssdr.DemodBank(4, n)
+    small.set_params(0, params[:4])
+    ref = small.process(src)
+    for k in ("pcm_f32", "pcm_i16", "rssi"):
+        assert np.array_equal(res[k][:4], ref[k])
+        assert np.array_equal(res[k], res[k][np.arange(B) % 4])          # replicas of a channel are identical
+    o, _ = tier_u.demod(src[0], tier_u.DemodParams("usb"), tier_u.DemodState())
+    assert _rel_rms(res["pcm_f32"][B - 4], o) < RMS_TOL
+    with pytest.raises(ValueError):
+        big.process(iq, out={"pcm_f32": np.empty((B, n), np.float64)})
+    big.close(); small.close()
+
+
 def test_demod_wire_format_and_sideband_rejection(ssdr):
     n = 512 * 16
     iq = tier_u.synth_demod_iq("usb", n, seed=4)
