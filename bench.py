@@ -121,16 +121,22 @@ def cpu_waterfall_rows(iq, threads):
 
 
 def cpu_baseline(target_s=12.0):
+    """The numpy/scipy statement on all host cores over a bounded sample: 256-channel tiles of the workload, repeated
+    until about ``target_s`` seconds of CPU work have been timed."""
     from oracle import tier_u
     cores = os.cpu_count() or 1
-    probe = tier_u.synth_batch(4, N_AVG, NFFT, seed=1)
-    t = time.perf_counter(); cpu_waterfall_rows(probe, cores); dt = time.perf_counter() - t
-    nch = int(max(4, min(256, 4 * target_s / max(dt, 1e-3))))
-    iq = np.tile(probe, (nch // 4 + 1, 1, 1))[:nch]
-    t = time.perf_counter(); cpu_waterfall_rows(iq, cores); dt = time.perf_counter() - t
-    return {"value": nch * N_AVG * NFFT / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
-            "sample": "%d of 4096 channels x %d x %d, scipy.fft(workers=%d) + numpy epilogue + per-row "
-                      "spectrum_db2col restatement (oracle/tier_p.py); %.1f s" % (nch, N_AVG, NFFT, cores, dt)}
+    tile = np.tile(tier_u.synth_batch(8, N_AVG, NFFT, seed=1), (32, 1, 1))        # 256 channels x 10 x 16384
+    cpu_waterfall_rows(tile[:32], cores)                                           # warm-up (imports, FFT plans)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        cpu_waterfall_rows(tile, cores)
+        done += tile.shape[0]
+        dt = time.perf_counter() - t0
+        if dt >= target_s or done >= B_PER_GPU:
+            break
+    return {"value": done * N_AVG * NFFT / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": "%d of 4096 channels x %d x %d (256-channel tiles), scipy.fft(workers=%d) + numpy epilogue + per-row "
+                      "spectrum_db2col restatement (oracle/tier_p.py); %.1f s of CPU work" % (done, N_AVG, NFFT, cores, dt)}
 
 
 def run_reference(args, rank, world):
@@ -139,8 +145,8 @@ def run_reference(args, rank, world):
         return
     from oracle import tier_u
     cores = os.cpu_count() or 1
-    nch = 16
-    iq = tier_u.synth_batch(nch, N_AVG, NFFT, seed=7)
+    nch = 128
+    iq = np.tile(tier_u.synth_batch(8, N_AVG, NFFT, seed=7), (16, 1, 1))
     for _ in range(max(args.warmup, 1)):
         cpu_waterfall_rows(iq, cores)
     t = time.perf_counter()

@@ -73,7 +73,10 @@ struct Cfg {
     // Warps of a one-frame-per-SM group start their warp-local passes STAGGER cycles apart per level (4 levels, by
     // warp / 4): in lock step all sixteen warps hit the shared-memory pipe and then the fp32 pipe together; staggered,
     // one warp's loads overlap another's butterflies (measured: 2.26 -> 2.09 ms on config 2).
-    static constexpr int STAGGER = (LG == 14) ? 500 : 0;
+#ifndef SSDR_STAGGER
+#define SSDR_STAGGER 500
+#endif
+    static constexpr int STAGGER = (LG == 14) ? SSDR_STAGGER : 0;
     static_assert(NP == 2 || NP == 3, "supported sizes: 64 .. 16384");
     static_assert(M0 == 32 || M0 == 1024, "first pass leaves 32 or 1024 sub-transforms");
     // dynamic shared memory layout (bytes)
