@@ -395,7 +395,7 @@ SSDR_DEV float div_rn(float a, const Divisor& d) {
 // Groups are independent: every barrier below is group-scoped.
 template <class C, bool LINEAR>
 SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsigned (&acc)[16], const WfKernelParams& kp,
-                            int kb, int tB) {
+                            int kb, int tB, int stage_words) {
     constexpr int N = C::N, G = C::G;
     const int lane = threadIdx.x & 31;
     const unsigned gmask = group_mask<G>(lane);
@@ -410,7 +410,7 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
     constexpr int q0 = LINEAR ? 0 : 16, q1 = LINEAR ? 1 : 16;
     auto key_at = [&](int q) -> unsigned { return (q & 1) ? (acc[q >> 1] >> 16) : (acc[q >> 1] & 0xffffu); };
     if (t == tB) red[5] = (int)key_at(q1);
-    if (t == 0) { red[0] = 0; red[1] = 0; red[2] = 0; red[3] = 0; red[4] = 0x7fffffff; }
+    if (t == 0) { red[0] = 0; red[1] = 0; red[2] = 0x7fffffff; red[3] = 0; red[4] = 0x7fffffff; }
     group_sync<C>(slot);
     unsigned raw0 = 0;
     if (t == 0) {
@@ -448,9 +448,61 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
     const int vmax = kmax;
 
     if (dp.auto_scale) {          // group-uniform
+        const int want = kp.p_lo + 1;
+        int v_lo, cnt_lo, mn = 0x7fffffff;
+        const int nbins = 255 * kp.n_avg + 1;
+        if (G >= 256 && nbins + 32 <= stage_words) {
+            // ---- rank p_lo (0-based) from a histogram of the keys in the (idle) frame buffer: 32 shared-memory
+            // atomics per thread, one scan.  The first barrier above already ordered every warp's last FFT pass.
+            unsigned* hist = reinterpret_cast<unsigned*>(stage);
+            int kmin = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) kmin = min(kmin, (int)min(acc[i] & 0xffffu, acc[i] >> 16));
+            kmin = __reduce_min_sync(gmask, kmin);
+            if (leader) atomicMin(&red[2], kmin);              // red[2] was set to INT_MAX below (see init)
+            for (int i = t; i < nbins + 32; i += G) hist[i] = 0u;
+            group_sync<C>(slot);
+            kmin = red[2];
+            if (kmin == vmax) {                                 // a constant row: every key is the same value
+                v_lo = vmax; cnt_lo = N;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) atomicAdd(&hist[key_at(q)], 1u);
+                group_sync<C>(slot);
+                const int cpt = ((nbins + G - 1) / G) | 1;      // odd chunk length: conflict-free chunk walks
+                const int b0 = t * cpt, b1 = min(b0 + cpt, nbins);
+                int sum = 0;
+                for (int b = b0; b < b1; ++b) sum += (int)hist[b];
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+                if (lane == 31) hist[nbins + (t >> 5)] = (unsigned)incl;
+                group_sync<C>(slot);
+                int prefix = incl - sum;
+                for (int w = 0; w < (t >> 5); ++w) prefix += (int)hist[nbins + w];
+                if (prefix < want && want <= prefix + sum) {    // exactly one thread owns the rank
+                    int c = prefix, b = b0;
+                    for (; b < b1; ++b) { c += (int)hist[b]; if (c >= want) break; }
+                    red[0] = b; red[1] = c;
+                }
+                group_sync<C>(slot);
+                v_lo = red[0]; cnt_lo = red[1];
+            }
+            // min{key > v_lo}
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int a = (int)(acc[i] & 0xffffu), b = (int)(acc[i] >> 16);
+                if (a > v_lo) mn = min(mn, a);
+                if (b > v_lo) mn = min(mn, b);
+            }
+            mn = __reduce_min_sync(gmask, mn);
+            if (leader) atomicMin(&red[4], mn);
+            group_sync<C>(slot);
+            mn = red[4];
+        } else {
         // ---- rank p_lo (0-based) by bisection on the key bits: smallest v with count(keys <= v) >= p_lo + 1.
         // Packed count: keys < 2^15, so (mid + 0x8000 - key) has bit 15 set iff key <= mid, per 16-bit half.
-        const int want = kp.p_lo + 1;
+        if constexpr (G > 32) { if (t == 0) red[2] = 0; group_sync<C>(slot); }     // red[2] doubles as a bisection slot
         int lo = 0, hi = (1 << kp.key_bits) - 1;
 #pragma unroll 1
         for (int it = 0; it < kp.key_bits; ++it) {
@@ -463,9 +515,9 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
             if (total >= want) hi = mid; else lo = mid + 1;
             if constexpr (G > 32) { if (t == 0) red[(it + 2) % 3] = 0; }   // read by everyone before the previous barrier
         }
-        const int v_lo = hi;
+        v_lo = hi;
         // count(keys <= v_lo) and min{key > v_lo}
-        int c = 0, mn = 0x7fffffff;
+        int c = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int a = (int)(acc[i] & 0xffffu), b = (int)(acc[i] >> 16);
@@ -480,8 +532,9 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
             group_sync<C>(slot);
             if (leader) atomicMin(&red[4], mn);
         }
-        const int cnt_lo = group_sum(c, 0);
+        cnt_lo = group_sum(c, 0);
         if constexpr (G > 32) mn = red[4];
+        }
         const int v_hi = (cnt_lo >= want + 1 || mn == 0x7fffffff) ? v_lo : mn;
         // numpy _lerp in float32
         const float a = wfdb((float)v_lo), b = wfdb((float)v_hi), g = kp.p_gamma;
@@ -689,7 +742,7 @@ wf_fft_kernel(const WfKernelParams kp) {
         if (acc[0] == 0x12345678u) kp.pixels[ch] = (uint8_t)acc[1];
 #else
         colour_stage<C, false>(reinterpret_cast<float*>(d), red, slot, t, ch, acc, kp,
-                               (C::NP == 3) ? ((t >> 5) + C::R0 * (t & 31)) : t, (C::NP == 3) ? 32 : 1);
+                               (C::NP == 3) ? ((t >> 5) + C::R0 * (t & 31)) : t, (C::NP == 3) ? 32 : 1, 2 * C::PADN);
 #endif
         if constexpr (C::SPLIT) group_sync<C>(slot);     // the row stage has been read before the next channel's first store
     }
@@ -726,7 +779,7 @@ wf_colorrow_kernel(const WfKernelParams kp) {
             }
         }
         group_sync<C>(slot);          // the previous row's transposed reads are done
-        colour_stage<C, true>(stage, red, slot, t, ch, acc, kp, 0, 0);
+        colour_stage<C, true>(stage, red, slot, t, ch, acc, kp, 0, 0, C::PADN);
     }
 }
 
