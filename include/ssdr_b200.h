@@ -108,7 +108,8 @@ typedef struct {
     float low_clip_db, high_clip_db, dynamic_range, wf_min_db, wf_max_db;
 } ssdr_wf_scalars_t;
 
-/* nfft: power of two 256..16384 (WF_BINS); batch: channels; n_avg: averaging_n 1..100;
+/* nfft: power of two 256..65536 (WF_BINS; 32768 and 65536 take a three-kernel path through an HBM scratch
+ * buffer); batch: channels; n_avg: averaging_n 1..100;
  * window: 1 = Hann, 0 = rectangular; cal_db: dBFS->dBm offset (SSDR_WF_CAL_DB).
  * p_lo/p_gamma: lower index and float32 weight of numpy's 40th-percentile interpolation for
  * nfft points, computed by the caller with numpy's own expression. */

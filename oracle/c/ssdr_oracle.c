@@ -53,9 +53,16 @@ int so_fft_plan(int N, int* radices) {
     int lg = 0;
     while ((1 << lg) < N) lg++;
     if ((1 << lg) != N || lg < 6 || lg > 16) return -1;
-    /* lg = r + 5k: one first pass of radix 2^r (r = 1..4; a radix-32 pass when r == 0) that reads
-     * the input and applies the window, followed by k radix-32 passes. */
-    int np = 0, k = lg / 5, r = lg - 5 * k;
+    /* lg <= 14: lg = r + 5k: one first pass of radix 2^r (r = 1..4; a radix-32 pass when r == 0) that reads
+     * the input and applies the window, followed by k radix-32 passes.
+     * lg = 15, 16: a front pass of radix 2^(lg - 14) (window, chain twiddles) followed by the 16384-point plan
+     * 16 x 32 x 32 -- the frame no longer fits one SM's shared memory, the front pass is its own kernel. */
+    int np = 0;
+    if (lg > 14) {
+        radices[np++] = 1 << (lg - 14);
+        lg = 14;
+    }
+    int k = lg / 5, r = lg - 5 * k;
     if (r == 0) { r = 5; k -= 1; }
     radices[np++] = 1 << r;
     for (int i = 0; i < k; ++i) radices[np++] = 32;

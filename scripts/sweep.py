@@ -9,7 +9,7 @@ import supersdr_b200 as S
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--sizes", default="256,512,1024,2048,4096,8192,16384")
+    ap.add_argument("--sizes", default="256,512,1024,2048,4096,8192,16384,32768,65536")
     ap.add_argument("--batches", default="1,16,256,4096,65536")
     ap.add_argument("--n-avg", type=int, default=1)
     ap.add_argument("--fmt", default="cf32", choices=["cf32", "s16be"])
@@ -40,7 +40,10 @@ def main():
             print(json.dumps({"nfft": N, "batch": B, "n_avg": a.n_avg, "fmt": a.fmt, "ms": round(ms, 5),
                               "msamples_per_s": round(B * a.n_avg * N / ms / 1e3, 1), "gbs": round(alg / ms / 1e6, 1),
                               "frac_of_measured_hbm": round(alg / ms / 1e6 / peak, 4),
-                              "l2_resident": in_bytes < 126e6}), flush=True)
+                              "l2_resident": in_bytes < 126e6,
+                              # N > 16384: front pass + scratch round trip: 3x the single-pass input bytes move
+                              "hbm_passes": 3 if N > 16384 else 1,
+                              "moved_gbs": round((alg + (2 * in_bytes if N > 16384 else 0)) / ms / 1e6, 1)}), flush=True)
             bank.close(); iq.free(); px.free()
 
 

@@ -63,6 +63,11 @@ struct ssdr_wf {
     std::vector<float> h_wtab, h_thr, h_win;
     float* d_wtab = nullptr;
     float* d_win = nullptr;
+    // large-N path (nfft > 16384)
+    float* d_wtab_sub = nullptr;      // 16384-point twiddle table of the sub-transforms
+    void* d_scratch = nullptr;        // front-pass output, sized for scratch_ch channels
+    int scratch_ch = 0;
+    uint16_t* d_sums = nullptr;       // [batch][nfft]
     float* d_thr = nullptr;
     ssdr_wf_display_t* d_disp = nullptr;
     cudaStream_t compute = nullptr, copy = nullptr;
@@ -173,7 +178,7 @@ int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, d
     SSDR_ARG(out != nullptr, "null handle pointer");
     *out = nullptr;
     int radices[8];
-    SSDR_ARG(wf_plan(nfft, radices) > 0, "nfft %d unsupported (power of two 256..16384)", nfft);
+    SSDR_ARG(wf_plan(nfft, radices) > 0, "nfft %d unsupported (power of two 256..65536)", nfft);
     SSDR_ARG(batch >= 1, "batch %d < 1", batch);
     SSDR_ARG(n_avg >= 1 && n_avg <= 100, "n_avg %d outside 1..100 (supersdr.py:376-385)", n_avg);
     SSDR_ARG(p_lo >= 0 && p_lo < nfft && p_gamma >= 0.f && p_gamma < 1.f, "bad percentile index (%d, %g)", p_lo, (double)p_gamma);
@@ -205,6 +210,17 @@ int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, d
     if ((rc = dev_alloc(&h->d_wtab, 2 * (size_t)nfft))) return fail(rc);
     if ((rc = dev_alloc(&h->d_thr, 257))) return fail(rc);
     if ((rc = dev_alloc(&h->d_win, (size_t)nfft / 2))) return fail(rc);
+    if (nfft > 16384) {
+        std::vector<float> sub(2 * 16384);
+        for (int k = 0; k < 16384; ++k) {
+            double a = 2.0 * 3.14159265358979323846 * (double)k / 16384.0;
+            sub[2 * k] = (float)std::cos(a);
+            sub[2 * k + 1] = (float)(-std::sin(a));
+        }
+        if ((rc = dev_alloc(&h->d_wtab_sub, sub.size()))) return fail(rc);
+        if ((rc = dev_alloc(&h->d_sums, (size_t)batch * nfft))) return fail(rc);
+        if (cudaMemcpy(h->d_wtab_sub, sub.data(), sizeof(float) * sub.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("table upload failed"); return fail(SSDR_E_CUDA); }
+    }
     if ((rc = dev_alloc(&h->d_disp, (size_t)batch))) return fail(rc);
     if ((rc = dev_alloc(&h->d_sc, (size_t)batch))) return fail(rc);
     if (cudaMemcpy(h->d_wtab, h->h_wtab.data(), sizeof(float) * 2 * nfft, cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -231,7 +247,7 @@ int ssdr_wf_destroy(ssdr_wf_t h) {
     if (!h) return SSDR_OK;
     if (h->compute) cudaStreamSynchronize(h->compute);
     if (h->copy) cudaStreamSynchronize(h->copy);
-    cudaFree(h->d_wtab); cudaFree(h->d_win); cudaFree(h->d_thr); cudaFree(h->d_disp); cudaFree(h->d_in[0]); cudaFree(h->d_in[1]);
+    cudaFree(h->d_wtab); cudaFree(h->d_win); cudaFree(h->d_wtab_sub); cudaFree(h->d_scratch); cudaFree(h->d_sums); cudaFree(h->d_thr); cudaFree(h->d_disp); cudaFree(h->d_in[0]); cudaFree(h->d_in[1]);
     cudaFree(h->d_px); cudaFree(h->d_col); cudaFree(h->d_spec); cudaFree(h->d_sc);
     for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -270,13 +286,27 @@ static WfLaunch wf_base(ssdr_wf_t h) {
     WfLaunch a;
     a.wtab = h->d_wtab; a.win = h->d_win; a.thr = h->d_thr; a.nfft = h->nfft; a.n_avg = h->n_avg; a.window = h->window;
     a.p_lo = h->p_lo; a.p_gamma = h->p_gamma; a.est_c1 = h->est_c1; a.est_c0 = h->est_c0;
+    a.wtab_sub = h->d_wtab_sub; a.scratch = h->d_scratch; a.sums = h->d_sums;
     return a;
+}
+
+// large-N path: the front-pass scratch holds `channels` channels (complex64, same size as their input)
+static int wf_ensure_scratch(ssdr_wf_t h, int channels) {
+    if (h->nfft <= 16384 || h->scratch_ch >= channels) return SSDR_OK;
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    cudaFree(h->d_scratch); h->d_scratch = nullptr; h->scratch_ch = 0;
+    int rc = dev_alloc(reinterpret_cast<unsigned char**>(&h->d_scratch), (size_t)channels * h->n_avg * h->nfft * 8);
+    if (rc) return rc;
+    h->scratch_ch = channels;
+    return SSDR_OK;
 }
 
 int ssdr_wf_process_dev(ssdr_wf_t h, const void* iq_dev, int iq_format, uint8_t* pixels_dev, float* colour_dev,
                         float* spectrum_dev, ssdr_wf_scalars_t* scalars_dev) {
     SSDR_ARG(h && iq_dev, "null argument");
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
+    int rcs = wf_ensure_scratch(h, h->batch);
+    if (rcs) return rcs;
     WfLaunch a = wf_base(h);
     a.iq = iq_dev; a.iq_format = iq_format; a.disp = h->d_disp; a.batch = h->batch;
     a.pixels = pixels_dev; a.colour = colour_dev; a.spectrum = spectrum_dev; a.scalars = scalars_dev ? scalars_dev : h->d_sc;
@@ -286,6 +316,7 @@ int ssdr_wf_process_dev(ssdr_wf_t h, const void* iq_dev, int iq_format, uint8_t*
 int ssdr_wf_colorrow_u8_dev(ssdr_wf_t h, const uint8_t* lines_dev, uint8_t* pixels_dev, float* colour_dev,
                             float* spectrum_dev, ssdr_wf_scalars_t* scalars_dev) {
     SSDR_ARG(h && lines_dev, "null argument");
+    SSDR_ARG(h->nfft <= 16384, "the uint8-line entry supports nfft <= 16384 (got %d)", h->nfft);
     WfLaunch a = wf_base(h);
     a.lines = lines_dev; a.disp = h->d_disp; a.batch = h->batch;
     a.pixels = pixels_dev; a.colour = colour_dev; a.spectrum = spectrum_dev; a.scalars = scalars_dev ? scalars_dev : h->d_sc;
@@ -326,6 +357,7 @@ static int wf_process_host(ssdr_wf_t h, const void* in_host, size_t bytes_per_ch
                            uint8_t* pixels, float* colour, float* spectrum, ssdr_wf_scalars_t* scalars) {
     int rc = wf_ensure_staging(h, bytes_per_channel, colour != nullptr, spectrum != nullptr);
     if (rc) return rc;
+    if (!lines && (rc = wf_ensure_scratch(h, h->chunk_ch))) return rc;
     const size_t N = (size_t)h->nfft;
     int slot = 0;
     for (int c0 = 0; c0 < h->batch; c0 += h->chunk_ch, slot ^= 1) {
@@ -340,6 +372,7 @@ static int wf_process_host(ssdr_wf_t h, const void* in_host, size_t bytes_per_ch
         if (lines) a.lines = static_cast<const uint8_t*>(h->d_in[slot]);
         else { a.iq = h->d_in[slot]; a.iq_format = iq_format; }
         a.disp = h->d_disp + c0; a.batch = nch;
+        if (a.sums) a.sums += (size_t)c0 * N;
         a.pixels = h->d_px + (size_t)c0 * N;
         a.colour = colour ? h->d_col + (size_t)c0 * N : nullptr;
         a.spectrum = spectrum ? h->d_spec + (size_t)c0 * N : nullptr;
@@ -368,6 +401,7 @@ int ssdr_wf_process(ssdr_wf_t h, const void* iq_host, int iq_format, uint8_t* pi
 int ssdr_wf_colorrow_u8(ssdr_wf_t h, const uint8_t* lines_host, uint8_t* pixels, float* colour, float* spectrum,
                         ssdr_wf_scalars_t* scalars) {
     SSDR_ARG(h && lines_host, "null argument");
+    SSDR_ARG(h->nfft <= 16384, "the uint8-line entry supports nfft <= 16384 (got %d)", h->nfft);
     return wf_process_host(h, lines_host, (size_t)h->n_avg * h->nfft, 0, true, pixels, colour, spectrum, scalars);
 }
 

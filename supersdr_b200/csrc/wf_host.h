@@ -15,6 +15,11 @@ struct WfLaunch {
     const float* wtab = nullptr;       // device, 2*nfft floats
     const float* win = nullptr;        // device, nfft/2 floats (first half of the Hann window)
     const float* thr = nullptr;        // device, 257 floats
+    // large-N path (nfft > 16384): twiddle table of the 16384-point sub-transforms, front-pass scratch
+    // [batch * rf][n_avg][16384] complex64 and byte sums [batch][nfft] uint16
+    const float* wtab_sub = nullptr;
+    void* scratch = nullptr;
+    uint16_t* sums = nullptr;
     ssdr_wf_display_t* disp = nullptr; // device, [batch]
     uint8_t* pixels = nullptr;
     float* colour = nullptr;

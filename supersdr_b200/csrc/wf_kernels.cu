@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <type_traits>
 #include <vector>
@@ -107,6 +108,8 @@ struct WfKernelParams {
     float* spectrum;                // [batch][N] or null
     ssdr_wf_scalars_t* scalars;     // [batch] or null
     const uint8_t* lines;           // colorrow entry: [batch][n_avg][N] uint8 lines (else null)
+    uint16_t* sums;                 // large-N path: per-bin byte sums out [batch / rf][rf * N] (no colour stage), else null
+    int rf;                         // large-N path: front radix (virtual channel = channel * rf + q)
     int batch, n_avg;
     int p_lo;
     float p_gamma;
@@ -612,6 +615,30 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
     // the caller's next barrier (before the frame buffer is written again) orders these reads
 }
 
+// Large-N path (N_total = rf * N): this group has the byte sums of sub-transform q of channel ch = vc / rf.
+// Global bin q + rf k goes to output index (q + rf k) ^ (N_total / 2) = q + rf (k ^ N/2): transpose the sums
+// to k order through shared memory exactly like the colour row, then store them rf apart (2 bytes each).
+template <class C>
+SSDR_DEV void sums_stage(unsigned* stage, int slot, int t, int vc, unsigned (&acc)[16], const WfKernelParams& kp, int kb) {
+    constexpr int N = C::N, G = C::G;
+    auto key_at = [&](int q) -> unsigned { return (q & 1) ? (acc[q >> 1] >> 16) : (acc[q >> 1] & 0xffffu); };
+    auto sidx = [](int o) -> int {
+        if constexpr (C::SWZ >= 0) return o ^ ((o >> C::SWZ) & 31);
+        else return o;
+    };
+    group_sync<C>(slot);                                   // every warp of the group is past its last FFT pass
+#pragma unroll
+    for (int q = 0; q < 32; ++q) stage[sidx(kb + G * (q ^ 16))] = key_at(q);
+    group_sync<C>(slot);
+    const int ch = vc / kp.rf, qf = vc - ch * kp.rf;
+    uint16_t* out = kp.sums + (size_t)ch * kp.rf * N + qf;
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+        const int o = t + i * G;
+        out[(size_t)o * kp.rf] = (uint16_t)stage[sidx(o)];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the fused waterfall kernel
 // ---------------------------------------------------------------------------------------------
@@ -741,6 +768,8 @@ wf_fft_kernel(const WfKernelParams kp) {
 #if SSDR_EXP & 2
         if (acc[0] == 0x12345678u) kp.pixels[ch] = (uint8_t)acc[1];
 #else
+        if (kp.sums) sums_stage<C>(reinterpret_cast<unsigned*>(d), slot, t, ch, acc, kp, (C::NP == 3) ? ((t >> 5) + C::R0 * (t & 31)) : t);
+        else
         colour_stage<C, false>(reinterpret_cast<float*>(d), red, slot, t, ch, acc, kp,
                                (C::NP == 3) ? ((t >> 5) + C::R0 * (t & 31)) : t, (C::NP == 3) ? 32 : 1, 2 * C::PADN);
 #endif
@@ -784,6 +813,143 @@ wf_colorrow_kernel(const WfKernelParams kp) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Large frames (N = 32768, 65536: more than one SM's shared memory).  Plan rf x 16 x 32 x 32:
+//   1. wf_front_kernel: the radix-rf front pass -- window, butterfly, chain twiddles W_N^(j q) -- over HBM:
+//      reads the frame once, writes the rf sub-frames y_q[j] (j < 16384) of every frame to a scratch buffer laid
+//      out as rf "virtual channels" per channel;
+//   2. wf_fft_kernel<14> without window on the scratch, in sums mode (per-bin byte sums, no colour stage);
+//   3. wf_colour_big_kernel: rank selection (histogram) + colour row over the N sums of a channel.
+// HBM traffic: 8 + 8 + 8 bytes per sample instead of 8 (stated in the roofline of these sizes).
+// ---------------------------------------------------------------------------------------------
+template <int RF, int FMT, bool WINDOW>
+__global__ void __launch_bounds__(256) wf_front_kernel(const void* __restrict__ iq, float2* __restrict__ scratch,
+                                                       const float2* __restrict__ wtab, const float* __restrict__ win,
+                                                       int batch, int n_avg) {
+    constexpr int M = 16384, N = RF * M;
+    const size_t total = (size_t)batch * n_avg * M;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e % M);
+        const size_t fr = e / M;                           // ch * n_avg + f
+        const size_t ch = fr / n_avg, f = fr - ch * n_avg;
+        float2 x[RF];
+#pragma unroll
+        for (int b = 0; b < RF; ++b) x[b] = load_iq<FMT>(iq, fr * N + (size_t)(j + b * M));
+        if constexpr (WINDOW) {
+            float wv[RF / 2];
+#pragma unroll
+            for (int m = 0; m < RF / 2; ++m) wv[m] = __ldg(win + j + m * M);
+            l1_window<RF>(x, wv);
+        } else {
+            l1<RF>(x);
+        }
+        dft_rest<RF>(x);
+        tw_two_level<RF>(x, __ldg(wtab + j));
+#pragma unroll
+        for (int q = 0; q < RF; ++q) __stcs(scratch + ((ch * RF + q) * n_avg + f) * M + j, x[q]);
+    }
+}
+
+// One CTA per channel: sums uint16[N] (output order) -> scalars, colour row, pixels, spectrum.
+// Same arithmetic as colour_stage (utils_supersdr.py:787-813); the keys are re-read from
+// global memory (L2) instead of living in registers.
+__global__ void __launch_bounds__(1024) wf_colour_big_kernel(const WfKernelParams kp, int N) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned* hist = reinterpret_cast<unsigned*>(smem);
+    const int nbins = 255 * kp.n_avg + 1;
+    int* red = reinterpret_cast<int*>(hist + nbins + 32);
+    const int t = threadIdx.x, lane = t & 31, G = blockDim.x;
+    for (int ch = blockIdx.x; ch < kp.batch; ch += gridDim.x) {
+        const uint16_t* keys = kp.sums + (size_t)ch * N;
+        const ssdr_wf_display_t dp = kp.disp[ch];
+        for (int i = t; i < nbins + 32; i += G) hist[i] = 0u;
+        if (t == 0) { red[0] = 0; red[1] = 0; red[2] = 0x7fffffff; red[3] = 0; red[4] = 0x7fffffff; }
+        __syncthreads();
+        const unsigned key1 = keys[1];                      // wf_db[0] = wf_db[1]
+        int kmax = 0, kmin = 0x7fffffff;
+        for (int o = t; o < N; o += G) {
+            const int k = (int)(o == 0 ? key1 : (unsigned)keys[o]);
+            atomicAdd(&hist[k], 1u);
+            kmax = max(kmax, k); kmin = min(kmin, k);
+        }
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        if (lane == 0) { atomicMax(&red[3], kmax); atomicMin(&red[2], kmin); }
+        __syncthreads();
+        const int vmax = red[3];
+        kmin = red[2];
+
+        float low_clip = dp.low_clip_db, high_clip = 0.f, dyn = dp.dynamic_range;
+        const float fn = (float)kp.n_avg, z3 = (float)(3 * dp.zoom);
+        const Divisor dfn = make_divisor(fn);
+        auto wfdb = [&](float s) { return ((div_rn<true>(s, dfn) - 255.0f) - 13.0f) + z3; };
+        if (dp.auto_scale) {
+            const int want = kp.p_lo + 1;
+            const int cpt = ((nbins + G - 1) / G) | 1;
+            const int b0 = t * cpt, b1 = min(b0 + cpt, nbins);
+            int sum = 0, first = 0x7fffffff;
+            for (int b = b0; b < b1; ++b) sum += (int)hist[b];
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+            if (lane == 31) hist[nbins + (t >> 5)] = (unsigned)incl;
+            __syncthreads();
+            int prefix = incl - sum;
+            for (int w = 0; w < (t >> 5); ++w) prefix += (int)hist[nbins + w];
+            if (prefix < want && want <= prefix + sum) {
+                int c = prefix, b = b0;
+                for (; b < b1; ++b) { c += (int)hist[b]; if (c >= want) break; }
+                red[0] = b; red[1] = c;
+            }
+            __syncthreads();
+            const int v_lo = red[0], cnt_lo = red[1];
+            for (int b = max(b0, v_lo + 1); b < b1; ++b) if (hist[b]) { first = b; break; }     // min{key > v_lo}
+            first = __reduce_min_sync(0xffffffffu, first);
+            if (lane == 0) atomicMin(&red[4], first);
+            __syncthreads();
+            const int mn = red[4];
+            const int v_hi = (cnt_lo >= want + 1 || mn == 0x7fffffff) ? v_lo : mn;
+            const float a = wfdb((float)v_lo), b = wfdb((float)v_hi), g = kp.p_gamma;
+            const float dba = b - a;
+            float p;
+            if (g >= 0.5f) { float tt = 1.0f - g; tt = dba * tt; p = b - tt; }
+            else { float tt = dba * g; p = a + tt; }
+            low_clip = p;
+            high_clip = wfdb((float)vmax);
+            const float dd = high_clip - low_clip;
+            dyn = dd > 40.0f ? dd : 40.0f;
+        }
+        const float low = low_clip + (float)dp.delta_low_db;
+        const float nf = dyn + (float)dp.delta_high_db;
+        const float den = nf - (float)dp.delta_low_db;
+        if (t == 0) {
+            if (dp.auto_scale) { kp.disp[ch].low_clip_db = low_clip; kp.disp[ch].dynamic_range = dyn; }
+            if (kp.scalars) {
+                ssdr_wf_scalars_t sc;
+                sc.low_clip_db = low_clip; sc.high_clip_db = dp.auto_scale ? high_clip : wfdb((float)vmax);
+                sc.dynamic_range = dyn; sc.wf_min_db = low - z3; sc.wf_max_db = (low_clip + nf) - z3;
+                kp.scalars[ch] = sc;
+            }
+        }
+        const Divisor dden = make_divisor(den);
+        const size_t row = (size_t)ch * N;
+        for (int o = t; o < N; o += G) {
+            const unsigned raw = keys[o];
+            const float s = (float)(o == 0 ? key1 : raw);
+            const float m = div_rn<true>(s, dfn);
+            const float w = ((m - 255.0f) - 13.0f) + z3;
+            float c = dden.ok ? div_rn<true>(w - low, dden) : div_rn<false>(w - low, dden);
+            c = fminf(fmaxf(c, 0.0f), 1.0f);
+            c = c * 254.0f;
+            c = fminf(fmaxf(c, 0.0f), 255.0f);
+            if (kp.colour) kp.colour[row + o] = c;
+            if (kp.pixels) kp.pixels[row + o] = (uint8_t)__float2int_rn(c);
+            if (kp.spectrum) kp.spectrum[row + o] = div_rn<true>((float)raw, dfn);
+        }
+        __syncthreads();                                     // hist / red are reused by the next channel
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int LG>
@@ -822,10 +988,49 @@ static int launch_colorrow(const WfKernelParams& kp, cudaStream_t st) {
 
 int wf_plan(int nfft, int* radices) {
     int lg = ilog2(nfft);
-    if ((1 << lg) != nfft || lg < 8 || lg > 14) return -1;
+    if ((1 << lg) != nfft || lg < 8 || lg > 16) return -1;
+    int n = 0;
+    if (lg > 14) { radices[n++] = 1 << (lg - 14); lg = 14; }      // front pass of the large-N path
     PlanC p = make_plan(lg);
-    for (int i = 0; i < p.np; ++i) radices[i] = p.r[i];
-    return p.np;
+    for (int i = 0; i < p.np; ++i) radices[n++] = p.r[i];
+    return n;
+}
+
+// N = 32768 / 65536: front pass -> 16384-point kernel in sums mode -> colour kernel (three launches)
+static int launch_big(const WfLaunch& a, WfKernelParams kp, cudaStream_t st) {
+    const int rf = a.nfft / 16384;
+    if (!a.scratch || !a.sums || !a.wtab_sub) { set_error("large-N launch without scratch buffers"); return SSDR_E_STATE; }
+    const size_t pts = (size_t)a.batch * a.n_avg * 16384;
+    int grid = (int)std::min<size_t>((pts + 255) / 256, (size_t)sm_count() * 32);
+    float2* scr = reinterpret_cast<float2*>(a.scratch);
+    const float2* wt = reinterpret_cast<const float2*>(a.wtab);
+#define SSDR_FRONT(RF, FMT, W) wf_front_kernel<RF, FMT, W><<<grid, 256, 0, st>>>(a.iq, scr, wt, a.win, a.batch, a.n_avg)
+    if (rf == 2) {
+        if (a.iq_format == SSDR_IQ_CF32) { if (a.window) SSDR_FRONT(2, SSDR_IQ_CF32, true); else SSDR_FRONT(2, SSDR_IQ_CF32, false); }
+        else { if (a.window) SSDR_FRONT(2, SSDR_IQ_S16BE, true); else SSDR_FRONT(2, SSDR_IQ_S16BE, false); }
+    } else {
+        if (a.iq_format == SSDR_IQ_CF32) { if (a.window) SSDR_FRONT(4, SSDR_IQ_CF32, true); else SSDR_FRONT(4, SSDR_IQ_CF32, false); }
+        else { if (a.window) SSDR_FRONT(4, SSDR_IQ_S16BE, true); else SSDR_FRONT(4, SSDR_IQ_S16BE, false); }
+    }
+#undef SSDR_FRONT
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    // 16384-point sub-transforms of the rf virtual channels per channel
+    WfKernelParams k2 = kp;
+    k2.iq = a.scratch; k2.wtab = reinterpret_cast<const float2*>(a.wtab_sub); k2.batch = a.batch * rf; k2.sums = a.sums; k2.rf = rf;
+    k2.pixels = nullptr; k2.colour = nullptr; k2.spectrum = nullptr; k2.scalars = nullptr;
+    int rc = launch_fft<14>(k2, SSDR_IQ_CF32, 0, st);
+    if (rc) return rc;
+    // colour row over the N sums of each channel
+    WfKernelParams k3 = kp;
+    k3.sums = a.sums;
+    const size_t smem = ((size_t)255 * a.n_avg + 1 + 32 + 8) * sizeof(unsigned);
+    SSDR_CUDA(cudaFuncSetAttribute(wf_colour_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int g3 = std::min(a.batch, sm_count() * 2);
+    wf_colour_big_kernel<<<g3, 1024, smem, st>>>(k3, a.nfft);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
 }
 
 int wf_launch(const WfLaunch& a, cudaStream_t st) {
@@ -838,6 +1043,7 @@ int wf_launch(const WfLaunch& a, cudaStream_t st) {
     kp.key_bits = 1;
     while ((1 << kp.key_bits) <= 255 * a.n_avg) ++kp.key_bits;
     const int lg = ilog2(a.nfft);
+    if (!a.lines && lg > 14) return launch_big(a, kp, st);
     if (a.lines) {
         switch (lg) {
             case 8: return launch_colorrow<8>(kp, st);

@@ -16,7 +16,7 @@ def _sc(res):
 
 
 def test_spec_tables_equal_oracle(ssdr):
-    for N in (256, 512, 1024, 2048, 4096, 8192, 16384):
+    for N in (256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536):
         b = ssdr.WaterfallBank(N, 1, 1)
         tw, thr, plan = b.tables()
         assert plan == c_oracle.fft_plan(N)
@@ -27,7 +27,8 @@ def test_spec_tables_equal_oracle(ssdr):
 
 
 @pytest.mark.parametrize("N,B,n", [(256, 33, 3), (512, 9, 2), (1024, 1, 1), (1024, 8, 10), (2048, 5, 4),
-                                   (4096, 3, 2), (8192, 3, 2), (16384, 3, 2), (16384, 149, 1)])
+                                   (4096, 3, 2), (8192, 3, 2), (16384, 3, 2), (16384, 149, 1),
+                                   (32768, 3, 2), (32768, 150, 1), (65536, 2, 3), (65536, 75, 1)])
 def test_waterfall_bit_exact_vs_c_oracle(ssdr, N, B, n):
     iq = tier_u.synth_batch(B, n, N, seed=N + B)
     bank = ssdr.WaterfallBank(N, B, n)
@@ -42,7 +43,8 @@ def test_waterfall_bit_exact_vs_c_oracle(ssdr, N, B, n):
 
 
 @pytest.mark.parametrize("N,window", [(256, True), (512, False), (1024, True), (1024, False), (2048, True),
-                                      (4096, True), (8192, False), (16384, True), (16384, False)])
+                                      (4096, True), (8192, False), (16384, True), (16384, False),
+                                      (32768, True), (65536, True), (65536, False)])
 def test_waterfall_rounding_noise_is_bit_exact(ssdr, N, window):
     """Adversarial for last-bit differences: one strong tone on an EXACT bin (optionally a second weak
     one) and no noise.  Every other bin then holds pure float32 rounding noise, which is reproduced only
@@ -177,6 +179,12 @@ def test_bad_arguments_raise(ssdr):
         ssdr.WaterfallBank(1000, 1, 1)            # not a power of two
     with pytest.raises(ssdr.SsdrError):
         ssdr.WaterfallBank(1024, 1, 101)          # averaging_n capped at 100 (supersdr.py:378)
+    with pytest.raises(ssdr.SsdrError):
+        ssdr.WaterfallBank(131072, 1, 1)          # largest supported frame is 65536
+    big = ssdr.WaterfallBank(32768, 1, 1)
+    with pytest.raises(ssdr.SsdrError):
+        big.colorrow(np.zeros((1, 1, 32768), np.uint8))      # the uint8-line entry stops at 16384
+    big.close()
     bank = ssdr.WaterfallBank(1024, 2, 1)
     with pytest.raises(ValueError):
         bank.process(np.zeros((1, 1, 1024), np.complex64))
