@@ -250,7 +250,24 @@ def main():
         e2e = {"value": world * n_samples * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": n_samples * 8, "d2h_bytes_per_step": B * NFFT + host_sc.nbytes, "steps": e2e_steps,
                "api": "WaterfallBank.process -> ssdr_wf_process (pinned host buffers)"}
-        host_iq.free(); host_px.free()
+        host_iq.free()
+        # the same rows from the Kiwi wire format (big-endian int16 I/Q, kiwi/client.py:449-453): half the bytes over PCIe
+        wire_dev = S.DeviceBuffer(n_samples * 4)
+        S._lib.check(S.lib.ssdr_synth_iq_dev(wire_dev.ptr, S.SSDR_IQ_S16BE, B, N_AVG, NFFT, 1234 + rank))
+        host_wire = S.PinnedArray((B, N_AVG, NFFT, 4), np.uint8)
+        S._lib.check(S.lib.ssdr_memcpy_d2h(S._lib.ptr(host_wire.array), wire_dev.ptr, n_samples * 4))
+        wire_dev.free()
+        bank.process(host_wire.array, want_colour=False, want_spectrum=False, out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            bank.process(host_wire.array, want_colour=False, want_spectrum=False, out=out)
+        w_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e["wire_s16be"] = {"value": world * n_samples * e2e_steps / w_s / 1e6, "unit": "Msamples/s",
+                             "h2d_bytes_per_step": n_samples * 4, "note": "same workload fed in the Kiwi wire format "
+                             "(int16 big-endian I/Q, unpack fused into the kernel's loads)"}
+        host_wire.free(); host_px.free()
     clk = clocks.stop()
 
     # ---- demodulator (BASELINE configs 3 and 4) as secondary lines ---------------------------------------

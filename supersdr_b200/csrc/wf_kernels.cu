@@ -70,7 +70,11 @@ struct Cfg {
     static constexpr int TW1 = (NP == 3) ? 32 * 31 : 0;          // middle-pass twiddle table
     static constexpr int SWZ = (NP == 3) ? ilog2(R0) : -1;       // staging swizzle shift (colour stage)
     static constexpr int MIN_CTAS = (LG >= 14) ? 1 : 2;
+#ifdef SSDR_NO_SPLIT      // developer check: plain group barriers, for compute-sanitizer racecheck (which does not model mbarriers)
+    static constexpr bool SPLIT = false;
+#else
     static constexpr bool SPLIT = (FPC == 1 && G > 32);     // split-phase frame-buffer hand-off (mbarrier)
+#endif
     // Warps of a one-frame-per-SM group start their warp-local passes STAGGER cycles apart per level (4 levels, by
     // warp / 4): in lock step all sixteen warps hit the shared-memory pipe and then the fp32 pipe together; staggered,
     // one warp's loads overlap another's butterflies (measured: 2.26 -> 2.09 ms on config 2).

@@ -174,6 +174,46 @@ def test_edge_inputs(ssdr):
     bank.close()
 
 
+@pytest.mark.parametrize("N,B,n", [(16384, 2, 100), (8192, 2, 100), (8192, 2, 33), (65536, 1, 100), (2048, 3, 100)])
+def test_averaging_extremes_bit_exact(ssdr, N, B, n):
+    """averaging_n up to its cap of 100 (supersdr.py:376-385): 15-bit sums, the histogram rank selection where it
+    fits the frame buffer and the bisection where it does not, against the C oracle."""
+    iq = tier_u.synth_batch(B, n, N, seed=7 * N + n)
+    bank = ssdr.WaterfallBank(N, B, n)
+    res = bank.process(iq)
+    ref = c_oracle.wf_rows(iq, threads=8)
+    assert np.array_equal(res["spectrum"], ref["spectrum"])
+    assert np.array_equal(res["colour"], ref["colour"])
+    assert np.array_equal(res["pixels"], ref["pixels"])
+    assert np.array_equal(_sc(res), ref["scalars"])
+    bank.close()
+
+
+def test_constant_and_two_level_rows(ssdr):
+    """Rows whose keys are all equal (digital silence) or take two values only: the degenerate inputs of the
+    histogram rank selection, through the FFT path and through the uint8-line entry."""
+    N = 16384
+    iq = np.zeros((2, 2, N), np.complex64)
+    iq[1, :, :] = 3000.0                                   # DC only: one strong bin (+ window leakage), silence elsewhere
+    bank = ssdr.WaterfallBank(N, 2, 2)
+    res = bank.process(iq)
+    ref = c_oracle.wf_rows(iq)
+    for k in ("spectrum", "colour", "pixels"):
+        assert np.array_equal(res[k], ref[k])
+    assert np.array_equal(_sc(res), ref["scalars"])
+    lines = np.full((2, 3, N), 77, np.uint8)
+    lines[1, :, ::2] = 200
+    got = bank3 = None
+    bank3 = ssdr.WaterfallBank(N, 2, 3)
+    got = bank3.colorrow(lines)
+    for b in range(2):
+        st = tier_p.ColourState()
+        spec, col, px = tier_p.waterfall_line(lines[b], st)
+        assert np.array_equal(got["spectrum"][b], spec) and np.array_equal(got["colour"][b], col)
+        assert np.array_equal(got["pixels"][b], px)
+    bank.close(); bank3.close()
+
+
 def test_bad_arguments_raise(ssdr):
     with pytest.raises(ssdr.SsdrError):
         ssdr.WaterfallBank(1000, 1, 1)            # not a power of two
