@@ -108,11 +108,14 @@ demod_kernel(const DemodKernelParams kp) {
 
         for (int b = 0; b < nblk; ++b) {
             const size_t s0 = (size_t)ch * kp.pitch + (size_t)b * FR;
-            // ---- mixer: lane-strided, coalesced --------------------------------------------
-#pragma unroll 4
+            // ---- mixer: lane-strided, coalesced; all sixteen loads of the frame in flight together ----------
+            float2 xin[SPL];
+#pragma unroll
+            for (int r = 0; r < SPL; ++r) xin[r] = ld_iq<FMT>(kp.iq, s0 + lane + 32 * r);
+#pragma unroll
             for (int r = 0; r < SPL; ++r) {
                 const int k = lane + 32 * r;
-                float2 x = ld_iq<FMT>(kp.iq, s0 + k);
+                const float2 x = xin[r];
                 float c, s;
                 nco(ph1 + (unsigned)k * cp.inc1, c, s);
                 // x * exp(-j theta): (xr + j xi)(c - j s)
