@@ -10,7 +10,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 def test_c_fft_is_an_fft():
     rng = np.random.default_rng(0)
-    for N in (64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384):
+    for N in (64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536):
         x = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
         _, spec = c_oracle.wf_frame_bytes(x, window=False, want_spectrum=True)
         ref = np.fft.fft(x.astype(np.complex128))
@@ -19,7 +19,7 @@ def test_c_fft_is_an_fft():
 
 
 def test_c_bytes_vs_float64_boundary_aware():
-    for N in (256, 1024, 4096, 16384):
+    for N in (256, 1024, 4096, 16384, 65536):
         x = tier_u.synth_iq(N, seed=N)[0]
         by = c_oracle.wf_frame_bytes(x)
         mism, unexplained = tier_u.compare_bytes_boundary_aware(by, x)
@@ -47,6 +47,12 @@ def test_plan_and_tables():
     assert c_oracle.fft_plan(1024) == [32, 32] and c_oracle.fft_plan(16384) == [16, 32, 32]
     assert c_oracle.fft_plan(512) == [16, 32] and c_oracle.fft_plan(256) == [8, 32]
     assert c_oracle.fft_plan(2048) == [2, 32, 32] and c_oracle.fft_plan(8192) == [8, 32, 32]
+    # larger than one SM's shared memory: a front pass over HBM, then the 16384-point plan
+    assert c_oracle.fft_plan(32768) == [2, 16, 32, 32] and c_oracle.fft_plan(65536) == [4, 16, 32, 32]
+    # the window table is the first half of the periodic Hann window; the second half is 1 - w
+    w = c_oracle.window_table(1024).astype(np.float64)
+    assert w.size == 512 and w[0] == 0 and abs(w[256] - 0.5) < 1e-7
+    assert np.allclose(w, tier_u.hann(1024)[:512], atol=6e-8) and np.allclose(1 - w, tier_u.hann(1024)[512:], atol=6e-8)
     t = c_oracle.thresholds(1024, -10.0)
     assert t[0] == 0 and np.all(np.diff(t[1:]) > 0)
     # threshold k sits half a dB below byte k: 10 log10(T[k]/ref) - 10 + 255 == k - 0.5
