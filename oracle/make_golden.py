@@ -103,6 +103,37 @@ def gen_tier_p_audio(m):
     return len(xs)
 
 
+def write_kiwi_iq_wav(path, blocks, fs=12000, t0=1234567.25):
+    """A Kiwi IQ WAV file as kiwirecorder writes it: RIFF/WAVE, 16-byte fmt chunk (PCM, 2 channels, 16 bit), then a
+    10-byte 'kiwi' GNSS chunk (<BBII) before every 'data' chunk of interleaved little-endian int16 I/Q."""
+    import struct
+    body = b"WAVE" + b"fmt " + struct.pack("<L", 16) + struct.pack("<HHLLHH", 1, 2, fs, fs * 4, 4, 16)
+    t = t0
+    for b in blocks:
+        sec = int(t)
+        body += b"kiwi" + struct.pack("<L", 10) + struct.pack("<BBII", 1, 0, sec, int(round((t - sec) * 1e9)))
+        raw = np.ascontiguousarray(b, dtype="<i2").tobytes()
+        body += b"data" + struct.pack("<L", len(raw)) + raw
+        t += (len(raw) // 4) / (fs * (1 + 3e-5))          # a slightly fast sample clock, as real Kiwis have
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<L", len(body)) + body)
+
+
+def gen_kiwi_wav():
+    """kiwi/wavreader.py run on a synthetic recording -> tests/golden/kiwi_iq.wav + kiwi_iq_wav.npz."""
+    sys.path.insert(0, ref_import.REFERENCE_DIR)
+    from kiwi import wavreader
+    rng = np.random.default_rng(11)
+    blocks = [rng.integers(-20000, 20000, (512, 2)).astype(np.int16) for _ in range(6)]
+    path = os.path.join(OUT, "kiwi_iq.wav")
+    write_kiwi_iq_wav(path, blocks)
+    t, z = wavreader.read_kiwi_iq_wav(path)
+    per = [(tt, zz) for tt, zz in wavreader.KiwiIQWavReader(path)]
+    np.savez_compressed(os.path.join(OUT, "kiwi_iq_wav.npz"), t=t, z=z, n_blocks=len(per),
+                        none_blocks=np.array([tt is None for tt, _ in per]), last_t=per[-1][0], last_z=per[-1][1])
+    print("kiwi_iq.wav", os.path.getsize(path))
+
+
 def gen_tier_u():
     # waterfall: BASELINE config 1 (single 1024-pt frame) + one 16384-pt, 2-frame channel
     x1 = tier_u.synth_iq(1024, seed=1234)
@@ -129,5 +160,6 @@ if __name__ == "__main__":
     print("tier_p waterfall cases:", gen_tier_p_waterfall(m))
     print("tier_p audio blocks:", gen_tier_p_audio(m))
     gen_tier_u()
+    gen_kiwi_wav()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

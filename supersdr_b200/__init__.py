@@ -9,7 +9,9 @@ from ._lib import (SsdrError, init, last_error, DeviceBuffer, PinnedArray, lib, 
 from .waterfall import WaterfallBank, kiwi_waterfall, percentile_index
 from .sound import (DemodBank, InterpBank, filtering, kiwi_sound, start_audio_stream, demod_params,
                     design_lowpass, default_passband, unpack_iq)
+from .wavreader import KiwiIQWavReader, KiwiIQWavError, WavIQSource, read_kiwi_iq_wav
 
 __all__ = ["SsdrError", "init", "last_error", "DeviceBuffer", "PinnedArray", "WaterfallBank", "kiwi_waterfall",
            "percentile_index", "DemodBank", "InterpBank", "filtering", "kiwi_sound", "start_audio_stream",
-           "demod_params", "design_lowpass", "default_passband", "unpack_iq"]
+           "demod_params", "design_lowpass", "default_passband", "unpack_iq", "KiwiIQWavReader", "KiwiIQWavError",
+           "WavIQSource", "read_kiwi_iq_wav"]
