@@ -200,6 +200,16 @@ int ssdr_interp_process_dev(ssdr_interp_t h, const int16_t* pcm_dev, int n, cons
                             const float* balance_dev, int16_t* stereo_dev, double* mono_dev);
 int ssdr_interp_sync(ssdr_interp_t h);
 
+/* kiwi_sound.play_buffer, non-integer sample ratio ("high bandwidth kiwis", utils_supersdr.py:1125-1126):
+ * scipy.signal.resample_poly(pcm * volume/100, up, down, padtype="line"), stateless per block, then balance and the
+ * int16 cast of utils_supersdr.py:1136-1138.  h[n_h] is the polyphase filter exactly as resample_poly builds it
+ * (firwin(2*10*max(up,down)+1, 1/max(up,down), window=("kaiser", 5.0)) * up, zero-padded in front); output sample j
+ * is upfirdn sample first + j, j < n_keep (the reference keeps n_out - 1 samples).  Host buffers; pcm int16[batch][n],
+ * stereo_out int16[batch][n_keep][2], mono_f64 (optional) float64[batch][n_keep]. */
+int ssdr_resample_line(const int16_t* pcm_host, int batch, int n, const float* volume, const float* balance,
+                       const double* h, int n_h, int up, int down, int first, int n_keep,
+                       int16_t* stereo_out, double* mono_f64);
+
 /* filtering.lowpass (utils_supersdr.py:346-348): np.convolve(signal, h, "valid") in float64.
  * x[n] -> out[n - n_taps + 1]; separate multiply / add in ascending tap order. */
 int ssdr_fir_valid_f64(const double* x_host, size_t n, const double* taps, int n_taps, double* out_host);

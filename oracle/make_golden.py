@@ -103,6 +103,34 @@ def gen_tier_p_audio(m):
     return len(xs)
 
 
+def gen_tier_p_audio_resample(m):
+    """kiwi_sound.play_buffer on its non-integer-ratio path (utils_supersdr.py:1125-1126): a 20.25 kHz Kiwi into a
+    48 kHz sound card, resample_poly(x, 64, 27, padtype="line")[:-1]."""
+    rng = np.random.default_rng(78)
+    snd = m.kiwi_sound.__new__(m.kiwi_sound)
+    snd.SAMPLE_RATIO = 48000 / 20250
+    snd.n_low, snd.n_high = 27, 64
+    snd.late_flag = False
+    snd.audio_buffer = queue.Queue()
+    snd.rssi, snd.mute_counter, snd.max_rssi_before_mute, snd.muting_delay = -90, 0, -20, 15
+    snd.audio_rec = type("AR", (), {"recording_flag": False})()
+    xs, vols, bals, outs = [], [], [], []
+    t = np.arange(512)
+    for k in range(8):
+        x = rng.integers(-20000, 20000, 512).astype(np.int16)
+        if k == 2:
+            x = np.rint(15000 * np.sin(2 * np.pi * 0.01 * t) + 20 * t).astype(np.int16)      # a ramp: the "line" extension matters
+        snd.volume = int(rng.integers(1, 16)) * 10
+        snd.audio_balance = float(np.round(rng.uniform(-1, 1), 2))
+        snd.audio_buffer.put(x)
+        out = np.zeros((1213, 2), np.int16)
+        snd.play_buffer(out, 1213, None, None)
+        xs.append(x); vols.append(snd.volume); bals.append(snd.audio_balance); outs.append(out.copy())
+    np.savez_compressed(os.path.join(OUT, "tier_p_audio_resample.npz"), x=np.stack(xs), volume=np.array(vols),
+                        balance=np.array(bals), out=np.stack(outs), up=64, down=27)
+    return len(xs)
+
+
 def write_kiwi_iq_wav(path, blocks, fs=12000, t0=1234567.25):
     """A Kiwi IQ WAV file as kiwirecorder writes it: RIFF/WAVE, 16-byte fmt chunk (PCM, 2 channels, 16 bit), then a
     10-byte 'kiwi' GNSS chunk (<BBII) before every 'data' chunk of interleaved little-endian int16 I/Q."""
@@ -159,6 +187,7 @@ if __name__ == "__main__":
     m = ref_import.load()
     print("tier_p waterfall cases:", gen_tier_p_waterfall(m))
     print("tier_p audio blocks:", gen_tier_p_audio(m))
+    print("tier_p audio resample blocks:", gen_tier_p_audio_resample(m))
     gen_tier_u()
     gen_kiwi_wav()
     for f in sorted(os.listdir(OUT)):

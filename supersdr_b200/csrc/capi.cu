@@ -680,6 +680,41 @@ int ssdr_interp_sync(ssdr_interp_t h) {
     return SSDR_OK;
 }
 
+int ssdr_resample_line(const int16_t* pcm_host, int batch, int n, const float* volume, const float* balance, const double* h,
+                       int n_h, int up, int down, int first, int n_keep, int16_t* stereo_out, double* mono_f64) {
+    SSDR_ARG(pcm_host && volume && balance && h && stereo_out, "null argument");
+    SSDR_ARG(batch >= 1 && n >= 1 && n_h >= 1 && up >= 1 && down >= 1 && first >= 0 && n_keep >= 0, "bad argument");
+    // the kept samples must exist: upfirdn produces ((n - 1) up + n_h - 1) / down + 1 samples
+    SSDR_ARG((long long)(first + n_keep) <= ((long long)(n - 1) * up + n_h - 1) / down + 1, "first + n_keep exceeds the upfirdn output length");
+    if (n_keep == 0) return SSDR_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    int16_t *d_x = nullptr, *d_o = nullptr;
+    float *d_v = nullptr, *d_b = nullptr;
+    double *d_h = nullptr, *d_m = nullptr;
+    const size_t nin = (size_t)batch * n, nout = (size_t)batch * n_keep;
+    int rc = SSDR_OK;
+    auto cleanup = [&]() { cudaFree(d_x); cudaFree(d_o); cudaFree(d_v); cudaFree(d_b); cudaFree(d_h); cudaFree(d_m); };
+    if ((rc = dev_alloc(&d_x, nin)) || (rc = dev_alloc(&d_o, nout * 2)) || (rc = dev_alloc(&d_v, (size_t)batch)) ||
+        (rc = dev_alloc(&d_b, (size_t)batch)) || (rc = dev_alloc(&d_h, (size_t)n_h)) || (mono_f64 && (rc = dev_alloc(&d_m, nout)))) { cleanup(); return rc; }
+    cudaError_t e = cudaMemcpy(d_x, pcm_host, nin * sizeof(int16_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_v, volume, sizeof(float) * batch, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_b, balance, sizeof(float) * batch, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_h, h, sizeof(double) * n_h, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        ResampleKernelParams kp;
+        kp.pcm = d_x; kp.volume = d_v; kp.balance = d_b; kp.h = d_h; kp.stereo = d_o; kp.mono = d_m;
+        kp.n = n; kp.n_h = n_h; kp.up = up; kp.down = down; kp.first = first; kp.n_keep = n_keep;
+        rc = resample_line_launch(kp, batch, 0);
+        if (!rc) e = cudaMemcpy(stereo_out, d_o, nout * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost);
+        if (!rc && e == cudaSuccess && mono_f64) e = cudaMemcpy(mono_f64, d_m, nout * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cleanup();
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "resample copy", __FILE__, __LINE__);
+    return SSDR_OK;
+}
+
 int ssdr_fir_valid_f64(const double* x_host, size_t n, const double* taps, int n_taps, double* out_host) {
     SSDR_ARG(x_host && taps && out_host && n_taps >= 1, "bad argument");
     if (n < (size_t)n_taps) return SSDR_OK;

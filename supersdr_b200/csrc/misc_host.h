@@ -26,7 +26,18 @@ struct InterpLaunch {
     int batch;
 };
 
+struct ResampleKernelParams {
+    const int16_t* pcm;       // [batch][n]
+    const float* volume;      // [batch] percent
+    const float* balance;     // [batch]
+    const double* h;          // [n_h] polyphase filter as resample_poly builds it (pre-padded, scaled by up)
+    int16_t* stereo;          // [batch][n_keep][2]
+    double* mono;             // optional [batch][n_keep]
+    int n, n_h, up, down, first, n_keep;
+};
+
 int interp_launch(const InterpLaunch& a, cudaStream_t st);
+int resample_line_launch(const ResampleKernelParams& kp, int batch, cudaStream_t st);
 int fir_valid_launch(const double* x, const double* h, int T, double* out, size_t n_out, cudaStream_t st);
 int unpack_launch(const void* in, float* out, size_t n, cudaStream_t st);
 int synth_launch(void* out, int fmt, int batch, int frames, int nfft, unsigned seed, cudaStream_t st);

@@ -60,6 +60,42 @@ interp_kernel(const InterpKernelParams kp) {
     }
 }
 
+// kiwi_sound.play_buffer, non-integer ratio (utils_supersdr.py:1125-1126): scipy.signal.resample_poly(x, up, down,
+// padtype="line")[:-1], stateless per block.  The polyphase filter h (zero-padded, scaled by up) is designed by the
+// host exactly as resample_poly designs it; this is scipy's upfirdn: output y uses phase t = (y down) mod up and the
+// input window ending at x_idx = (y down) div up, the signal extended on both sides along the line through its first
+// and last sample, products accumulated in ascending time order with separate float64 multiplies and adds.
+__global__ void resample_line_kernel(const ResampleKernelParams kp) {
+    const int ch = blockIdx.y;
+    const int16_t* x = kp.pcm + (size_t)ch * kp.n;
+    const double scale = (double)kp.volume[ch] / 100.0;
+    const double bal = (double)kp.balance[ch];
+    double lv = fmin(1.0 - bal, 1.0), rv = fmin(1.0 + bal, 1.0);
+    lv = lv * lv; rv = rv * rv;
+    const int hpp = (kp.n_h + kp.up - 1) / kp.up;              // coefficients per phase (h zero-padded to a multiple of up)
+    const double x_first = __dmul_rn((double)x[0], scale), x_last = __dmul_rn((double)x[kp.n - 1], scale);
+    const double slope = (kp.n > 1) ? __ddiv_rn(__dadd_rn(x_last, -x_first), (double)(kp.n - 1)) : 0.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < kp.n_keep; j += gridDim.x * blockDim.x) {
+        const long long yd = (long long)(j + kp.first) * kp.down;
+        const int t = (int)(yd % kp.up), x_idx = (int)(yd / kp.up);
+        double acc = 0.0;
+        for (int i = 0; i < hpp; ++i) {
+            const int xi = x_idx - hpp + 1 + i;
+            const int hi = (hpp - 1 - i) * kp.up + t;
+            const double hv = (hi < kp.n_h) ? kp.h[hi] : 0.0;
+            double xv;
+            if (xi < 0) xv = __dadd_rn(x_first, __dmul_rn((double)xi, slope));
+            else if (xi >= kp.n) xv = __dadd_rn(x_last, __dmul_rn((double)(xi - kp.n + 1), slope));
+            else xv = __dmul_rn((double)x[xi], scale);
+            acc = __dadd_rn(acc, __dmul_rn(xv, hv));
+        }
+        const size_t o = (size_t)ch * kp.n_keep + j;
+        if (kp.mono) kp.mono[o] = acc;
+        const int l = __double2int_rz(__dmul_rn(acc, lv)), r = __double2int_rz(__dmul_rn(acc, rv));
+        reinterpret_cast<unsigned*>(kp.stereo)[o] = ((unsigned)l & 0xffffu) | ((unsigned)r << 16);
+    }
+}
+
 // filtering.lowpass, utils_supersdr.py:346-348: out[j] = sum_t h[t] x[j + T - 1 - t]  ("valid")
 __global__ void fir_valid_kernel(const double* __restrict__ x, const double* __restrict__ h, int T, double* __restrict__ out, size_t n_out) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += (size_t)gridDim.x * blockDim.x) {
@@ -130,6 +166,14 @@ __global__ void synth_kernel(void* out, int batch, int frames, int nfft, unsigne
 int interp_launch(const InterpLaunch& a, cudaStream_t st) {
     dim3 grid((a.kp.n + IT - 1) / IT, a.batch);
     interp_kernel<<<grid, IT, 0, st>>>(a.kp);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+int resample_line_launch(const ResampleKernelParams& kp, int batch, cudaStream_t st) {
+    dim3 grid((kp.n_keep + 255) / 256, batch);
+    resample_line_kernel<<<grid, 256, 0, st>>>(kp);
     count_launch();
     SSDR_CUDA(cudaGetLastError());
     return SSDR_OK;

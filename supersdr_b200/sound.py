@@ -178,6 +178,54 @@ class InterpBank:
             pass
 
 
+class ResampleLine:
+    """``scipy.signal.resample_poly(x, up, down, padtype="line")[:-1]`` on the GPU -- kiwi_sound.play_buffer's path for
+    non-integer sample ratios (utils_supersdr.py:1125-1126).  The polyphase filter is designed on the host exactly as
+    resample_poly designs it (scipy.signal.firwin, Kaiser beta 5, 10 * max(up, down) taps per side, gain up, zero-padded
+    in front so that output samples sit at the filter centre); the block is stateless, like the reference."""
+
+    def __init__(self, up, down, device=None):
+        from math import gcd
+        from scipy.signal import firwin          # host-side filter design only, as the reference's resample_poly call
+        _lib.init(device)
+        g = gcd(int(up), int(down))
+        self.up, self.down = int(up) // g, int(down) // g
+        max_rate = max(self.up, self.down)
+        self.half_len = 10 * max_rate
+        h = firwin(2 * self.half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0)).astype(np.float64)
+        h *= self.up
+        self.n_pre_pad = self.down - self.half_len % self.down
+        self.n_pre_remove = (self.half_len + self.n_pre_pad) // self.down
+        self._h_design = h
+
+    def _plan(self, n_in):
+        n_out = n_in * self.up
+        n_out = n_out // self.down + bool(n_out % self.down)
+        olen = lambda len_h: (((n_in - 1) * self.up + len_h) - 1) // self.down + 1
+        n_post_pad = 0
+        while olen(len(self._h_design) + self.n_pre_pad + n_post_pad) < n_out + self.n_pre_remove:
+            n_post_pad += 1
+        h = np.concatenate((np.zeros(self.n_pre_pad), self._h_design, np.zeros(n_post_pad)))
+        return np.ascontiguousarray(h), n_out
+
+    def process(self, pcm_i16, volume=100, balance=0.0, want_mono=False, drop_last=True):
+        """pcm_i16: int16[B, n] -> stereo int16[B, n_keep, 2] (n_keep = resample_poly's length, minus one when
+        ``drop_last`` as the reference does) and optionally the float64 mono buffer."""
+        pcm = np.ascontiguousarray(pcm_i16, dtype=np.int16)
+        if pcm.ndim != 2:
+            raise ValueError("pcm must be int16[B, n]")
+        B, n = pcm.shape
+        h, n_out = self._plan(n)
+        n_keep = n_out - 1 if drop_last else n_out
+        vol = np.ascontiguousarray(np.broadcast_to(np.asarray(volume, np.float32), (B,)))
+        bal = np.ascontiguousarray(np.broadcast_to(np.asarray(balance, np.float32), (B,)))
+        out = np.empty((B, n_keep, 2), np.int16)
+        mono = np.empty((B, n_keep), np.float64) if want_mono else None
+        check(lib.ssdr_resample_line(ptr(pcm), B, n, ptr(vol), ptr(bal), ptr(h), int(h.size), self.up, self.down,
+                                     int(self.n_pre_remove), int(n_keep), ptr(out), ptr(mono)))
+        return (out, mono) if want_mono else out
+
+
 class filtering:
     """Drop-in for utils_supersdr.filtering (utils_supersdr.py:333-348): same design, ``lowpass``
     evaluated on the GPU (a one-channel, ratio-1 interpolator bank = plain 'valid' FIR)."""
@@ -350,7 +398,12 @@ class kiwi_sound:
             return
         popped = [self.audio_buffer.get() for _ in range(self.CHUNKS)]
         popped = np.array(popped).flatten().astype(np.int16)
-        out = self._interp.process(popped.reshape(1, -1), self.volume, self.audio_balance)[0]
+        if self.SAMPLE_RATIO % 1:                           # high bandwidth kiwis (3ch 20kHz), utils_supersdr.py:1125-1126
+            if getattr(self, "_resampler", None) is None or (self._resampler.up, self._resampler.down) != (self.n_high, self.n_low):
+                self._resampler = ResampleLine(self.n_high, self.n_low)
+            out = self._resampler.process(popped.reshape(1, -1), self.volume, self.audio_balance)[0]
+        else:
+            out = self._interp.process(popped.reshape(1, -1), self.volume, self.audio_balance)[0]
         outdata[:, 0] = out[:, 0]
         outdata[:, 1] = out[:, 1]
         if self.rssi > self.max_rssi_before_mute:          # mute on TX, utils_supersdr.py:1141-1147

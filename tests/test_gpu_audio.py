@@ -166,3 +166,31 @@ def test_interp_batched_streaming(ssdr):
     f = ssdr.filtering(6000, 48000)
     x = rng.standard_normal(5000)
     assert np.abs(f.lowpass(x) - np.convolve(x, f.h, "valid")).max() < 1e-12
+
+
+def test_resample_line_reference_golden(ssdr):
+    """play_buffer's non-integer-ratio path (utils_supersdr.py:1125-1126) against fixtures from the unmodified
+    reference (20.25 kHz -> 48 kHz, resample_poly(x, 64, 27, padtype="line")[:-1])."""
+    g = np.load(os.path.join(GOLD, "tier_p_audio_resample.npz"))
+    rs = ssdr.ResampleLine(int(g["up"]), int(g["down"]))
+    for k in range(g["x"].shape[0]):
+        out = rs.process(g["x"][k][None], float(g["volume"][k]), float(g["balance"][k]))[0]
+        assert out.shape == g["out"][k].shape
+        d = np.abs(out.astype(int) - g["out"][k].astype(int))
+        assert (np.minimum(d, 65536 - d)).max() <= 1           # float64 summation order of upfirdn is not pinned: <= 1 LSB
+
+
+@pytest.mark.parametrize("up,down,n", [(64, 27, 512), (64, 27, 1024), (160, 147, 441), (3, 2, 100), (5, 7, 333)])
+def test_resample_line_vs_scipy(ssdr, up, down, n):
+    from scipy.signal import resample_poly
+    rng = np.random.default_rng(up * 1000 + n)
+    B = 4
+    x = rng.integers(-30000, 30000, (B, n)).astype(np.int16)
+    x[1] = (-25000 + (50000 // n) * np.arange(n)).astype(np.int16)         # a ramp: the "line" extension is exercised
+    vol = np.array([100, 50, 70, 130], np.float32)
+    rs = ssdr.ResampleLine(up, down)
+    out, mono = rs.process(x, vol, 0.25, want_mono=True)
+    for b in range(B):
+        ref = resample_poly(x[b].astype(np.float64) * (float(vol[b]) / 100), up, down, padtype="line")[:-1]
+        assert mono[b].shape == ref.shape
+        assert np.abs(mono[b] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
