@@ -215,6 +215,30 @@ int ssdr_resample_line(const int16_t* pcm_host, int batch, int n, const float* v
 int ssdr_fir_valid_f64(const double* x_host, size_t n, const double* taps, int n_taps, double* out_host);
 
 /* ---------------------------------------------------------------------------------------------
+ * display epilogues:  colour rows -> scrolling waterfall image -> RGB, and the spectrum trace
+ *
+ * Replaces kiwi_waterfall.run's image bookkeeping (utils_supersdr.py:893-897: 3-deep delay deque, wf_data scrolled
+ * one line per row -- here a ring, no O(H W) copy), the palette look-up pygame does for
+ * make_surface(wf_data.T).set_palette(palRGB) (supersdr.py:929-930, create_cm utils_supersdr.py:1391-1412;
+ * pixel index = uint8(rint(value)), parity unpinned: the cast happens inside pygame) and
+ * display_stuff.plot_spectrum's trace (utils_supersdr.py:1678-1679).  All channels of a handle advance together.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ssdr_wf_image* ssdr_wf_image_t;
+/* palette_rgb: uint8[256][3] (entry i colours pixel value i). */
+int ssdr_wf_image_create(ssdr_wf_image_t* h, int batch, int height, int width, const uint8_t* palette_rgb);
+int ssdr_wf_image_destroy(ssdr_wf_image_t h);
+/* One wf_color row per channel, float32[batch][width] (host, or device with _dev): delay deque + scroll. */
+int ssdr_wf_image_push(ssdr_wf_image_t h, const float* colour_host);
+int ssdr_wf_image_push_dev(ssdr_wf_image_t h, const float* colour_dev);
+/* kiwi_waterfall.set_white_flag (utils_supersdr.py:875-877): display line 0 <- 255. */
+int ssdr_wf_image_white(ssdr_wf_image_t h);
+/* rgb uint8[batch][height][width][3]; wf_data float64[batch][height][width] (= kiwi_waterfall.wf_data), NULL = skip. */
+int ssdr_wf_image_get(ssdr_wf_image_t h, uint8_t* rgb, double* wf_data);
+/* v float64[batch][width] = nanmean of the newest t_avg lines; y int32[batch][width] = spectrum_height - 1 -
+ * int(v / 255 * spectrum_height) (-1 where v is NaN); NULL = skip. */
+int ssdr_wf_image_trace(ssdr_wf_image_t h, int t_avg, int spectrum_height, double* v, int32_t* y);
+
+/* ---------------------------------------------------------------------------------------------
  * IQ wire-format unpack (kiwi/client.py:443-454): big-endian int16 I,Q -> complex64, unscaled
  * ------------------------------------------------------------------------------------------- */
 int ssdr_unpack_iq_s16be(const void* s16be_host, float* cf32_host, size_t n_complex);

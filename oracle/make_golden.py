@@ -131,6 +131,14 @@ def gen_tier_p_audio_resample(m):
     return len(xs)
 
 
+def gen_palette(m):
+    """display_stuff.create_cm('cutesdr') (utils_supersdr.py:1391-1412) -> tests/golden/palette_cutesdr.npz."""
+    disp = m.display_stuff.__new__(m.display_stuff)
+    cm = np.asarray(disp.create_cm("cutesdr"), dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "palette_cutesdr.npz"), colormap=cm)
+    return cm.shape
+
+
 def write_kiwi_iq_wav(path, blocks, fs=12000, t0=1234567.25):
     """A Kiwi IQ WAV file as kiwirecorder writes it: RIFF/WAVE, 16-byte fmt chunk (PCM, 2 channels, 16 bit), then a
     10-byte 'kiwi' GNSS chunk (<BBII) before every 'data' chunk of interleaved little-endian int16 I/Q."""
@@ -190,5 +198,6 @@ if __name__ == "__main__":
     print("tier_p audio resample blocks:", gen_tier_p_audio_resample(m))
     gen_tier_u()
     gen_kiwi_wav()
+    print("palette:", gen_palette(m))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -28,3 +28,11 @@ ib = S.InterpBank(3, 4, max_samples=512)
 ib.process(rng.integers(-20000, 20000, (3, 512)).astype(np.int16), volume=80, balance=0.2)
 ib.close()
 print("interp ok", flush=True)
+img = S.WaterfallImage(2, 8, 1024)
+for _ in range(6):
+    img.push(rng.uniform(0, 254, (2, 1024)).astype(np.float32))
+img.image(True, True); img.trace(15, 100); img.set_white_flag()
+img.close()
+rs = S.ResampleLine(64, 27)
+rs.process(rng.integers(-20000, 20000, (2, 512)).astype(np.int16), 90, -0.1)
+print("image / resample ok", flush=True)

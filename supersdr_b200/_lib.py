@@ -89,6 +89,13 @@ _PROTOS = {
     "ssdr_interp_process": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "ssdr_interp_process_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "ssdr_interp_sync": (_i, [_vp]),
+    "ssdr_wf_image_create": (_i, [_pvp, _i, _i, _i, _vp]),
+    "ssdr_wf_image_destroy": (_i, [_vp]),
+    "ssdr_wf_image_push": (_i, [_vp, _vp]),
+    "ssdr_wf_image_push_dev": (_i, [_vp, _vp]),
+    "ssdr_wf_image_white": (_i, [_vp]),
+    "ssdr_wf_image_get": (_i, [_vp, _vp, _vp]),
+    "ssdr_wf_image_trace": (_i, [_vp, _i, _i, _vp, _vp]),
     "ssdr_resample_line": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ssdr_fir_valid_f64": (_i, [_vp, _sz, _vp, _i, _vp]),
     "ssdr_unpack_iq_s16be": (_i, [_vp, _vp, _sz]),

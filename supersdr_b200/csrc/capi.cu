@@ -112,6 +112,20 @@ struct ssdr_interp {
     double* d_mono = nullptr;
 };
 
+struct ssdr_wf_image {
+    int batch = 0, H = 0, W = 0, head = 0;
+    long long run_index = 0;
+    float* d_ring = nullptr;          // [batch][H][W]
+    float* d_delay = nullptr;         // [3][batch][W]
+    float* d_row = nullptr;           // one row of 255s (white flag)
+    uint8_t* d_pal = nullptr;         // [256][3]
+    uint8_t* d_rgb = nullptr;
+    double* d_f64 = nullptr;
+    int* d_y = nullptr;
+    std::vector<int> deque;           // delay slots, newest first (utils_supersdr.py:893, maxlen 3)
+    cudaStream_t st = nullptr;
+};
+
 extern "C" {
 
 // =============================================================================================
@@ -731,6 +745,113 @@ int ssdr_fir_valid_f64(const double* x_host, size_t n, const double* taps, int n
     cudaFree(d_x); cudaFree(d_h); cudaFree(d_o);
     if (rc) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "fir_valid copy", __FILE__, __LINE__);
+    return SSDR_OK;
+}
+
+// =============================================================================================
+// display epilogues
+// =============================================================================================
+static const int kWfDelay = 3;        // kiwi_waterfall.wf_buffer_len (utils_supersdr.py:604)
+
+int ssdr_wf_image_create(ssdr_wf_image_t* out, int batch, int height, int width, const uint8_t* palette_rgb) {
+    SSDR_ARG(out != nullptr, "null handle pointer");
+    *out = nullptr;
+    SSDR_ARG(batch >= 1 && height >= 1 && width >= 1 && palette_rgb, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    ssdr_wf_image* h = new ssdr_wf_image();
+    h->batch = batch; h->H = height; h->W = width;
+    int rc;
+    auto fail = [&](int code) { ssdr_wf_image_destroy(h); return code; };
+    if ((rc = dev_alloc(&h->d_ring, (size_t)batch * height * width))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_delay, (size_t)kWfDelay * batch * width))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_row, (size_t)width))) return fail(rc);
+    if ((rc = dev_alloc(&h->d_pal, (size_t)768))) return fail(rc);
+    std::vector<float> white((size_t)width, 255.0f);
+    if (cudaMemset(h->d_ring, 0, sizeof(float) * (size_t)batch * height * width) != cudaSuccess ||
+        cudaMemcpy(h->d_row, white.data(), sizeof(float) * width, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->d_pal, palette_rgb, 768, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("image setup failed"); return fail(SSDR_E_CUDA); }
+    *out = h;
+    return SSDR_OK;
+}
+
+int ssdr_wf_image_destroy(ssdr_wf_image_t h) {
+    if (!h) return SSDR_OK;
+    if (h->st) cudaStreamSynchronize(h->st);
+    cudaFree(h->d_ring); cudaFree(h->d_delay); cudaFree(h->d_row); cudaFree(h->d_pal); cudaFree(h->d_rgb); cudaFree(h->d_f64); cudaFree(h->d_y);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return SSDR_OK;
+}
+
+static int wf_image_push_any(ssdr_wf_image_t h, const float* src, cudaMemcpyKind kind) {
+    const size_t row = (size_t)h->batch * h->W;
+    // deque(maxlen = 3).appendleft: a full deque silently drops its oldest (rightmost) entry first
+    int slot;
+    if ((int)h->deque.size() == kWfDelay) { slot = h->deque.back(); h->deque.pop_back(); }
+    else { bool used[kWfDelay] = {false, false, false}; for (int s : h->deque) used[s] = true; slot = 0; while (used[slot]) ++slot; }
+    SSDR_CUDA(cudaMemcpyAsync(h->d_delay + (size_t)slot * row, src, row * sizeof(float), kind, h->st));
+    h->deque.insert(h->deque.begin(), slot);
+    h->run_index++;
+    if (h->run_index > kWfDelay) {                       // scroll one line down, top line <- oldest delayed row
+        const int s = h->deque.back(); h->deque.pop_back();
+        h->head = (h->head + h->H - 1) % h->H;
+        SSDR_CUDA(cudaMemcpy2DAsync(h->d_ring + (size_t)h->head * h->W, sizeof(float) * (size_t)h->H * h->W,
+                                    h->d_delay + (size_t)s * row, sizeof(float) * h->W, sizeof(float) * h->W,
+                                    (size_t)h->batch, cudaMemcpyDeviceToDevice, h->st));
+    }
+    SSDR_CUDA(cudaStreamSynchronize(h->st));
+    return SSDR_OK;
+}
+
+int ssdr_wf_image_push(ssdr_wf_image_t h, const float* colour_host) {
+    SSDR_ARG(h && colour_host, "null argument");
+    return wf_image_push_any(h, colour_host, cudaMemcpyHostToDevice);
+}
+
+int ssdr_wf_image_push_dev(ssdr_wf_image_t h, const float* colour_dev) {
+    SSDR_ARG(h && colour_dev, "null argument");
+    return wf_image_push_any(h, colour_dev, cudaMemcpyDeviceToDevice);
+}
+
+int ssdr_wf_image_white(ssdr_wf_image_t h) {
+    SSDR_ARG(h != nullptr, "null handle");
+    for (int ch = 0; ch < h->batch; ++ch)
+        SSDR_CUDA(cudaMemcpyAsync(h->d_ring + ((size_t)ch * h->H + h->head) * h->W, h->d_row, sizeof(float) * h->W,
+                                  cudaMemcpyDeviceToDevice, h->st));
+    SSDR_CUDA(cudaStreamSynchronize(h->st));
+    return SSDR_OK;
+}
+
+int ssdr_wf_image_get(ssdr_wf_image_t h, uint8_t* rgb, double* wf_data) {
+    SSDR_ARG(h != nullptr, "null handle");
+    const size_t px = (size_t)h->batch * h->H * h->W;
+    int rc;
+    if (rgb) {
+        if (!h->d_rgb && (rc = dev_alloc(&h->d_rgb, px * 3))) return rc;
+        if ((rc = image_rgb_launch(h->d_ring, h->d_pal, h->d_rgb, h->batch, h->H, h->W, h->head, h->st))) return rc;
+        SSDR_CUDA(cudaMemcpyAsync(rgb, h->d_rgb, px * 3, cudaMemcpyDeviceToHost, h->st));
+    }
+    if (wf_data) {
+        if (!h->d_f64 && (rc = dev_alloc(&h->d_f64, px))) return rc;
+        if ((rc = image_data_launch(h->d_ring, h->d_f64, h->batch, h->H, h->W, h->head, h->st))) return rc;
+        SSDR_CUDA(cudaMemcpyAsync(wf_data, h->d_f64, px * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    }
+    SSDR_CUDA(cudaStreamSynchronize(h->st));
+    return SSDR_OK;
+}
+
+int ssdr_wf_image_trace(ssdr_wf_image_t h, int t_avg, int spectrum_height, double* v, int32_t* y) {
+    SSDR_ARG(h != nullptr && t_avg >= 1 && spectrum_height >= 1, "bad argument");
+    const size_t n = (size_t)h->batch * h->W;
+    int rc;
+    if (!h->d_f64 && (rc = dev_alloc(&h->d_f64, (size_t)h->batch * h->H * h->W))) return rc;
+    if (!h->d_y && (rc = dev_alloc(&h->d_y, n))) return rc;
+    if ((rc = image_trace_launch(h->d_ring, h->d_f64, h->d_y, h->batch, h->H, h->W, h->head, t_avg, spectrum_height, h->st))) return rc;
+    if (v) SSDR_CUDA(cudaMemcpyAsync(v, h->d_f64, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (y) SSDR_CUDA(cudaMemcpyAsync(y, h->d_y, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    SSDR_CUDA(cudaStreamSynchronize(h->st));
     return SSDR_OK;
 }
 

@@ -2,6 +2,8 @@
 // synthetic IQ generator used by the bench and the full-size tests.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdint>
 
 #include "common.cuh"
@@ -162,6 +164,79 @@ __global__ void synth_kernel(void* out, int batch, int frames, int nfft, unsigne
 }
 
 }  // namespace
+
+// ---- display epilogues (8f.3) -----------------------------------------------------------
+// The waterfall image of the reference is wf_data[H][W] scrolled down one line per row (utils_supersdr.py:896-897,
+// an O(H W) copy) behind a 3-deep delay deque (:893).  Here it is a ring of float32 rows per channel: display line y
+// is ring slot (head + y) mod H.
+__global__ void image_rgb_kernel(const float* __restrict__ ring, const uint8_t* __restrict__ pal, uint8_t* __restrict__ rgb,
+                                 int batch, int H, int W, int head) {
+    const size_t total = (size_t)batch * H * W;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(e % W);
+        const size_t r = e / W;
+        const int y = (int)(r % H), ch = (int)(r / H);
+        const float v = ring[((size_t)ch * H + (head + y) % H) * W + x];
+        const int idx = min(max(__float2int_rn(v), 0), 255);     // pixel = uint8(rint(wf_color)), DESIGN.md 1
+        rgb[3 * e] = pal[3 * idx]; rgb[3 * e + 1] = pal[3 * idx + 1]; rgb[3 * e + 2] = pal[3 * idx + 2];
+    }
+}
+
+__global__ void image_data_kernel(const float* __restrict__ ring, double* __restrict__ out, int batch, int H, int W, int head) {
+    const size_t total = (size_t)batch * H * W;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(e % W);
+        const size_t r = e / W;
+        const int y = (int)(r % H), ch = (int)(r / H);
+        out[e] = (double)ring[((size_t)ch * H + (head + y) % H) * W + x];
+    }
+}
+
+// display_stuff.plot_spectrum (utils_supersdr.py:1678-1679): v = nanmean of the newest t_avg lines per bin (float64;
+// the sum of <= 15 float32 values is exact in float64), y = SH - 1 - int(v / 255 * SH).
+__global__ void image_trace_kernel(const float* __restrict__ ring, double* __restrict__ v_out, int* __restrict__ y_out,
+                                   int batch, int H, int W, int head, int t_avg, int spectrum_height) {
+    const size_t total = (size_t)batch * W;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(e % W), ch = (int)(e / W);
+        double sum = 0.0;
+        int cnt = 0;
+        for (int y = 0; y < t_avg && y < H; ++y) {
+            const float f = ring[((size_t)ch * H + (head + y) % H) * W + x];
+            if (f == f) { sum = __dadd_rn(sum, (double)f); ++cnt; }
+        }
+        const double v = cnt ? __ddiv_rn(sum, (double)cnt) : __longlong_as_double(0x7ff8000000000000LL);
+        if (v_out) v_out[e] = v;
+        if (y_out) y_out[e] = (v == v) ? spectrum_height - 1 - __double2int_rz(__dmul_rn(__ddiv_rn(v, 255.0), (double)spectrum_height)) : -1;
+    }
+}
+
+int image_rgb_launch(const float* ring, const uint8_t* pal, uint8_t* rgb, int batch, int H, int W, int head, cudaStream_t st) {
+    const size_t total = (size_t)batch * H * W;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+    image_rgb_kernel<<<blocks, 256, 0, st>>>(ring, pal, rgb, batch, H, W, head);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+int image_data_launch(const float* ring, double* out, int batch, int H, int W, int head, cudaStream_t st) {
+    const size_t total = (size_t)batch * H * W;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+    image_data_kernel<<<blocks, 256, 0, st>>>(ring, out, batch, H, W, head);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+int image_trace_launch(const float* ring, double* v, int* y, int batch, int H, int W, int head, int t_avg, int sh, cudaStream_t st) {
+    const size_t total = (size_t)batch * W;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+    image_trace_kernel<<<blocks, 256, 0, st>>>(ring, v, y, batch, H, W, head, t_avg, sh);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
 
 int interp_launch(const InterpLaunch& a, cudaStream_t st) {
     dim3 grid((a.kp.n + IT - 1) / IT, a.batch);

@@ -144,6 +144,87 @@ class WaterfallBank:
             pass
 
 
+def create_cm(which="cutesdr"):
+    """display_stuff.create_cm (utils_supersdr.py:1391-1412): the 255-entry CuteSDR colour map, as float tuples."""
+    colormap = []
+    if which == "cutesdr":
+        for i in range(255):
+            if i < 43:
+                col = (0, 0, 255 * (i) / 43)
+            if (i >= 43) and (i < 87):
+                col = (0, 255 * (i - 43) / 43, 255)
+            if (i >= 87) and (i < 120):
+                col = (0, 255, 255 - (255 * (i - 87) / 32))
+            if (i >= 120) and (i < 154):
+                col = ((255 * (i - 120) / 33), 255, 0)
+            if (i >= 154) and (i < 217):
+                col = (255, 255 - (255 * (i - 154) / 62), 0)
+            if i >= 217:
+                col = (255, 0, 128 * (i - 217) / 38)
+            colormap.append(col)
+    return colormap
+
+
+def palette_u8(colormap):
+    """uint8[256][3] look-up table from a ``create_cm`` colour map: components truncated to integers (what an 8-bit
+    palette stores; the conversion happens inside pygame -- parity unpinned), entry 255 = white (the value
+    ``set_white_flag`` writes, utils_supersdr.py:875-877)."""
+    pal = np.full((256, 3), 255, np.uint8)
+    cm = np.asarray(colormap, dtype=np.float64)
+    pal[:len(cm)] = np.clip(np.trunc(cm), 0, 255).astype(np.uint8)
+    return pal
+
+
+class WaterfallImage:
+    """The scrolling waterfall image and the spectrum trace on the GPU: ``push`` takes one
+    ``wf_color`` row per channel and reproduces kiwi_waterfall.run's 3-deep delay deque and one-line scroll
+    (utils_supersdr.py:893-897) on a ring buffer; ``image`` returns RGB through the palette and/or ``wf_data``;
+    ``trace`` is display_stuff.plot_spectrum's ``nanmean`` of the newest 15 lines and its y pixel (:1678-1679)."""
+
+    def __init__(self, batch, height, width, colormap="cutesdr", device=None):
+        _lib.init(device)
+        self.batch, self.height, self.width = int(batch), int(height), int(width)
+        self.palette = palette_u8(create_cm(colormap) if isinstance(colormap, str) else colormap)
+        h = C.c_void_p()
+        check(lib.ssdr_wf_image_create(C.byref(h), self.batch, self.height, self.width, ptr(np.ascontiguousarray(self.palette))))
+        self._h = h
+
+    def push(self, colour_rows):
+        rows = np.ascontiguousarray(colour_rows, dtype=np.float32)
+        if rows.shape != (self.batch, self.width):
+            raise ValueError("colour rows must be float32[%d, %d]" % (self.batch, self.width))
+        check(lib.ssdr_wf_image_push(self._h, ptr(rows)))
+
+    def push_dev(self, colour_dev_ptr):
+        check(lib.ssdr_wf_image_push_dev(self._h, colour_dev_ptr))
+
+    def set_white_flag(self):
+        check(lib.ssdr_wf_image_white(self._h))
+
+    def image(self, want_rgb=True, want_data=False):
+        rgb = np.empty((self.batch, self.height, self.width, 3), np.uint8) if want_rgb else None
+        data = np.empty((self.batch, self.height, self.width), np.float64) if want_data else None
+        check(lib.ssdr_wf_image_get(self._h, ptr(rgb), ptr(data)))
+        return rgb, data
+
+    def trace(self, t_avg=15, spectrum_height=200):
+        v = np.empty((self.batch, self.width), np.float64)
+        y = np.empty((self.batch, self.width), np.int32)
+        check(lib.ssdr_wf_image_trace(self._h, int(t_avg), int(spectrum_height), ptr(v), ptr(y)))
+        return v, y
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ssdr_wf_image_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class kiwi_waterfall:
     """Drop-in for utils_supersdr.kiwi_waterfall (utils_supersdr.py:592-898).
 
