@@ -239,6 +239,14 @@ int ssdr_wf_image_get(ssdr_wf_image_t h, uint8_t* rgb, double* wf_data);
 int ssdr_wf_image_trace(ssdr_wf_image_t h, int t_avg, int spectrum_height, double* v, int32_t* y);
 
 /* ---------------------------------------------------------------------------------------------
+ * IMA-ADPCM decode (kiwi/client.py:33-87 ImaAdpcmDecoder; Kiwis with audio compression enabled -- SuperSDR itself
+ * sends compression=0, utils_supersdr.py:978): data uint8[batch][n_bytes], two 4-bit codes per byte, low nibble
+ * first -> pcm int16[batch][2*n_bytes].  state int32[batch][2] = (step index, previous sample) per stream, read
+ * and updated, so consecutive calls stream (all zero = a fresh decoder).  Host buffers.
+ * ------------------------------------------------------------------------------------------- */
+int ssdr_adpcm_decode(const uint8_t* data_host, int batch, int n_bytes, int32_t* state, int16_t* pcm_out);
+
+/* ---------------------------------------------------------------------------------------------
  * IQ wire-format unpack (kiwi/client.py:443-454): big-endian int16 I,Q -> complex64, unscaled
  * ------------------------------------------------------------------------------------------- */
 int ssdr_unpack_iq_s16be(const void* s16be_host, float* cf32_host, size_t n_complex);

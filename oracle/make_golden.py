@@ -139,6 +139,29 @@ def gen_palette(m):
     return cm.shape
 
 
+def gen_adpcm():
+    """kiwi/client.py ImaAdpcmDecoder (:58-87) on random codes, streamed in three calls -> tests/golden/adpcm.npz."""
+    sys.path.insert(0, ref_import.REFERENCE_DIR)
+    from kiwi import client
+    rng = np.random.default_rng(21)
+    streams = []
+    for s_ in range(4):
+        data = rng.integers(0, 256, 3 * 333).astype(np.uint8)
+        if s_ == 1:
+            data[:] = 0x77                       # step index pinned at its upper clamp, samples saturate
+        if s_ == 2:
+            data[:] = 0x00                       # step index pinned at 0
+        dec = client.ImaAdpcmDecoder()
+        out, states = [], []
+        for c in range(3):
+            out.append(np.array(dec.decode(bytes(data[c * 333:(c + 1) * 333])), np.int16))
+            states.append((dec.index, dec.prev))
+        streams.append((data, np.concatenate(out), np.array(states, np.int32)))
+    np.savez_compressed(os.path.join(OUT, "adpcm.npz"), data=np.stack([d for d, _, _ in streams]),
+                        pcm=np.stack([p for _, p, _ in streams]), states=np.stack([t for _, _, t in streams]))
+    return len(streams)
+
+
 def write_kiwi_iq_wav(path, blocks, fs=12000, t0=1234567.25):
     """A Kiwi IQ WAV file as kiwirecorder writes it: RIFF/WAVE, 16-byte fmt chunk (PCM, 2 channels, 16 bit), then a
     10-byte 'kiwi' GNSS chunk (<BBII) before every 'data' chunk of interleaved little-endian int16 I/Q."""
@@ -199,5 +222,6 @@ if __name__ == "__main__":
     gen_tier_u()
     gen_kiwi_wav()
     print("palette:", gen_palette(m))
+    print("adpcm streams:", gen_adpcm())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

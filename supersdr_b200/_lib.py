@@ -96,6 +96,7 @@ _PROTOS = {
     "ssdr_wf_image_white": (_i, [_vp]),
     "ssdr_wf_image_get": (_i, [_vp, _vp, _vp]),
     "ssdr_wf_image_trace": (_i, [_vp, _i, _i, _vp, _vp]),
+    "ssdr_adpcm_decode": (_i, [_vp, _i, _i, _vp, _vp]),
     "ssdr_resample_line": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ssdr_fir_valid_f64": (_i, [_vp, _sz, _vp, _i, _vp]),
     "ssdr_unpack_iq_s16be": (_i, [_vp, _vp, _sz]),

@@ -855,6 +855,29 @@ int ssdr_wf_image_trace(ssdr_wf_image_t h, int t_avg, int spectrum_height, doubl
     return SSDR_OK;
 }
 
+int ssdr_adpcm_decode(const uint8_t* data_host, int batch, int n_bytes, int32_t* state, int16_t* pcm_out) {
+    SSDR_ARG(data_host && state && pcm_out && batch >= 1 && n_bytes >= 0, "bad argument");
+    if (n_bytes == 0) return SSDR_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    uint8_t* d_in = nullptr; int* d_st = nullptr; int16_t* d_out = nullptr;
+    const size_t nin = (size_t)batch * n_bytes;
+    int rc;
+    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_st); cudaFree(d_out); };
+    if ((rc = dev_alloc(&d_in, nin)) || (rc = dev_alloc(&d_st, (size_t)batch * 2)) || (rc = dev_alloc(&d_out, nin * 2))) { cleanup(); return rc; }
+    cudaError_t e = cudaMemcpy(d_in, data_host, nin, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_st, state, sizeof(int) * 2 * batch, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = adpcm_launch(d_in, batch, n_bytes, d_st, d_out, 0);
+        if (!rc) e = cudaMemcpy(pcm_out, d_out, nin * 2 * sizeof(int16_t), cudaMemcpyDeviceToHost);
+        if (!rc && e == cudaSuccess) e = cudaMemcpy(state, d_st, sizeof(int) * 2 * batch, cudaMemcpyDeviceToHost);
+    }
+    cleanup();
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "adpcm copy", __FILE__, __LINE__);
+    return SSDR_OK;
+}
+
 // =============================================================================================
 // IQ unpack
 // =============================================================================================

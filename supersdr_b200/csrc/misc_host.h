@@ -39,6 +39,7 @@ struct ResampleKernelParams {
 int image_rgb_launch(const float* ring, const uint8_t* pal, uint8_t* rgb, int batch, int H, int W, int head, cudaStream_t st);
 int image_data_launch(const float* ring, double* out, int batch, int H, int W, int head, cudaStream_t st);
 int image_trace_launch(const float* ring, double* v, int* y, int batch, int H, int W, int head, int t_avg, int sh, cudaStream_t st);
+int adpcm_launch(const uint8_t* data, int batch, int n_bytes, int* state, int16_t* pcm, cudaStream_t st);
 int interp_launch(const InterpLaunch& a, cudaStream_t st);
 int resample_line_launch(const ResampleKernelParams& kp, int batch, cudaStream_t st);
 int fir_valid_launch(const double* x, const double* h, int T, double* out, size_t n_out, cudaStream_t st);

@@ -165,6 +165,65 @@ __global__ void synth_kernel(void* out, int batch, int frames, int nfft, unsigne
 
 }  // namespace
 
+// ---- IMA-ADPCM (kiwi/client.py:33-87): 4-bit codes -> int16, low nibble first; the step index and the
+// previous sample are the per-stream state.  Sequential per stream: one thread per stream, 16 input bytes per load.
+__constant__ short kAdpcmStep[89] = {
+    7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 19, 21, 23, 25, 28, 31, 34, 37, 41, 45, 50, 55, 60, 66, 73, 80, 88, 97, 107, 118, 130,
+    143, 157, 173, 190, 209, 230, 253, 279, 307, 337, 371, 408, 449, 494, 544, 598, 658, 724, 796, 876, 963, 1060, 1166, 1282,
+    1411, 1552, 1707, 1878, 2066, 2272, 2499, 2749, 3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630,
+    9493, 10442, 11487, 12635, 13899, 15289, 16818, 18500, 20350, 22385, 24623, 27086, 29794, 32767};
+
+__device__ __forceinline__ int adpcm_sample(int code, int& index, int& prev) {
+    const int step = kAdpcmStep[index];
+    index = min(max(index + ((code & 4) ? 2 * (code & 3) + 2 : -1), 0), 88);      // indexAdjustTable: -1 x4, 2 4 6 8
+    int diff = step >> 3;
+    if (code & 1) diff += step >> 2;
+    if (code & 2) diff += step >> 1;
+    if (code & 4) diff += step;
+    if (code & 8) diff = -diff;
+    prev = min(max(prev + diff, -32768), 32767);
+    return prev;
+}
+
+__global__ void adpcm_kernel(const uint8_t* __restrict__ data, int batch, int n_bytes, int* __restrict__ state, int16_t* __restrict__ pcm) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= batch) return;
+    int index = min(max(state[2 * ch], 0), 88), prev = state[2 * ch + 1];
+    const uint8_t* src = data + (size_t)ch * n_bytes;
+    int16_t* dst = pcm + (size_t)ch * n_bytes * 2;
+    int i = 0;
+    if ((((size_t)src) & 15) == 0 && (((size_t)dst) & 15) == 0) {
+        for (; i + 16 <= n_bytes; i += 16) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+            unsigned o[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const unsigned b = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                const int s0 = adpcm_sample((int)(b & 15u), index, prev);
+                const int s1 = adpcm_sample((int)(b >> 4), index, prev);
+                o[k] = ((unsigned)s0 & 0xffffu) | ((unsigned)s1 << 16);
+            }
+            uint4* q = reinterpret_cast<uint4*>(dst + 2 * i);
+            q[0] = make_uint4(o[0], o[1], o[2], o[3]); q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            q[2] = make_uint4(o[8], o[9], o[10], o[11]); q[3] = make_uint4(o[12], o[13], o[14], o[15]);
+        }
+    }
+    for (; i < n_bytes; ++i) {
+        const unsigned b = src[i];
+        dst[2 * i] = (int16_t)adpcm_sample((int)(b & 15u), index, prev);
+        dst[2 * i + 1] = (int16_t)adpcm_sample((int)(b >> 4), index, prev);
+    }
+    state[2 * ch] = index; state[2 * ch + 1] = prev;
+}
+
+int adpcm_launch(const uint8_t* data, int batch, int n_bytes, int* state, int16_t* pcm, cudaStream_t st) {
+    adpcm_kernel<<<(batch + 127) / 128, 128, 0, st>>>(data, batch, n_bytes, state, pcm);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
 // ---- display epilogues (8f.3) -----------------------------------------------------------
 // The waterfall image of the reference is wf_data[H][W] scrolled down one line per row (utils_supersdr.py:896-897,
 // an O(H W) copy) behind a 3-deep delay deque (:893).  Here it is a ring of float32 rows per channel: display line y

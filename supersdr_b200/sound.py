@@ -226,6 +226,35 @@ class ResampleLine:
         return (out, mono) if want_mono else out
 
 
+class ImaAdpcmDecoder:
+    """Batched drop-in for kiwi/client.py:58-87: ``decode(data)`` turns 4-bit IMA-ADPCM codes into int16 samples and
+    carries (index, prev) from call to call.  ``batch`` independent streams decode in one launch."""
+
+    def __init__(self, batch=1, device=None):
+        _lib.init(device)
+        self.batch = int(batch)
+        self.state = np.zeros((self.batch, 2), np.int32)          # (index, prev) per stream
+
+    @property
+    def index(self):
+        return int(self.state[0, 0])
+
+    @property
+    def prev(self):
+        return int(self.state[0, 1])
+
+    def decode(self, data):
+        """bytes (one stream) or uint8[batch, n_bytes] -> int16 samples, two per byte (low nibble first)."""
+        single = isinstance(data, (bytes, bytearray, memoryview))
+        arr = np.frombuffer(bytes(data), np.uint8)[None] if single else np.ascontiguousarray(data, dtype=np.uint8)
+        if arr.ndim != 2 or arr.shape[0] != self.batch:
+            raise ValueError("data must be bytes or uint8[%d, n_bytes]" % self.batch)
+        arr = np.ascontiguousarray(arr)
+        out = np.empty((self.batch, 2 * arr.shape[1]), np.int16)
+        check(lib.ssdr_adpcm_decode(ptr(arr), self.batch, int(arr.shape[1]), ptr(self.state), ptr(out)))
+        return out[0] if single else out
+
+
 class filtering:
     """Drop-in for utils_supersdr.filtering (utils_supersdr.py:333-348): same design, ``lowpass``
     evaluated on the GPU (a one-channel, ratio-1 interpolator bank = plain 'valid' FIR)."""

@@ -194,3 +194,21 @@ def test_resample_line_vs_scipy(ssdr, up, down, n):
         ref = resample_poly(x[b].astype(np.float64) * (float(vol[b]) / 100), up, down, padtype="line")[:-1]
         assert mono[b].shape == ref.shape
         assert np.abs(mono[b] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_adpcm_reference_golden(ssdr):
+    """IMA-ADPCM decode against fixtures from the reference's ImaAdpcmDecoder (kiwi/client.py:58-87): four streams in
+    one launch, streamed in three calls (state carried), including the clamped-index and saturating cases."""
+    g = np.load(os.path.join(GOLD, "adpcm.npz"))
+    data, pcm, states = g["data"], g["pcm"], g["states"]
+    dec = ssdr.ImaAdpcmDecoder(batch=data.shape[0])
+    for c in range(3):
+        out = dec.decode(data[:, c * 333:(c + 1) * 333])
+        assert np.array_equal(out, pcm[:, c * 666:(c + 1) * 666])
+        assert np.array_equal(dec.state, states[:, c])
+    one = ssdr.ImaAdpcmDecoder()                       # the reference's single-stream surface: bytes in, samples out
+    assert np.array_equal(one.decode(bytes(data[0, :333])), pcm[0, :666]) and (one.index, one.prev) == tuple(states[0, 0])
+    big = ssdr.ImaAdpcmDecoder(batch=300)              # aligned 16-byte path + tail, many streams
+    d = np.tile(data[0, :512 + 5], (300, 1))
+    ref = ssdr.ImaAdpcmDecoder().decode(bytes(data[0, :512 + 5]))
+    assert np.array_equal(big.decode(d), np.tile(ref, (300, 1)))
