@@ -75,13 +75,11 @@ struct Cfg {
 #else
     static constexpr bool SPLIT = (FPC == 1 && G > 32);     // split-phase frame-buffer hand-off (mbarrier)
 #endif
-    // Warps of a one-frame-per-SM group start their warp-local passes STAGGER cycles apart per level (4 levels, by
-    // warp / 4): in lock step all sixteen warps hit the shared-memory pipe and then the fp32 pipe together; staggered,
-    // one warp's loads overlap another's butterflies (measured: 2.26 -> 2.09 ms on config 2).
-#ifndef SSDR_STAGGER
-#define SSDR_STAGGER 500
-#endif
-    static constexpr int STAGGER = (LG == 14) ? SSDR_STAGGER : 0;
+    // Warps start their warp-local passes STAGGER cycles apart per level (4 levels): leaving the pass-1 barrier in lock
+    // step, all warps of an SM hit the shared-memory pipe and then the fp32 pipe together; staggered, one warp's loads
+    // overlap another's butterflies (measured: 16384: 2.26 -> 2.09 ms on config 2; 8192: +15 %; 2048/4096: +3 %;
+    // smaller sizes lose).
+    static constexpr int STAGGER = (LG == 14) ? 500 : (LG == 13) ? 300 : (LG >= 11) ? 100 : 0;     // cycles per level, measured optima
     static_assert(NP == 2 || NP == 3, "supported sizes: 64 .. 16384");
     static_assert(M0 == 32 || M0 == 1024, "first pass leaves 32 or 1024 sub-transforms");
     // dynamic shared memory layout (bytes)
@@ -749,7 +747,7 @@ wf_fft_kernel(const WfKernelParams kp) {
 #endif
             // from here each warp owns a contiguous 1024-point (NP == 3) / 32-point sub-transform: warp-local
             if constexpr (C::STAGGER > 0) {
-                const int lvl = (threadIdx.x >> 7) & 3;
+                const int lvl = (LG == 14) ? ((threadIdx.x >> 7) & 3) : (LG == 13) ? ((threadIdx.x >> 6) & 3) : ((threadIdx.x >> 5) & 3);     // four levels
                 if (lvl) { const long long c0 = clock64(); while (clock64() - c0 < lvl * C::STAGGER) { } }
             }
 #if !(SSDR_EXP & 16)
