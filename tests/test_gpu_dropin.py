@@ -90,3 +90,45 @@ def test_kiwi_sound_dropin(ssdr):
     out = np.ones((2048, 2), np.int16)
     snd.play_buffer(out, 2048, None, None)
     assert snd.mute_counter == 15 and not out.any()
+
+
+def test_concurrent_threads_separate_handles(ssdr):
+    """The reference calls its classes from three threads (W/F thread supersdr.py:121-122, SND thread utils_supersdr.py:
+    1198-1199, PortAudio callback :1211-1213); ctypes drops the GIL, so the shim must be re-entrant across handles and
+    its error slot thread-local."""
+    import threading
+    iq = tier_u.synth_batch(3, 2, 4096, seed=5)
+    x = tier_u.synth_demod_iq("usb", 512 * 8, seed=2)[None]
+    pcm = np.random.default_rng(1).integers(-20000, 20000, (1, 512)).astype(np.int16)
+    wf, dm, ib = ssdr.WaterfallBank(4096, 3, 2), ssdr.DemodBank(1, 512 * 8), ssdr.InterpBank(1, 4, max_samples=512)
+    ref_px = wf.process(iq)["pixels"].copy()
+    ref_pcm = dm.process(x)["pcm_i16"].copy()
+    ref_st = ib.process(pcm, 80, 0.1).copy()
+    errors, results = [], {"wf": [], "dm": [], "ib": []}
+
+    def run(kind):
+        try:
+            for _ in range(20):
+                if kind == "wf":
+                    results[kind].append(np.array_equal(wf.process(iq)["pixels"], ref_px))
+                elif kind == "dm":
+                    dm.reset()
+                    results[kind].append(np.array_equal(dm.process(x)["pcm_i16"], ref_pcm))
+                else:
+                    ib.reset()
+                    results[kind].append(np.array_equal(ib.process(pcm, 80, 0.1), ref_st))
+                    try:                                     # an error raised in this thread ...
+                        ib.process(np.zeros((1, 4096), np.int16))
+                    except ssdr.SsdrError as e:
+                        assert "outside" in str(e)           # ... carries this thread's message
+        except Exception as e:                               # noqa: BLE001
+            errors.append((kind, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(k,)) for k in ("wf", "dm", "ib")]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert all(len(v) == 20 and all(v) for v in results.values())
+    wf.close(); dm.close(); ib.close()
