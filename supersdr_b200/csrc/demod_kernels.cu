@@ -48,6 +48,12 @@ __device__ __forceinline__ float2 ld_iq(const void* base, size_t idx) {
     }
 }
 
+// MUFU approximations (relative error ~1e-7, far inside the 1e-5 RMS tolerance of the demodulator): no denormal / range
+// fix-up code and no slow-path calls on the per-sample path
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // cos / sin of a 32-bit phase (2 pi phase / 2^32), MUFU path: abs error ~4e-7
 __device__ __forceinline__ void nco(unsigned ph, float& c, float& s) {
     float a = (float)(int)ph * 1.4629180792671596e-9f;   // 2 pi / 2^32
@@ -157,7 +163,7 @@ demod_kernel(const DemodKernelParams kp) {
             for (int r = 0; r < SPL; ++r) {
                 float p = acc[r].x * acc[r].x + acc[r].y * acc[r].y;
                 psum += p;
-                mag[r] = sqrtf(p);
+                mag[r] = sqrt_approx(p);
                 bmax = fmaxf(bmax, mag[r]);
             }
 #pragma unroll
@@ -244,13 +250,18 @@ demod_kernel(const DemodKernelParams kp) {
 #pragma unroll
                     for (int r = 0; r < SPL; ++r) m[r] = fmaxf(m[r], excl);
                 }
-                // u[k] = hm[k] 2^(k c2); M = prefix max with seed e_in 2^(-c2); e[k] = M[k] 2^(-k c2)
+                // u[k] = hm[k] 2^(k c2); M = prefix max with seed e_in 2^(-c2); e[k] = M[k] 2^(-k c2).  k = 16 lane + r:
+                // 2^(+-k c2) = 2^(+-16 lane c2) * (2^(+-c2))^r, the second factor by a running product (16 steps)
+                const float up1 = ex2_approx(cp.c2), dn1 = ex2_approx(-cp.c2);
+                float upk = ex2_approx((float)(SPL * lane) * cp.c2), dnk = ex2_approx(-(float)(SPL * lane) * cp.c2);
                 float mrun = 0.f;
                 float u[SPL];
+                float dn[SPL];
 #pragma unroll
                 for (int r = 0; r < SPL; ++r) {
-                    const float kf = (float)(SPL * lane + r);
-                    u[r] = m[r] * exp2f(kf * cp.c2);
+                    u[r] = m[r] * upk;
+                    dn[r] = dnk;
+                    upk *= up1; dnk *= dn1;
                     mrun = fmaxf(mrun, u[r]);
                     u[r] = mrun;
                 }
@@ -262,14 +273,13 @@ demod_kernel(const DemodKernelParams kp) {
                 }
                 pre = __shfl_up_sync(0xffffffffu, pre, 1);
                 if (lane == 0) pre = 0.f;
-                pre = fmaxf(pre, e_in * exp2f(-cp.c2));
+                pre = fmaxf(pre, e_in * dn1);
                 float e_last = 0.f;
 #pragma unroll
                 for (int r = 0; r < SPL; ++r) {
-                    const float kf = (float)(SPL * lane + r);
-                    float e = fmaxf(u[r], pre) * exp2f(-kf * cp.c2);
-                    float m2 = log2f(e * (1.0f / SSDR_FS));
-                    float g = kDemodAgcOut * exp2f(fmaxf(m2, cp.knee2) * cp.slope_m1);
+                    float e = fmaxf(u[r], pre) * dn[r];
+                    float m2 = lg2_approx(e * (1.0f / SSDR_FS));
+                    float g = kDemodAgcOut * ex2_approx(fmaxf(m2, cp.knee2) * cp.slope_m1);
                     out[r] = a[r] * g;
                     e_last = e;
                 }
