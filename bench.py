@@ -263,6 +263,47 @@ def main():
         except Exception as e:                               # noqa: BLE001  (the headline arms must survive)
             scatter = {"error": repr(e)[:200]}
 
+    # ---- peer-ingest arm (multi-GPU only): the same root-ingest deployment WITHOUT a scatter -- every rank's waterfall
+    # kernel reads its shard in place from rank 0's HBM over NVLink (CUDA IPC mapping, peer loads), so the transfer
+    # overlaps the butterflies tile by tile and no staging copy is written or re-read. ----------------------
+    peer = None
+    if dist is not None and not args.no_scatter:
+        try:
+            from supersdr_b200 import sharding
+            root = None
+            handle = [None]
+            if rank == 0:
+                root = S.DeviceBuffer(world * n_samples * 8)
+                for r_ in range(world):
+                    S._lib.check(S.lib.ssdr_synth_iq_dev(root.ptr.value + r_ * n_samples * 8, S.SSDR_IQ_CF32, B, N_AVG, NFFT, 1234 + r_))
+                handle[0] = sharding.export_device_buffer(root.ptr.value)
+            dist.broadcast_object_list(handle, src=0)
+            base = root.ptr.value if rank == 0 else sharding.open_peer_buffer(handle[0])
+            mine = base + rank * n_samples * 8
+            pg_steps = max(2, min(args.steps, 4))
+            bank.set_remote_input(rank != 0)
+            bank.time_dev(mine, S.SSDR_IQ_CF32, px_dev.ptr, 1)
+            barrier()
+            pg_ms = max_over_ranks(bank.time_dev(mine, S.SSDR_IQ_CF32, px_dev.ptr, pg_steps) / pg_steps)
+            barrier()
+            peer_px = px_dev.download(np.uint8, (B, NFFT))
+            bank.set_remote_input(False)
+            bank.time_dev(iq_dev.ptr, S.SSDR_IQ_CF32, px_dev.ptr, 1); bank.sync()      # same seed, local copy
+            same = bool(np.array_equal(peer_px, px_dev.download(np.uint8, (B, NFFT))))
+            peer = {"value": world * n_samples / pg_ms / 1e3, "unit": "Msamples/s", "ms_per_step": pg_ms,
+                    "root_egress_gbs": (world - 1) * n_samples * 8 / pg_ms / 1e6, "steps": pg_steps,
+                    "rows_equal_local_run": same,
+                    "what": "every rank's kernel loads its shard from rank 0's HBM over NVLink (peer loads, no scatter, no "
+                            "staging copy); rank 0 reads local memory"}
+            barrier()
+            if rank != 0:
+                sharding.close_peer_buffer(base)
+            barrier()
+            if root is not None:
+                root.free()
+        except Exception as e:                               # noqa: BLE001
+            peer = {"error": repr(e)[:200]}
+
     # ---- end-to-end arm: pinned host IQ -> H2D -> kernel -> D2H pixels, every step ----------------------
     e2e = None
     checksum = None
@@ -377,6 +418,8 @@ def main():
     }
     if scatter is not None:
         line["scatter_from_root"] = scatter
+    if peer is not None:
+        line["peer_ingest"] = peer
     if demod:
         line["demod"] = demod
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

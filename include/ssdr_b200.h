@@ -80,6 +80,14 @@ int ssdr_memcpy_d2h(void* host, const void* dev, size_t bytes);
 int ssdr_dev_memset(void* dev, int value, size_t bytes);
 int ssdr_device_sync(void);
 
+/* Peer ingest (multi-GPU, one process per GPU): export a device allocation of this process so that another rank's
+ * kernels can read it in place over NVLink -- the root-ingest deployment without a staging copy: every rank's waterfall
+ * kernel loads its shard straight from the root's HBM, the transfer overlapping the butterflies.
+ * handle64: 64 opaque bytes (cudaIpcMemHandle_t) to pass to the other process by any means. */
+int ssdr_ipc_export(void* dev, void* handle64);
+int ssdr_ipc_open(const void* handle64, void** dev);     /* maps the peer allocation; enables peer access */
+int ssdr_ipc_close(void* dev);
+
 /* Deterministic synthetic IQ written directly in HBM (bench / full-size tests): per channel three
  * tones (0.5, 0.05, 0.005 FS at hashed bins) + uniform-sum noise of sigma ~1e-3 FS, SURVEY 8d.
  * iq_dev: [batch][frames][nfft] in the given format. */
@@ -117,6 +125,9 @@ int ssdr_wf_create(ssdr_wf_t* h, int nfft, int batch, int n_avg, int window, dou
                    int p_lo, float p_gamma);
 int ssdr_wf_destroy(ssdr_wf_t h);
 int ssdr_wf_set_display(ssdr_wf_t h, int first_channel, int count, const ssdr_wf_display_t* params);
+/* Tell the handle that the device inputs of ssdr_wf_process_dev live in a PEER GPU's memory (ssdr_ipc_open): the kernel
+ * then reads them in place over NVLink and skips its L2 bulk prefetch, which is pathologically slow on peer addresses. */
+int ssdr_wf_set_remote_input(ssdr_wf_t h, int remote);
 /* Spec tables the handle uses (for parity tests): twiddles float32[2*nfft], thresholds float32[256],
  * radix plan (returns number of passes). */
 int ssdr_wf_get_tables(ssdr_wf_t h, float* twiddles, float* thresholds, int* radices);

@@ -55,6 +55,9 @@ _PROTOS = {
     "ssdr_init": (_i, [_i]),
     "ssdr_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.c_char_p, _i]),
     "ssdr_launch_count": (C.c_uint64, []),
+    "ssdr_ipc_export": (_i, [_vp, _vp]),
+    "ssdr_ipc_open": (_i, [_vp, _pvp]),
+    "ssdr_ipc_close": (_i, [_vp]),
     "ssdr_dev_alloc": (_i, [_pvp, _sz]),
     "ssdr_dev_free": (_i, [_vp]),
     "ssdr_host_alloc": (_i, [_pvp, _sz]),
@@ -67,6 +70,7 @@ _PROTOS = {
     "ssdr_wf_create": (_i, [_pvp, _i, _i, _i, _i, _d, _i, _f]),
     "ssdr_wf_destroy": (_i, [_vp]),
     "ssdr_wf_set_display": (_i, [_vp, _i, _i, C.POINTER(WfDisplay)]),
+    "ssdr_wf_set_remote_input": (_i, [_vp, _i]),
     "ssdr_wf_get_tables": (_i, [_vp, _vp, _vp, C.POINTER(_i)]),
     "ssdr_wf_get_window": (_i, [_vp, _vp]),
     "ssdr_wf_process": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),

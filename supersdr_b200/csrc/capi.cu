@@ -57,6 +57,7 @@ using namespace ssdr;
 // =============================================================================================
 struct ssdr_wf {
     int nfft = 0, batch = 0, n_avg = 1, window = 1, p_lo = 0;
+    int remote_input = 0;             // device inputs live in a peer GPU's memory (ssdr_wf_set_remote_input)
     float p_gamma = 0.f;
     double cal_db = 0.0;
     float est_c1 = 0.f, est_c0 = 0.f;
@@ -174,6 +175,29 @@ int ssdr_memcpy_d2h(void* host, const void* dev, size_t bytes) { SSDR_CUDA(cudaM
 int ssdr_dev_memset(void* dev, int value, size_t bytes) { SSDR_CUDA(cudaMemset(dev, value, bytes)); return SSDR_OK; }
 int ssdr_device_sync(void) { SSDR_CUDA(cudaDeviceSynchronize()); return SSDR_OK; }
 
+int ssdr_ipc_export(void* dev, void* handle64) {
+    SSDR_ARG(dev && handle64, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    SSDR_CUDA(cudaIpcGetMemHandle(&h, dev));
+    std::memcpy(handle64, &h, 64);
+    return SSDR_OK;
+}
+
+int ssdr_ipc_open(const void* handle64, void** dev) {
+    SSDR_ARG(handle64 && dev, "null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    SSDR_CUDA(cudaIpcOpenMemHandle(dev, h, cudaIpcMemLazyEnablePeerAccess));
+    return SSDR_OK;
+}
+
+int ssdr_ipc_close(void* dev) {
+    SSDR_ARG(dev != nullptr, "null argument");
+    SSDR_CUDA(cudaIpcCloseMemHandle(dev));
+    return SSDR_OK;
+}
+
 int ssdr_synth_iq_dev(void* iq_dev, int iq_format, int batch, int frames, int nfft, uint32_t seed) {
     SSDR_ARG(iq_dev && batch > 0 && frames > 0 && nfft > 0, "bad synth arguments");
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
@@ -280,6 +304,12 @@ int ssdr_wf_set_display(ssdr_wf_t h, int first, int count, const ssdr_wf_display
     return SSDR_OK;
 }
 
+int ssdr_wf_set_remote_input(ssdr_wf_t h, int remote) {
+    SSDR_ARG(h != nullptr, "null handle");
+    h->remote_input = remote ? 1 : 0;
+    return SSDR_OK;
+}
+
 int ssdr_wf_get_tables(ssdr_wf_t h, float* twiddles, float* thresholds, int* radices) {
     SSDR_ARG(h != nullptr, "null handle");
     if (twiddles) std::memcpy(twiddles, h->h_wtab.data(), sizeof(float) * 2 * (size_t)h->nfft);
@@ -323,6 +353,7 @@ int ssdr_wf_process_dev(ssdr_wf_t h, const void* iq_dev, int iq_format, uint8_t*
     if (rcs) return rcs;
     WfLaunch a = wf_base(h);
     a.iq = iq_dev; a.iq_format = iq_format; a.disp = h->d_disp; a.batch = h->batch;
+    a.remote_input = h->remote_input;
     a.pixels = pixels_dev; a.colour = colour_dev; a.spectrum = spectrum_dev; a.scalars = scalars_dev ? scalars_dev : h->d_sc;
     return wf_launch(a, h->compute);
 }

@@ -11,6 +11,7 @@ namespace ssdr {
 struct WfLaunch {
     const void* iq = nullptr;          // device, [batch][n_avg][nfft]
     int iq_format = SSDR_IQ_CF32;
+    int remote_input = 0;              // iq lives in a peer GPU's memory (read over NVLink): no L2 bulk prefetch
     const uint8_t* lines = nullptr;    // device, colorrow entry (iq ignored)
     const float* wtab = nullptr;       // device, 2*nfft floats
     const float* win = nullptr;        // device, nfft/2 floats (first half of the Hann window)

@@ -112,6 +112,8 @@ struct WfKernelParams {
     const uint8_t* lines;           // colorrow entry: [batch][n_avg][N] uint8 lines (else null)
     uint16_t* sums;                 // large-N path: per-bin byte sums out [batch / rf][rf * N] (no colour stage), else null
     int rf;                         // large-N path: front radix (virtual channel = channel * rf + q)
+    int prefetch;                   // 1: bulk-prefetch the next frame into L2 (local input); 0 for peer (NVLink) input, where the
+                                    // bulk prefetch is pathologically slow (measured 120x) and the loads stream at link rate anyway
     int batch, n_avg;
     int p_lo;
     float p_gamma;
@@ -706,7 +708,7 @@ wf_fft_kernel(const WfKernelParams kp) {
 #pragma unroll 1
         for (int f = 0; f < kp.n_avg; ++f) {
             // the frame after next (or the first frame of this group's next channel) -> L2
-            if (t == 0) {
+            if (kp.prefetch && t == 0) {
                 const bool last = (f + 1 == kp.n_avg);
                 const size_t nxt = last ? (size_t)(ch + ch_stride) * kp.n_avg * N : off + N;
                 if (!last || ch + ch_stride < kp.batch)
@@ -1041,7 +1043,7 @@ int wf_launch(const WfLaunch& a, cudaStream_t st) {
     kp.iq = a.iq; kp.wtab = reinterpret_cast<const float2*>(a.wtab); kp.win = a.win; kp.thr = a.thr; kp.disp = a.disp;
     kp.pixels = a.pixels; kp.colour = a.colour; kp.spectrum = a.spectrum; kp.scalars = a.scalars;
     kp.lines = a.lines; kp.batch = a.batch; kp.n_avg = a.n_avg; kp.p_lo = a.p_lo; kp.p_gamma = a.p_gamma;
-    kp.est_c1 = a.est_c1; kp.est_c0 = a.est_c0;
+    kp.est_c1 = a.est_c1; kp.est_c0 = a.est_c0; kp.prefetch = a.remote_input ? 0 : 1;
     kp.key_bits = 1;
     while ((1 << kp.key_bits) <= 255 * a.n_avg) ++kp.key_bits;
     const int lg = ilog2(a.nfft);

@@ -63,3 +63,30 @@ def gather_rows_to_root(local_rows, total_channels, group=None):
         for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, t.contiguous(), 0, group)]):
             q.wait()
     return None
+
+
+def export_device_buffer(dev_ptr):
+    """64-byte IPC handle of a device allocation of this process (ssdr_ipc_export): send it to the other ranks (e.g.
+    ``torch.distributed.broadcast_object_list``) so that their kernels can read the buffer in place over NVLink."""
+    import ctypes as C
+    from . import _lib
+    h = (C.c_ubyte * 64)()
+    _lib.check(_lib.lib.ssdr_ipc_export(C.c_void_p(dev_ptr), h))
+    return bytes(h)
+
+
+def open_peer_buffer(handle64):
+    """Map a peer rank's exported allocation; returns the device pointer valid in this process (close with
+    ``close_peer_buffer``)."""
+    import ctypes as C
+    from . import _lib
+    p = C.c_void_p()
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle64)
+    _lib.check(_lib.lib.ssdr_ipc_open(buf, C.byref(p)))
+    return p.value
+
+
+def close_peer_buffer(dev_ptr):
+    import ctypes as C
+    from . import _lib
+    _lib.check(_lib.lib.ssdr_ipc_close(C.c_void_p(dev_ptr)))

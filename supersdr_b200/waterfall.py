@@ -61,6 +61,10 @@ class WaterfallBank:
                                     float(low_clip_db), float(dynamic_range))
         check(lib.ssdr_wf_set_display(self._h, first, count, arr))
 
+    def set_remote_input(self, remote=True):
+        """Device inputs of ``process_dev`` / ``time_dev`` live in a peer GPU's memory (sharding.open_peer_buffer)."""
+        check(lib.ssdr_wf_set_remote_input(self._h, int(bool(remote))))
+
     def tables(self):
         """(twiddles complex64[nfft], thresholds float32[256], radix plan) the kernels use."""
         tw = np.empty(2 * self.nfft, np.float32)

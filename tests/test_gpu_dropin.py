@@ -1,5 +1,6 @@
 """GPU: the drop-in classes keep the reference's call surface and produce what the
 reference pipeline would produce from the same server-side lines / PCM."""
+import os
 import types
 
 import numpy as np
@@ -132,3 +133,42 @@ def test_concurrent_threads_separate_handles(ssdr):
     assert not errors, errors
     assert all(len(v) == 20 and all(v) for v in results.values())
     wf.close(); dm.close(); ib.close()
+
+
+def test_peer_ingest_across_processes(ssdr):
+    """Root-ingest without a staging copy: another process maps this process's device buffer (CUDA IPC,
+    ssdr_ipc_export / ssdr_ipc_open) and its waterfall kernel reads the IQ in place; the rows equal the local run."""
+    import subprocess
+    import sys
+    from supersdr_b200 import sharding
+    B, n, N = 6, 2, 16384
+    iq = ssdr.DeviceBuffer(B * n * N * 8)
+    px = ssdr.DeviceBuffer(B * N)
+    ssdr._lib.check(ssdr.lib.ssdr_synth_iq_dev(iq.ptr, ssdr.SSDR_IQ_CF32, B, n, N, 4321))
+    bank = ssdr.WaterfallBank(N, B, n)
+    bank.process_dev(iq.ptr, ssdr.SSDR_IQ_CF32, px.ptr)
+    bank.sync()
+    want = px.download(np.uint8, (B, N))
+    handle = sharding.export_device_buffer(iq.ptr.value)
+    child = (
+        "import sys, numpy as np\n"
+        "import supersdr_b200 as S\n"
+        "from supersdr_b200 import sharding\n"
+        "S.init(0)\n"
+        "B, n, N = %d, %d, %d\n"
+        "p = sharding.open_peer_buffer(bytes.fromhex(sys.argv[1]))\n"
+        "px = S.DeviceBuffer(B * N)\n"
+        "bank = S.WaterfallBank(N, B, n)\n"
+        "bank.set_remote_input(True)\n"
+        "bank.process_dev(p, S.SSDR_IQ_CF32, px.ptr); bank.sync()\n"
+        "print('CHECKSUM', int(px.download(np.uint8, (B, N)).astype(np.uint64).sum()), flush=True)\n"
+        "sys.stdout.buffer.write(px.download(np.uint8, (B, N)).tobytes())\n"
+        "sharding.close_peer_buffer(p)\n" % (B, n, N))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", child, handle.hex()], cwd=root, capture_output=True, timeout=300)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    head, _, rest = out.stdout.partition(b"\n")
+    assert head.startswith(b"CHECKSUM")
+    got = np.frombuffer(rest[:B * N], np.uint8).reshape(B, N)
+    assert np.array_equal(got, want)
+    bank.close(); iq.free(); px.free()
