@@ -91,11 +91,10 @@ struct ssdr_demod {
     float* d_taps = nullptr;
     cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_read[2] = {nullptr, nullptr}, ev_done = nullptr;
+    cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
     double am_pow16[5];
-    void* d_in = nullptr;          // two chunk slots of in_bytes / 2 each
+    void* d_in = nullptr;          // device staging of the host API, [batch][max_samples] complex64
     size_t in_bytes = 0;
-    int chunk_ch = 0;
     float* d_f32 = nullptr;
     int16_t* d_i16 = nullptr;
     float* d_rssi = nullptr;
@@ -487,10 +486,8 @@ int ssdr_demod_create(ssdr_demod_t* out, int batch, int max_samples) {
         cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(SSDR_E_CUDA); }
     if (cudaEventCreate(&h->ev_t0) != cudaSuccess || cudaEventCreate(&h->ev_t1) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
-    for (int i = 0; i < 2; ++i)
-        if (cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_read[i], cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
-    if (cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
+    if (cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
     cudaMemset(h->d_chan, 0, sizeof(DemodChan) * (size_t)batch);
     cudaMemset(h->d_taps, 0, sizeof(float) * (size_t)batch * SSDR_FIR_TAPS);
     *out = h;
@@ -507,7 +504,7 @@ int ssdr_demod_destroy(ssdr_demod_t h) {
     cudaFree(h->d_in); cudaFree(h->d_f32); cudaFree(h->d_i16); cudaFree(h->d_rssi);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
-    for (int i = 0; i < 2; ++i) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_read[i]) cudaEventDestroy(h->ev_read[i]); }
+    if (h->ev_copied) cudaEventDestroy(h->ev_copied);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->compute) cudaStreamDestroy(h->compute);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
@@ -604,8 +601,8 @@ int ssdr_demod_process(ssdr_demod_t h, const void* iq_host, int iq_format, int n
         const size_t s0 = (size_t)f0 * SSDR_FRAME, ns = (size_t)nf * SSDR_FRAME;
         SSDR_CUDA(cudaMemcpy2DAsync(d_iq + s0 * sb, pitch_b * sb, static_cast<const unsigned char*>(iq_host) + s0 * sb, pitch_b * sb,
                                     ns * sb, (size_t)h->batch, cudaMemcpyHostToDevice, h->copy_in));
-        SSDR_CUDA(cudaEventRecord(h->ev_copied[0], h->copy_in));
-        SSDR_CUDA(cudaStreamWaitEvent(h->compute, h->ev_copied[0], 0));
+        SSDR_CUDA(cudaEventRecord(h->ev_copied, h->copy_in));
+        SSDR_CUDA(cudaStreamWaitEvent(h->compute, h->ev_copied, 0));
         if ((rc = demod_launch_block(h, d_iq + s0 * sb, iq_format, (int)ns, n_samples, pcm_f32 ? h->d_f32 + s0 : nullptr,
                                      pcm_i16 ? h->d_i16 + s0 : nullptr, rssi_dbm ? h->d_rssi + f0 : nullptr))) return rc;
         SSDR_CUDA(cudaEventRecord(h->ev_done, h->compute));
