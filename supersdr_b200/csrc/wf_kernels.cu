@@ -580,20 +580,34 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
     const size_t row = (size_t)ch * N;
     group_sync<C>(slot);                                                 // every warp of the group is past its last FFT pass
     const Divisor dden = make_divisor(den);
-    auto emit_row = [&](auto fast) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            const float s = (float)key_at(q);
-            const float m = div_rn<true>(s, dfn);
-            const float w = ((m - 255.0f) - 13.0f) + z3;
-            float c = div_rn<decltype(fast)::value>(w - low, dden);
-            c = fminf(fmaxf(c, 0.0f), 1.0f);
-            c = c * 254.0f;
-            c = fminf(fmaxf(c, 0.0f), 255.0f);
-            stage[sidx(out_index(q))] = c;
-        }
+    auto colour_of = [&](float s, auto fast) -> float {
+        const float m = div_rn<true>(s, dfn);
+        const float w = ((m - 255.0f) - 13.0f) + z3;
+        float c = div_rn<decltype(fast)::value>(w - low, dden);
+        c = fminf(fmaxf(c, 0.0f), 1.0f);
+        c = c * 254.0f;
+        return fminf(fmaxf(c, 0.0f), 255.0f);
     };
-    if (dden.ok) emit_row(std::true_type{}); else emit_row(std::false_type{});     // group-uniform
+    // The colour value depends on the bin only through its integer key: when there are (many) fewer possible keys than
+    // bins, the group fills a key -> colour table once (behind the row stage in the frame buffer) and every bin looks
+    // its value up instead of repeating the two divisions.
+    const int nkeys = 255 * kp.n_avg + 1;
+    constexpr int row_words = LINEAR ? N + N / 32 : N;          // extent of the row stage (padded when LINEAR)
+    const bool use_lut = (G >= 256) && (4 * nkeys <= N) && (row_words + nkeys <= stage_words);
+    if (use_lut) {
+        float* lut = stage + row_words;
+        auto fill = [&](auto fast) { for (int k = t; k < nkeys; k += G) lut[k] = colour_of((float)k, fast); };
+        if (dden.ok) fill(std::true_type{}); else fill(std::false_type{});
+        group_sync<C>(slot);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) stage[sidx(out_index(q))] = lut[key_at(q)];
+    } else {
+        auto emit_row = [&](auto fast) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) stage[sidx(out_index(q))] = colour_of((float)key_at(q), fast);
+        };
+        if (dden.ok) emit_row(std::true_type{}); else emit_row(std::false_type{});     // group-uniform
+    }
     group_sync<C>(slot);
 #pragma unroll 4
     for (int i = 0; i < 32; ++i) {
