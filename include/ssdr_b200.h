@@ -181,6 +181,13 @@ int ssdr_demod_create(ssdr_demod_t* h, int batch, int max_samples_per_call);
 int ssdr_demod_destroy(ssdr_demod_t h);
 int ssdr_demod_set(ssdr_demod_t h, int first_channel, int count, const ssdr_demod_params_t* params);
 int ssdr_demod_reset(ssdr_demod_t h);   /* zero all per-channel streaming state */
+/* FIR engine of the fused kernel.  FFMA: direct form on the fp32 pipe (one warp per channel).  TCGEN05: the FIR as a
+ * Toeplitz GEMM on the 5th-generation tensor cores (3 x TF32 split, accumulators in TMEM); channels are grouped four at a
+ * time by filter, so it pays when many channels share a pass-band width.  Same state, same outputs to the demodulator's
+ * tolerance (1e-5 relative RMS); engines may be switched between calls.  No reference counterpart (the DSP is remote). */
+#define SSDR_DEMOD_ENGINE_FFMA    0
+#define SSDR_DEMOD_ENGINE_TCGEN05 1
+int ssdr_demod_set_engine(ssdr_demod_t h, int engine);
 /* n_samples per channel, multiple of SSDR_FRAME.  iq [batch][n_samples]; outputs (NULL = skip):
  * pcm_f32 [batch][n_samples], pcm_i16 [batch][n_samples] (rint + saturate),
  * rssi_dbm [batch][n_samples/512] (what the SND header's s-meter carries, utils:1068-1069). */

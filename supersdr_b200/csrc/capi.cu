@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -98,6 +99,13 @@ struct ssdr_demod {
     float* d_f32 = nullptr;
     int16_t* d_i16 = nullptr;
     float* d_rssi = nullptr;
+    // FIR engine (ssdr_demod_set_engine) and, for the tcgen05 engine, the channels grouped in quads that share a filter
+    int engine = SSDR_DEMOD_ENGINE_FFMA;
+    std::vector<float> h_taps;     // host mirror of d_taps, [batch][127]
+    bool quads_dirty = true;
+    int n_quads = 0;
+    int4* d_quad_ch = nullptr;
+    int* d_quad_fid = nullptr;
 };
 
 struct ssdr_interp {
@@ -490,6 +498,11 @@ int ssdr_demod_create(ssdr_demod_t* out, int batch, int max_samples) {
         cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); return fail(SSDR_E_CUDA); }
     cudaMemset(h->d_chan, 0, sizeof(DemodChan) * (size_t)batch);
     cudaMemset(h->d_taps, 0, sizeof(float) * (size_t)batch * SSDR_FIR_TAPS);
+    h->h_taps.assign((size_t)batch * SSDR_FIR_TAPS, 0.0f);
+    if (const char* e = std::getenv("SSDR_DEMOD_ENGINE")) {      // developer override of the default engine
+        if (!std::strcmp(e, "tcgen05")) h->engine = SSDR_DEMOD_ENGINE_TCGEN05;
+        else if (!std::strcmp(e, "ffma")) h->engine = SSDR_DEMOD_ENGINE_FFMA;
+    }
     *out = h;
     if ((rc = ssdr_demod_reset(h))) { *out = nullptr; return fail(rc); }
     return SSDR_OK;
@@ -502,6 +515,7 @@ int ssdr_demod_destroy(ssdr_demod_t h) {
     if (h->copy_out) cudaStreamSynchronize(h->copy_out);
     cudaFree(h->d_chan); cudaFree(h->d_state); cudaFree(h->d_hist); cudaFree(h->d_taps);
     cudaFree(h->d_in); cudaFree(h->d_f32); cudaFree(h->d_i16); cudaFree(h->d_rssi);
+    cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->ev_copied) cudaEventDestroy(h->ev_copied);
@@ -551,6 +565,52 @@ int ssdr_demod_set(ssdr_demod_t h, int first, int count, const ssdr_demod_params
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     SSDR_CUDA(cudaMemcpy(h->d_chan + first, chan.data(), sizeof(DemodChan) * (size_t)count, cudaMemcpyHostToDevice));
     SSDR_CUDA(cudaMemcpy(h->d_taps + (size_t)first * SSDR_FIR_TAPS, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice));
+    std::memcpy(h->h_taps.data() + (size_t)first * SSDR_FIR_TAPS, taps.data(), sizeof(float) * taps.size());
+    h->quads_dirty = true;
+    return SSDR_OK;
+}
+
+int ssdr_demod_set_engine(ssdr_demod_t h, int engine) {
+    SSDR_ARG(h != nullptr, "null handle");
+    SSDR_ARG(engine == SSDR_DEMOD_ENGINE_FFMA || engine == SSDR_DEMOD_ENGINE_TCGEN05, "unknown demodulator engine %d", engine);
+    h->engine = engine;
+    return SSDR_OK;
+}
+
+// tcgen05 engine: one M = 128 tile is four channels x one frame and all four share the B operand (the taps), so channels
+// are grouped by filter (bitwise-equal taps) into quads; a filter with n channels takes ceil(n / 4) quads, the last one
+// padded with -1.  The streaming state stays per channel, so regrouping between calls is free.
+static int demod_build_quads(ssdr_demod_t h) {
+    const int B = h->batch;
+    const size_t tb = sizeof(float) * SSDR_FIR_TAPS;
+    std::vector<int> order((size_t)B);
+    for (int i = 0; i < B; ++i) order[(size_t)i] = i;
+    const float* t = h->h_taps.data();
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return std::memcmp(t + (size_t)a * SSDR_FIR_TAPS, t + (size_t)b * SSDR_FIR_TAPS, tb) < 0;
+    });
+    std::vector<int4> qc;
+    std::vector<int> qf;
+    int fid = -1, fill = 4;
+    for (int i = 0; i < B; ++i) {
+        const int ch = order[(size_t)i];
+        const bool same = i > 0 && !std::memcmp(t + (size_t)ch * SSDR_FIR_TAPS, t + (size_t)order[(size_t)i - 1] * SSDR_FIR_TAPS, tb);
+        if (!same) { ++fid; fill = 4; }
+        if (fill == 4) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(fid); fill = 0; }
+        int4& q = qc.back();
+        (fill == 0 ? q.x : fill == 1 ? q.y : fill == 2 ? q.z : q.w) = ch;
+        ++fill;
+    }
+    SSDR_CUDA(cudaStreamSynchronize(h->compute));
+    cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid);
+    h->d_quad_ch = nullptr; h->d_quad_fid = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&h->d_quad_ch, qc.size()))) return rc;
+    if ((rc = dev_alloc(&h->d_quad_fid, qf.size()))) return rc;
+    SSDR_CUDA(cudaMemcpy(h->d_quad_ch, qc.data(), sizeof(int4) * qc.size(), cudaMemcpyHostToDevice));
+    SSDR_CUDA(cudaMemcpy(h->d_quad_fid, qf.data(), sizeof(int) * qf.size(), cudaMemcpyHostToDevice));
+    h->n_quads = (int)qc.size();
+    h->quads_dirty = false;
     return SSDR_OK;
 }
 
@@ -560,6 +620,10 @@ static int demod_launch_block(ssdr_demod_t h, const void* iq_dev, int iq_format,
     a.iq = iq_dev; a.iq_format = iq_format; a.chan = h->d_chan; a.state = h->d_state; a.hist = h->d_hist; a.taps = h->d_taps;
     a.pcm_f32 = pcm_f32_dev; a.pcm_i16 = pcm_i16_dev; a.rssi = rssi_dev; a.batch = h->batch; a.n_samples = n_samples; a.pitch = pitch;
     for (int s = 0; s < 5; ++s) a.am_pow16[s] = h->am_pow16[s];
+    if (h->engine == SSDR_DEMOD_ENGINE_TCGEN05) {
+        if (h->quads_dirty) { int rc = demod_build_quads(h); if (rc) return rc; }
+        return demod_tc_launch(a, h->d_quad_ch, h->d_quad_fid, h->n_quads, h->compute);
+    }
     return demod_launch(a, h->compute);
 }
 

@@ -63,4 +63,8 @@ struct DemodLaunch {
 
 int demod_launch(const DemodLaunch& a, cudaStream_t st);
 
+// tcgen05 engine (demod_tc_kernels.cu).  quad_ch[q] = four channels that share one filter (slot 0 valid, unused slots -1),
+// quad_fid[q] = id of that filter; consecutive quads of one filter are adjacent so a CTA rebuilds its B operand rarely.
+int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_quads, cudaStream_t st);
+
 }  // namespace ssdr

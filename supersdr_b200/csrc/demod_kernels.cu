@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "demod_host.h"
+#include "demod_post.cuh"
 
 namespace ssdr {
 
@@ -35,30 +36,6 @@ constexpr int WARPS = 4;
 constexpr int TAP_PAD = 128;
 
 __device__ __forceinline__ int zpos(int i) { return i + (i >> 4); }   // 1 pad per 16: lane stride 17
-
-template <int FMT>
-__device__ __forceinline__ float2 ld_iq(const void* base, size_t idx) {
-    if constexpr (FMT == SSDR_IQ_CF32) {
-        return __ldcs(reinterpret_cast<const float2*>(base) + idx);
-    } else {
-        unsigned v = __ldcs(reinterpret_cast<const unsigned*>(base) + idx);
-        const unsigned sw = __byte_perm(v, 0u, 0x2301);   // swap the bytes of both 16-bit halves
-        const int i = (int)(short)(sw & 0xffffu), q = (int)sw >> 16;
-        return make_float2((float)i, (float)q);
-    }
-}
-
-// MUFU approximations (relative error ~1e-7, far inside the 1e-5 RMS tolerance of the demodulator): no denormal / range
-// fix-up code and no slow-path calls on the per-sample path
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-// cos / sin of a 32-bit phase (2 pi phase / 2^32), MUFU path: abs error ~4e-7
-__device__ __forceinline__ void nco(unsigned ph, float& c, float& s) {
-    float a = (float)(int)ph * 1.4629180792671596e-9f;   // 2 pi / 2^32
-    __sincosf(a, &s, &c);
-}
 
 // One FIR step = 8 taps t = 32*s4 + 8*PH + u.  Sample (r, t) sits K = 127 + r - t past the lane base
 // (buffer coordinates) and is kept in register slot K & 31, so consecutive steps reuse 15 of the 23
@@ -100,12 +77,8 @@ demod_kernel(const DemodKernelParams kp) {
         const DemodChan cp = kp.chan[ch];
         DemodState* stp = kp.state + ch;
         // ---- load per-channel state ---------------------------------------------------------
-        unsigned ph1 = stp->ph1, ph2 = stp->ph2;
-        float e_in = stp->e_in;
-        double dc = stp->dc;
-        float2 zprev = make_float2(stp->zprev_re, stp->zprev_im);
-        unsigned blk = stp->blk;
-        float ring = (lane < SSDR_HANG_BLOCKS) ? stp->ring[lane] : 0.0f;
+        DemodRegs st;
+        demod_regs_load(st, stp, lane);
         __syncwarp();
         for (int i = lane; i < H; i += 32) ws->z[zpos(1 + i)] = kp.hist[(size_t)ch * H + i];
         if (lane == 0) ws->z[0] = make_float2(0.f, 0.f);
@@ -117,13 +90,13 @@ demod_kernel(const DemodKernelParams kp) {
             // ---- mixer: lane-strided, coalesced; all sixteen loads of the frame in flight together ----------
             float2 xin[SPL];
 #pragma unroll
-            for (int r = 0; r < SPL; ++r) xin[r] = ld_iq<FMT>(kp.iq, s0 + lane + 32 * r);
+            for (int r = 0; r < SPL; ++r) xin[r] = demod_ld_iq<FMT>(kp.iq, s0 + lane + 32 * r);
 #pragma unroll
             for (int r = 0; r < SPL; ++r) {
                 const int k = lane + 32 * r;
                 const float2 x = xin[r];
                 float c, s;
-                nco(ph1 + (unsigned)k * cp.inc1, c, s);
+                nco(st.ph1 + (unsigned)k * cp.inc1, c, s);
                 // x * exp(-j theta): (xr + j xi)(c - j s)
                 float2 y = make_float2(x.x * c + x.y * s, x.y * c - x.x * s);
                 ws->z[zpos(1 + H + k)] = y;
@@ -156,170 +129,13 @@ demod_kernel(const DemodKernelParams kp) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { int k = lane + 32 * i; if (k < H) ws->z[zpos(1 + k)] = tmp[i]; }
             }
-            // ---- magnitude, RSSI -----------------------------------------------------------------
-            float mag[SPL];
-            float psum = 0.f, bmax = 0.f;
-#pragma unroll
-            for (int r = 0; r < SPL; ++r) {
-                float p = acc[r].x * acc[r].x + acc[r].y * acc[r].y;
-                psum += p;
-                mag[r] = sqrt_approx(p);
-                bmax = fmaxf(bmax, mag[r]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                psum += __shfl_xor_sync(0xffffffffu, psum, o);
-                bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-            }
-            if (kp.rssi && lane == 0) {
-                float mp = fmaxf(psum * (1.0f / FR), 1e-30f);
-                kp.rssi[(size_t)ch * (kp.pitch / FR) + b] = 10.0f * log10f(mp * (1.0f / (SSDR_FS * SSDR_FS))) + kDemodFsDbm;
-            }
-            // ---- detector --------------------------------------------------------------------------
-            float a[SPL];
-            if (cp.mode == SSDR_MODE_NBFM) {
-                float2 last = acc[SPL - 1];
-                float2 prv = make_float2(__shfl_up_sync(0xffffffffu, last.x, 1), __shfl_up_sync(0xffffffffu, last.y, 1));
-                if (lane == 0) prv = zprev;
-#pragma unroll
-                for (int r = 0; r < SPL; ++r) {
-                    float2 z = acc[r];
-                    float re = z.x * prv.x + z.y * prv.y;     // z * conj(prev)
-                    float im = z.y * prv.x - z.x * prv.y;
-                    // a zero product (first sample of a stream, or silence) demodulates to 0, not +-pi
-                    a[r] = (re == 0.0f && im == 0.0f) ? 0.0f : atan2f(im, re) * (32767.0f / 3.14159265358979f);
-                    prv = z;
-                }
-            } else if (cp.mode == SSDR_MODE_AM) {
-                // carrier tracker dc[k] = dc[k-1] + beta (mag[k] - dc[k-1]) in float64: lane-local
-                // recurrence from a zero (lane 0: true) carry-in, then an affine warp scan.
-                double B = (lane == 0) ? dc : 0.0;
-#pragma unroll
-                for (int r = 0; r < SPL; ++r) B = B + kDemodAmBeta * ((double)mag[r] - B);
-#pragma unroll
-                for (int s = 0; s < 5; ++s) {
-                    double up = __shfl_up_sync(0xffffffffu, B, 1 << s);
-                    if (lane >= (1 << s)) B = B + kp.am_pow16[s] * up;   // (om^16)^(2^s)
-                }
-                double carry = __shfl_up_sync(0xffffffffu, B, 1);
-                if (lane == 0) carry = dc;
-                dc = __shfl_sync(0xffffffffu, B, 31);
-                // B after the scan is the carrier at the end of this lane's segment; replay with the carry-in
-                double d = carry;
-#pragma unroll
-                for (int r = 0; r < SPL; ++r) {
-                    d = d + kDemodAmBeta * ((double)mag[r] - d);
-                    a[r] = (float)((double)mag[r] - d);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < SPL; ++r) {
-                    const int k = SPL * lane + r;
-                    float c, s;
-                    nco(ph2 + (unsigned)k * cp.inc2, c, s);
-                    a[r] = acc[r].x * c - acc[r].y * s;       // Re(z * exp(+j theta2))
-                }
-            }
-            // ---- AGC ---------------------------------------------------------------------------------
-            float out[SPL];
-            if (cp.mode == SSDR_MODE_NBFM) {
-#pragma unroll
-                for (int r = 0; r < SPL; ++r) out[r] = a[r];
-            } else if (!cp.agc_on) {
-#pragma unroll
-                for (int r = 0; r < SPL; ++r) out[r] = a[r] * cp.man_gain;
-            } else {
-                // hang: hm[k] = max(max(ring), prefix max of mag)
-                float hb = ring;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) hb = fmaxf(hb, __shfl_xor_sync(0xffffffffu, hb, o));
-                float m[SPL];
-                float run = 0.f;
-#pragma unroll
-                for (int r = 0; r < SPL; ++r) { run = fmaxf(run, mag[r]); m[r] = cp.agc_hang ? run : mag[r]; }
-                if (cp.agc_hang) {
-                    float excl = run;                          // inclusive scan of lane maxima
-#pragma unroll
-                    for (int s = 0; s < 5; ++s) {
-                        float up = __shfl_up_sync(0xffffffffu, excl, 1 << s);
-                        if (lane >= (1 << s)) excl = fmaxf(excl, up);
-                    }
-                    excl = __shfl_up_sync(0xffffffffu, excl, 1);
-                    if (lane == 0) excl = 0.f;
-                    excl = fmaxf(excl, hb);
-#pragma unroll
-                    for (int r = 0; r < SPL; ++r) m[r] = fmaxf(m[r], excl);
-                }
-                // u[k] = hm[k] 2^(k c2); M = prefix max with seed e_in 2^(-c2); e[k] = M[k] 2^(-k c2).  k = 16 lane + r:
-                // 2^(+-k c2) = 2^(+-16 lane c2) * (2^(+-c2))^r, the second factor by a running product (16 steps)
-                const float up1 = ex2_approx(cp.c2), dn1 = ex2_approx(-cp.c2);
-                float upk = ex2_approx((float)(SPL * lane) * cp.c2), dnk = ex2_approx(-(float)(SPL * lane) * cp.c2);
-                float mrun = 0.f;
-                float u[SPL];
-                float dn[SPL];
-#pragma unroll
-                for (int r = 0; r < SPL; ++r) {
-                    u[r] = m[r] * upk;
-                    dn[r] = dnk;
-                    upk *= up1; dnk *= dn1;
-                    mrun = fmaxf(mrun, u[r]);
-                    u[r] = mrun;
-                }
-                float pre = mrun;
-#pragma unroll
-                for (int s = 0; s < 5; ++s) {
-                    float up = __shfl_up_sync(0xffffffffu, pre, 1 << s);
-                    if (lane >= (1 << s)) pre = fmaxf(pre, up);
-                }
-                pre = __shfl_up_sync(0xffffffffu, pre, 1);
-                if (lane == 0) pre = 0.f;
-                pre = fmaxf(pre, e_in * dn1);
-                float e_last = 0.f;
-#pragma unroll
-                for (int r = 0; r < SPL; ++r) {
-                    float e = fmaxf(u[r], pre) * dn[r];
-                    float m2 = lg2_approx(e * (1.0f / SSDR_FS));
-                    float g = kDemodAgcOut * ex2_approx(fmaxf(m2, cp.knee2) * cp.slope_m1);
-                    out[r] = a[r] * g;
-                    e_last = e;
-                }
-                e_in = __shfl_sync(0xffffffffu, e_last, 31);
-            }
-            // ---- outputs: 16 consecutive samples per lane ----------------------------------------------
-            const size_t o0 = s0 + (size_t)SPL * lane;
-            if (kp.pcm_f32) {
-                float4* p = reinterpret_cast<float4*>(kp.pcm_f32 + o0);
-#pragma unroll
-                for (int r = 0; r < SPL; r += 4) __stcs(p + r / 4, make_float4(out[r], out[r + 1], out[r + 2], out[r + 3]));
-            }
-            if (kp.pcm_i16) {
-                unsigned pk[SPL / 2];
-#pragma unroll
-                for (int r = 0; r < SPL; r += 2) {
-                    short v0, v1;
-                    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(v0) : "f"(out[r]));
-                    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(v1) : "f"(out[r + 1]));
-                    pk[r / 2] = ((unsigned)(unsigned short)v0) | ((unsigned)(unsigned short)v1 << 16);
-                }
-                uint4* p = reinterpret_cast<uint4*>(kp.pcm_i16 + o0);
-                __stcs(p, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-                __stcs(p + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
-            }
-            // ---- per-frame state ---------------------------------------------------------------------------
-            zprev = make_float2(__shfl_sync(0xffffffffu, acc[SPL - 1].x, 31), __shfl_sync(0xffffffffu, acc[SPL - 1].y, 31));
-            if (lane == (int)(blk % SSDR_HANG_BLOCKS)) ring = bmax;
-            blk++;
-            ph1 += (unsigned)FR * cp.inc1;
-            ph2 += (unsigned)FR * cp.inc2;
+            // ---- magnitude / RSSI, detector, AGC, outputs, per-frame state ------------------------------
+            demod_frame_tail<LanesNatural>(acc, cp, kp, ch, b, s0, st);
             __syncwarp();
         }
         // ---- store per-channel state ---------------------------------------------------------------
         for (int i = lane; i < H; i += 32) kp.hist[(size_t)ch * H + i] = ws->z[zpos(1 + i)];
-        if (lane < SSDR_HANG_BLOCKS) stp->ring[lane] = ring;
-        if (lane == 0) {
-            stp->ph1 = ph1; stp->ph2 = ph2; stp->e_in = e_in; stp->dc = dc;
-            stp->zprev_re = zprev.x; stp->zprev_im = zprev.y; stp->blk = blk;
-        }
+        demod_regs_store(st, stp, lane);
         __syncwarp();
     }
 }

@@ -1,0 +1,251 @@
+// Demodulator back end shared by the two FIR engines (demod_kernels.cu: FFMA2 FIR; demod_tc_kernels.cu: tcgen05 FIR):
+// one warp holds one 512-sample frame of FIR output, 16 consecutive samples per LOGICAL lane, and runs
+// magnitude / RSSI -> AM / SSB / CW / NBFM detector -> AGC -> float32 + int16 PCM, carrying the per-channel streaming
+// state (parameter model utils_supersdr.py:936-945,1022-1029; SND header s-meter utils_supersdr.py:1068-1069).
+//
+// The two engines differ in which physical lane holds which 16 samples, so every lane-order-dependent step (prefix
+// scans, carries, the sample index) goes through a lane map LM; order-free reductions use xor shuffles directly.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "demod_host.h"
+
+namespace ssdr {
+
+constexpr int kDemodSpl = SSDR_FRAME / 32;    // 16 samples per lane
+
+// MUFU approximations (relative error ~1e-7, far inside the 1e-5 RMS tolerance of the demodulator): no denormal / range
+// fix-up code and no slow-path calls on the per-sample path
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// cos / sin of a 32-bit phase (2 pi phase / 2^32), MUFU path: abs error ~4e-7
+__device__ __forceinline__ void nco(unsigned ph, float& c, float& s) {
+    float a = (float)(int)ph * 1.4629180792671596e-9f;   // 2 pi / 2^32
+    __sincosf(a, &s, &c);
+}
+
+// logical lane = physical lane
+struct LanesNatural {
+    __device__ __forceinline__ static int logical(int lane) { return lane; }
+    template <class V> __device__ __forceinline__ static V up(V v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+    template <class V> __device__ __forceinline__ static V from(V v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+};
+// tcgen05 engine: TMEM lane i < 16 holds the real parts of 32-sample block i, lane 16 + i its imaginary parts; after the
+// pair exchange physical lane p holds the complex samples of logical lane 2 (p & 15) + (p >> 4)
+struct LanesPaired {
+    __device__ __forceinline__ static int logical(int lane) { return ((lane & 15) << 1) | (lane >> 4); }
+    __device__ __forceinline__ static int phys(int l) { return ((l >> 1) & 15) | ((l & 1) << 4); }
+    template <class V> __device__ __forceinline__ static V up(V v, int d) {        // callers ignore the result when logical < d
+        return __shfl_sync(0xffffffffu, v, phys((logical(threadIdx.x & 31) - d) & 31));
+    }
+    template <class V> __device__ __forceinline__ static V from(V v, int l) { return __shfl_sync(0xffffffffu, v, phys(l)); }
+};
+
+// per-channel streaming state held in registers while a warp walks the frames of its channel
+struct DemodRegs {
+    unsigned ph1, ph2;
+    float e_in;
+    double dc;
+    float2 zprev;
+    unsigned blk;
+    float ring;               // physical lane < SSDR_HANG_BLOCKS holds one slot of the hang ring
+};
+
+__device__ __forceinline__ void demod_regs_load(DemodRegs& st, const DemodState* stp, int lane) {
+    st.ph1 = stp->ph1; st.ph2 = stp->ph2;
+    st.e_in = stp->e_in;
+    st.dc = stp->dc;
+    st.zprev = make_float2(stp->zprev_re, stp->zprev_im);
+    st.blk = stp->blk;
+    st.ring = (lane < SSDR_HANG_BLOCKS) ? stp->ring[lane] : 0.0f;
+}
+__device__ __forceinline__ void demod_regs_store(const DemodRegs& st, DemodState* stp, int lane) {
+    if (lane < SSDR_HANG_BLOCKS) stp->ring[lane] = st.ring;
+    if (lane == 0) {
+        stp->ph1 = st.ph1; stp->ph2 = st.ph2; stp->e_in = st.e_in; stp->dc = st.dc;
+        stp->zprev_re = st.zprev.x; stp->zprev_im = st.zprev.y; stp->blk = st.blk;
+    }
+}
+
+// acc[r] = FIR output sample 16 L + r of frame b of channel ch (L = logical lane); s0 = index of the frame's first sample
+// in the pcm arrays.  Advances st by one frame.
+template <class LM>
+__device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl], const DemodChan& cp, const DemodKernelParams& kp,
+                                                 int ch, int b, size_t s0, DemodRegs& st) {
+    constexpr int SPL = kDemodSpl, FR = SSDR_FRAME;
+    const int lane = LM::logical(threadIdx.x & 31);
+    // ---- magnitude, RSSI -----------------------------------------------------------------
+    float mag[SPL];
+    float psum = 0.f, bmax = 0.f;
+#pragma unroll
+    for (int r = 0; r < SPL; ++r) {
+        float p = acc[r].x * acc[r].x + acc[r].y * acc[r].y;
+        psum += p;
+        mag[r] = sqrt_approx(p);
+        bmax = fmaxf(bmax, mag[r]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+    }
+    if (kp.rssi && lane == 0) {
+        float mp = fmaxf(psum * (1.0f / FR), 1e-30f);
+        kp.rssi[(size_t)ch * (kp.pitch / FR) + b] = 10.0f * log10f(mp * (1.0f / (SSDR_FS * SSDR_FS))) + kDemodFsDbm;
+    }
+    // ---- detector --------------------------------------------------------------------------
+    float a[SPL];
+    if (cp.mode == SSDR_MODE_NBFM) {
+        float2 last = acc[SPL - 1];
+        float2 prv = make_float2(LM::up(last.x, 1), LM::up(last.y, 1));
+        if (lane == 0) prv = st.zprev;
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) {
+            float2 z = acc[r];
+            float re = z.x * prv.x + z.y * prv.y;     // z * conj(prev)
+            float im = z.y * prv.x - z.x * prv.y;
+            // a zero product (first sample of a stream, or silence) demodulates to 0, not +-pi
+            a[r] = (re == 0.0f && im == 0.0f) ? 0.0f : atan2f(im, re) * (32767.0f / 3.14159265358979f);
+            prv = z;
+        }
+    } else if (cp.mode == SSDR_MODE_AM) {
+        // carrier tracker dc[k] = dc[k-1] + beta (mag[k] - dc[k-1]) in float64: lane-local
+        // recurrence from a zero (lane 0: true) carry-in, then an affine warp scan.
+        double B = (lane == 0) ? st.dc : 0.0;
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) B = B + kDemodAmBeta * ((double)mag[r] - B);
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            double up = LM::up(B, 1 << s);
+            if (lane >= (1 << s)) B = B + kp.am_pow16[s] * up;   // (om^16)^(2^s)
+        }
+        double carry = LM::up(B, 1);
+        if (lane == 0) carry = st.dc;
+        st.dc = LM::from(B, 31);
+        // B after the scan is the carrier at the end of this lane's segment; replay with the carry-in
+        double d = carry;
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) {
+            d = d + kDemodAmBeta * ((double)mag[r] - d);
+            a[r] = (float)((double)mag[r] - d);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) {
+            const int k = SPL * lane + r;
+            float c, s;
+            nco(st.ph2 + (unsigned)k * cp.inc2, c, s);
+            a[r] = acc[r].x * c - acc[r].y * s;       // Re(z * exp(+j theta2))
+        }
+    }
+    // ---- AGC ---------------------------------------------------------------------------------
+    float out[SPL];
+    if (cp.mode == SSDR_MODE_NBFM) {
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) out[r] = a[r];
+    } else if (!cp.agc_on) {
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) out[r] = a[r] * cp.man_gain;
+    } else {
+        // hang: hm[k] = max(max(ring), prefix max of mag)
+        float hb = st.ring;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hb = fmaxf(hb, __shfl_xor_sync(0xffffffffu, hb, o));
+        float m[SPL];
+        float run = 0.f;
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) { run = fmaxf(run, mag[r]); m[r] = cp.agc_hang ? run : mag[r]; }
+        if (cp.agc_hang) {
+            float excl = run;                          // inclusive scan of lane maxima
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                float up = LM::up(excl, 1 << s);
+                if (lane >= (1 << s)) excl = fmaxf(excl, up);
+            }
+            excl = LM::up(excl, 1);
+            if (lane == 0) excl = 0.f;
+            excl = fmaxf(excl, hb);
+#pragma unroll
+            for (int r = 0; r < SPL; ++r) m[r] = fmaxf(m[r], excl);
+        }
+        // u[k] = hm[k] 2^(k c2); M = prefix max with seed e_in 2^(-c2); e[k] = M[k] 2^(-k c2).  k = 16 lane + r:
+        // 2^(+-k c2) = 2^(+-16 lane c2) * (2^(+-c2))^r, the second factor by a running product (16 steps)
+        const float up1 = ex2_approx(cp.c2), dn1 = ex2_approx(-cp.c2);
+        float upk = ex2_approx((float)(SPL * lane) * cp.c2), dnk = ex2_approx(-(float)(SPL * lane) * cp.c2);
+        float mrun = 0.f;
+        float u[SPL];
+        float dn[SPL];
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) {
+            u[r] = m[r] * upk;
+            dn[r] = dnk;
+            upk *= up1; dnk *= dn1;
+            mrun = fmaxf(mrun, u[r]);
+            u[r] = mrun;
+        }
+        float pre = mrun;
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            float up = LM::up(pre, 1 << s);
+            if (lane >= (1 << s)) pre = fmaxf(pre, up);
+        }
+        pre = LM::up(pre, 1);
+        if (lane == 0) pre = 0.f;
+        pre = fmaxf(pre, st.e_in * dn1);
+        float e_last = 0.f;
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) {
+            float e = fmaxf(u[r], pre) * dn[r];
+            float m2 = lg2_approx(e * (1.0f / SSDR_FS));
+            float g = kDemodAgcOut * ex2_approx(fmaxf(m2, cp.knee2) * cp.slope_m1);
+            out[r] = a[r] * g;
+            e_last = e;
+        }
+        st.e_in = LM::from(e_last, 31);
+    }
+    // ---- outputs: 16 consecutive samples per lane ----------------------------------------------
+    const size_t o0 = s0 + (size_t)SPL * lane;
+    if (kp.pcm_f32) {
+        float4* p = reinterpret_cast<float4*>(kp.pcm_f32 + o0);
+#pragma unroll
+        for (int r = 0; r < SPL; r += 4) __stcs(p + r / 4, make_float4(out[r], out[r + 1], out[r + 2], out[r + 3]));
+    }
+    if (kp.pcm_i16) {
+        unsigned pk[SPL / 2];
+#pragma unroll
+        for (int r = 0; r < SPL; r += 2) {
+            short v0, v1;
+            asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(v0) : "f"(out[r]));
+            asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(v1) : "f"(out[r + 1]));
+            pk[r / 2] = ((unsigned)(unsigned short)v0) | ((unsigned)(unsigned short)v1 << 16);
+        }
+        uint4* p = reinterpret_cast<uint4*>(kp.pcm_i16 + o0);
+        __stcs(p, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        __stcs(p + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+    }
+    // ---- per-frame state ---------------------------------------------------------------------------
+    st.zprev = make_float2(LM::from(acc[SPL - 1].x, 31), LM::from(acc[SPL - 1].y, 31));
+    if ((threadIdx.x & 31) == (int)(st.blk % SSDR_HANG_BLOCKS)) st.ring = bmax;
+    st.blk++;
+    st.ph1 += (unsigned)FR * cp.inc1;
+    st.ph2 += (unsigned)FR * cp.inc2;
+}
+
+// sample load (K6 fused): complex64 or Kiwi big-endian int16 pairs (kiwi/client.py:449-453)
+template <int FMT>
+__device__ __forceinline__ float2 demod_ld_iq(const void* base, size_t idx) {
+    if constexpr (FMT == SSDR_IQ_CF32) {
+        return __ldcs(reinterpret_cast<const float2*>(base) + idx);
+    } else {
+        unsigned v = __ldcs(reinterpret_cast<const unsigned*>(base) + idx);
+        const unsigned sw = __byte_perm(v, 0u, 0x2301);   // swap the bytes of both 16-bit halves
+        const int i = (int)(short)(sw & 0xffffu), q = (int)sw >> 16;
+        return make_float2((float)i, (float)q);
+    }
+}
+
+}  // namespace ssdr

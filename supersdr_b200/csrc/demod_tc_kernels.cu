@@ -1,0 +1,286 @@
+// Fused demodulator, tensor-core engine: the 127-tap FIR of the demodulator as a Toeplitz GEMM on tcgen05 (sm_100a),
+// everything else (K6 unpack, NCO mix, detector, AGC, PCM, RSSI) as in demod_kernels.cu -- the back end is the same code
+// (demod_post.cuh).  Replaces the remote KiwiSDR SND computation the reference only parametrises
+// (utils_supersdr.py:1022-1029) and receives as PCM (utils_supersdr.py:1044-1076).  Spec: DESIGN.md 4.5.
+//
+// Formulation.  Cut the mixed signal z of a channel into 32-sample blocks.  The 32 FIR outputs of block i are
+//     y[32 i + n] = sum_k Z_i[k] T[k][n],   Z_i[k] = z[32 (i - 4) + k],  k < 160,   T[k][n] = h[128 + n - k]  (0 outside 0..126)
+// i.e. D[128 x 32] = A[128 x 160] B[160 x 32] with one ROW per (block, re | im) and the taps as a Toeplitz B operand.
+// A CTA step covers one 512-sample frame of FOUR channels that share a filter (host-side grouping): 4 channels x
+// {re, im} x 16 blocks = 128 rows = one M = 128 tile, and warp w reads back exactly its own channel (TMEM lanes 32 w ..).
+//
+//   * One copy of the signal serves all five K chunks: K chunk c of row i is block i - 4 + c, i.e. the same array read
+//     c rows further up.  The operand is stored as "mini-streams" of 12 rows (4 history blocks + 8 blocks) per 8-row
+//     group, 128-byte swizzle applied on absolute address bits, and the descriptor start address moves by c * 128 bytes
+//     with SBO = 12 rows (scripts/ubench/tcgen05_shift_probe.cu pins that this is what the hardware computes).
+//   * float32 accuracy from TF32 tensor cores: x = hi + lo (cvt.rna.tf32), D = A_hi [B_hi | B_lo] + A_lo B_hi -- two MMAs
+//     per K step (N = 64 and N = 32; the A operand is the larger one, so it is read twice, not three times), the two
+//     column halves are added after the TMEM read-back.  Relative RMS error vs float64 ~9e-7 (tolerance 1e-5).
+//   * MMAs are issued by one thread, completion comes back through tcgen05.commit -> mbarrier; the other CTAs of the SM
+//     mix / detect while this CTA's tile is in the tensor pipe.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "common.cuh"
+#include "demod_host.h"
+#include "demod_post.cuh"
+
+namespace ssdr {
+
+namespace {
+
+constexpr int T = SSDR_FIR_TAPS;          // 127
+constexpr int H = T - 1;                  // 126 history samples kept per channel
+constexpr int FR = SSDR_FRAME;            // 512
+constexpr int SPL = kDemodSpl;            // 16
+constexpr int WARPS = 4;                  // channels per CTA step
+constexpr int KCH = 5;                    // K chunks of 32 samples (160 = 128 history + 32)
+constexpr unsigned ROWB = 128;            // one 32-sample block of floats
+constexpr unsigned GROWS = 12;            // rows per mini-stream: 4 history blocks + 8 blocks
+constexpr unsigned GRPB = GROWS * ROWB;   // 1536 bytes = SBO of the A operand
+constexpr unsigned CHB = 4 * GRPB;        // per channel: re octets 0, 1 then im octets 0, 1
+constexpr unsigned A_BYTES = WARPS * CHB; // 24576 per precision part
+constexpr unsigned B_ATOM = 8 * 1024;     // per K chunk: 32 rows of B_hi (4 groups) then 32 rows of B_lo
+constexpr unsigned B_BYTES = KCH * B_ATOM;
+constexpr unsigned SMEM_BYTES = 2 * A_BYTES + B_BYTES + 1024;   // + alignment slack
+constexpr unsigned TMEM_COLS = 64;
+
+__device__ __forceinline__ unsigned swz(unsigned off) { return off ^ (((off >> 7) & 7u) << 4); }   // off from a 1024-aligned base
+__device__ __forceinline__ float tf32_hi(float x) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+
+__device__ __forceinline__ uint64_t desc_sw128(unsigned addr, unsigned sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);                   // start address
+    d |= (uint64_t)1 << 16;                                   // LBO (unused: swizzled K-major)
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;               // SBO: next 8-row group
+    d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                   // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ constexpr unsigned idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(unsigned tmem, uint64_t da, uint64_t db, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct alignas(8) TcShared {
+    unsigned long long bar;
+    unsigned tmem_base;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, const int* __restrict__ quad_fid, int n_quads) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ TcShared sh;
+    const unsigned raw = (unsigned)__cvta_generic_to_shared(smem_raw);
+    unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);          // 1024-aligned: swizzle phase = offset bits
+    unsigned char* sAh = base;
+    unsigned char* sAl = base + A_BYTES;
+    unsigned char* sB = base + 2 * A_BYTES;
+    const unsigned aAh = (unsigned)__cvta_generic_to_shared(sAh), aAl = aAh + A_BYTES, aB = aAh + 2 * A_BYTES;
+    const unsigned barp = (unsigned)__cvta_generic_to_shared(&sh.bar);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barp));
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&sh.tmem_base)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tm = sh.tmem_base;
+    unsigned phase = 0;
+
+    const int nblk = kp.n_samples / FR;
+    const int q0 = (int)((long long)blockIdx.x * n_quads / gridDim.x), q1 = (int)((long long)(blockIdx.x + 1) * n_quads / gridDim.x);
+    const unsigned wch = (unsigned)warp * CHB;              // this warp's channel slot inside A_hi / A_lo
+    int cur_fid = -1;
+
+    auto put = [&](unsigned off, float x) {                 // x -> (hi, lo) at swizzled offset off of both A parts
+        const float hi = tf32_hi(x);
+        *reinterpret_cast<float*>(sAh + off) = hi;
+        *reinterpret_cast<float*>(sAl + off) = x - hi;      // exact; the tensor core keeps its leading 11 bits
+    };
+
+    for (int q = q0; q < q1; ++q) {
+        const int4 q4 = quad_ch[q];
+        const int ch = (warp == 0) ? q4.x : (warp == 1) ? q4.y : (warp == 2) ? q4.z : q4.w;
+        const bool active = ch >= 0;
+        // ---- the quad's filter as a Toeplitz B operand (rebuilt only when the filter changes) ----------------------
+        const int fid = quad_fid[q];
+        if (fid != cur_fid) {                               // CTA-uniform; the previous quad's MMAs have completed
+            cur_fid = fid;
+            const float* taps = kp.taps + (size_t)q4.x * T;
+            for (int e = tid; e < 32 * 160; e += WARPS * 32) {
+                const int n = e / 160, k = e - n * 160, tau = 128 + n - k;
+                const float x = (tau >= 0 && tau < T) ? __ldg(taps + tau) : 0.f, hi = tf32_hi(x);
+                const int c = k >> 5, kk = k & 31;
+                const unsigned off = (unsigned)c * B_ATOM + (unsigned)(n >> 3) * 1024u + (unsigned)(n & 7) * 128u +
+                                     (unsigned)(((kk >> 2) ^ (n & 7)) << 4) + (unsigned)(kk & 3) * 4u;
+                *reinterpret_cast<float*>(sB + off) = hi;
+                *reinterpret_cast<float*>(sB + off + 4096u) = x - hi;
+            }
+        }
+        // ---- per-channel state; FIR history = blocks -4 .. -1 of the re / im mini-streams of octet 0 ------------
+        DemodChan cp = {};
+        DemodState* stp = nullptr;
+        DemodRegs st = {};
+        if (active) {
+            cp = kp.chan[ch];
+            stp = kp.state + ch;
+            demod_regs_load(st, stp, lane);
+#pragma unroll
+            for (int row = 0; row < 4; ++row) {
+                const int idx = 32 * row + lane - 2;        // sample -128 + 32 row + lane; the 126 kept samples start at -126
+                const float2 z = (idx >= 0) ? kp.hist[(size_t)ch * H + idx] : make_float2(0.f, 0.f);
+                const unsigned off = wch + (unsigned)row * ROWB + (unsigned)lane * 4u;
+                put(swz(off), z.x);
+                put(swz(off + 2 * GRPB), z.y);
+            }
+        }
+        for (int b = 0; b < nblk; ++b) {
+            const size_t s0 = active ? (size_t)ch * kp.pitch + (size_t)b * FR : 0;
+            if (active) {
+                // ---- mixer: lane-strided, coalesced; block r of the frame = one 128-byte row, lane = position -----------
+                float2 xin[SPL];
+#pragma unroll
+                for (int r = 0; r < SPL; ++r) xin[r] = demod_ld_iq<FMT>(kp.iq, s0 + lane + 32 * r);
+#pragma unroll
+                for (int r = 0; r < SPL; ++r) {
+                    const int k = lane + 32 * r;
+                    const float2 x = xin[r];
+                    float c, s;
+                    nco(st.ph1 + (unsigned)k * cp.inc1, c, s);
+                    const float2 y = make_float2(x.x * c + x.y * s, x.y * c - x.x * s);      // x exp(-j theta)
+                    const unsigned off = wch + (unsigned)(r >> 3) * GRPB + (unsigned)(4 + (r & 7)) * ROWB + (unsigned)lane * 4u;
+                    put(swz(off), y.x);
+                    put(swz(off + 2 * GRPB), y.y);
+                    if (r >= 4 && r < 8) {                  // blocks 4..7 are also the history of octet 1
+                        const unsigned offh = wch + GRPB + (unsigned)(r - 4) * ROWB + (unsigned)lane * 4u;
+                        put(swz(offh), y.x);
+                        put(swz(offh + 2 * GRPB), y.y);
+                    }
+                }
+            }
+            // generic-proxy writes -> visible to the tensor core (async proxy); order this step's TMEM reads before the MMAs
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) {
+                constexpr unsigned i64 = idesc_tf32(128, 64), i32 = idesc_tf32(128, 32);
+#pragma unroll 1
+                for (int c = 0; c < KCH; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {           // K step of 8 samples = 32 bytes inside the swizzled row
+                        const unsigned oa = (unsigned)c * ROWB + (unsigned)j * 32u, ob = aB + (unsigned)c * B_ATOM + (unsigned)j * 32u;
+                        const uint64_t db = desc_sw128(ob, 1024u);
+                        mma_tf32(tm, desc_sw128(aAh + oa, GRPB), db, i64, (c | j) != 0);       // A_hi [B_hi | B_lo] -> columns 0..63
+                        mma_tf32(tm, desc_sw128(aAl + oa, GRPB), db, i32, 1u);                  // A_lo B_hi -> columns 0..31
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(barp) : "memory");
+            }
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "WAIT_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@!p bra WAIT_%=;\n\t}" ::"r"(barp), "r"(phase) : "memory");
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- read back: lane i < 16 has the real parts of block i, lane 16 + i its imaginary parts ---------------------
+            float v[32];
+            {
+                float w[32];
+                const unsigned taddr = tm + ((unsigned)(warp * 32) << 16);
+                tmem_ld32(taddr, v);
+                tmem_ld32(taddr + 32u, w);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += w[i];
+            }
+            if (active) {
+                // ---- the frame's last four blocks become the history of the next frame (all MMAs have completed) ------------
+                {
+                    const unsigned row = (unsigned)lane >> 3, chunk = (unsigned)lane & 7u;
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        const unsigned src = swz(wch + (unsigned)part * 2 * GRPB + GRPB + (8 + row) * ROWB + chunk * 16u);
+                        const unsigned dst = swz(wch + (unsigned)part * 2 * GRPB + row * ROWB + chunk * 16u);
+                        *reinterpret_cast<float4*>(sAh + dst) = *reinterpret_cast<const float4*>(sAh + src);
+                        *reinterpret_cast<float4*>(sAl + dst) = *reinterpret_cast<const float4*>(sAl + src);
+                    }
+                }
+                // ---- pair exchange: lanes p and p ^ 16 swap the halves they do not keep ------------------------------------
+                float2 acc[SPL];
+                const bool lo16 = lane < 16;
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) {
+                    const float send = lo16 ? v[16 + i] : v[i];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+                    acc[i] = lo16 ? make_float2(v[i], recv) : make_float2(recv, v[16 + i]);
+                }
+                demod_frame_tail<LanesPaired>(acc, cp, kp, ch, b, s0, st);
+            }
+        }
+        if (active) {
+            // ---- store per-channel state: the last 126 mixed samples (hi + lo is exact) --------------------------------
+            __syncwarp();
+            for (int i = lane; i < H; i += 32) {
+                const int m = i + 2;
+                const unsigned off = swz(wch + (unsigned)(m >> 5) * ROWB + (unsigned)(m & 31) * 4u);
+                const unsigned offi = swz(wch + 2 * GRPB + (unsigned)(m >> 5) * ROWB + (unsigned)(m & 31) * 4u);
+                kp.hist[(size_t)ch * H + i] = make_float2(*reinterpret_cast<const float*>(sAh + off) + *reinterpret_cast<const float*>(sAl + off),
+                                                          *reinterpret_cast<const float*>(sAh + offi) + *reinterpret_cast<const float*>(sAl + offi));
+            }
+            demod_regs_store(st, stp, lane);
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(TMEM_COLS));
+}
+
+}  // namespace
+
+int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_quads, cudaStream_t st) {
+    DemodKernelParams kp;
+    kp.iq = a.iq; kp.chan = a.chan; kp.state = a.state; kp.hist = a.hist; kp.taps = a.taps;
+    kp.pcm_f32 = a.pcm_f32; kp.pcm_i16 = a.pcm_i16; kp.rssi = a.rssi;
+    kp.batch = a.batch; kp.n_samples = a.n_samples; kp.pitch = a.pitch ? a.pitch : a.n_samples;
+    for (int s = 0; s < 5; ++s) kp.am_pow16[s] = a.am_pow16[s];
+    auto kern = (a.iq_format == SSDR_IQ_CF32) ? demod_tc_kernel<SSDR_IQ_CF32> : demod_tc_kernel<SSDR_IQ_S16BE>;
+    SSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    int occ = 0;
+    SSDR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, SMEM_BYTES));
+    if (occ < 1) occ = 1;
+    int grid = sm_count() * occ;
+    if (grid > n_quads) grid = n_quads;
+    if (grid < 1) return SSDR_OK;
+    kern<<<grid, WARPS * 32, SMEM_BYTES, st>>>(kp, quad_ch, quad_fid, n_quads);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+}  // namespace ssdr

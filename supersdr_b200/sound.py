@@ -64,17 +64,25 @@ def demod_params(mode="usb", lc=None, hc=None, f_off=0.0, on=True, hang=False, t
 class DemodBank:
     """B channels of IQ @12 kHz -> PCM @12 kHz (float32 + int16) and per-frame RSSI."""
 
-    def __init__(self, batch=1, max_samples=_lib.FRAME * 64, device=None):
+    ENGINES = {"ffma": _lib.SSDR_DEMOD_ENGINE_FFMA, "tcgen05": _lib.SSDR_DEMOD_ENGINE_TCGEN05}
+
+    def __init__(self, batch=1, max_samples=_lib.FRAME * 64, device=None, engine=None):
         _lib.init(device)
         self.batch, self.max_samples = int(batch), int(max_samples)
         h = C.c_void_p()
         check(lib.ssdr_demod_create(C.byref(h), self.batch, self.max_samples))
         self._h = h
+        if engine is not None:
+            self.set_engine(engine)
         self.set_params(0, [demod_params()] * self.batch)
 
     def set_params(self, first, params):
         arr = (_lib.DemodParams * len(params))(*params)
         check(lib.ssdr_demod_set(self._h, int(first), len(params), arr))
+
+    def set_engine(self, engine):
+        """FIR engine of the fused kernel: "ffma" (fp32 pipe) or "tcgen05" (tensor cores); switchable between calls."""
+        check(lib.ssdr_demod_set_engine(self._h, self.ENGINES[engine] if isinstance(engine, str) else int(engine)))
 
     def set_all(self, **kw):
         self.set_params(0, [demod_params(**kw)] * self.batch)

@@ -12,13 +12,26 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 RMS_TOL = 1e-5          # north_star: float32 demod output within 1e-5 RMS of the numpy path
 
 
+@pytest.fixture(params=["ffma", "tcgen05"])
+def engine(request):
+    """Every demodulator test runs on both FIR engines of the fused kernel (ssdr_demod_set_engine): the handle reads its
+    default engine from SSDR_DEMOD_ENGINE when it is created."""
+    old = os.environ.get("SSDR_DEMOD_ENGINE")
+    os.environ["SSDR_DEMOD_ENGINE"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["SSDR_DEMOD_ENGINE"]
+    else:
+        os.environ["SSDR_DEMOD_ENGINE"] = old
+
+
 def _rel_rms(a, b):
     return np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-30)
 
 
 @pytest.mark.parametrize("mode", ["usb", "lsb", "cw", "am", "nbfm"])
 @pytest.mark.parametrize("hang,on,slope", [(False, True, 0), (True, True, 6), (False, False, 0)])
-def test_demod_vs_float64_oracle(ssdr, mode, hang, on, slope):
+def test_demod_vs_float64_oracle(ssdr, engine, mode, hang, on, slope):
     B, n = 6, 512 * 12
     kw = dict(mode=mode, hang=hang, on=on, slope=slope, decay=1000 if mode == "cw" else 4000)
     bank = ssdr.DemodBank(B, n)
@@ -37,7 +50,7 @@ def test_demod_vs_float64_oracle(ssdr, mode, hang, on, slope):
     bank.close()
 
 
-def test_demod_golden_fixture(ssdr):
+def test_demod_golden_fixture(ssdr, engine):
     g = np.load(os.path.join(GOLD, "tier_u_demod.npz"))
     for mode in tier_u.MODES:
         bank = ssdr.DemodBank(1, 4096)
@@ -48,7 +61,7 @@ def test_demod_golden_fixture(ssdr):
         bank.close()
 
 
-def test_demod_mixed_modes_and_chunking(ssdr):
+def test_demod_mixed_modes_and_chunking(ssdr, engine):
     """Config 4 in miniature: modes by ch % 5, per-channel tuning offsets; and the result does not
     depend on how the stream is cut into calls (per-frame state is bit-reproducible)."""
     modes = ["am", "lsb", "usb", "cw", "nbfm"]
@@ -70,7 +83,7 @@ def test_demod_mixed_modes_and_chunking(ssdr):
     one.close(); cut.close()
 
 
-def test_demod_host_pipeline_time_blocks(ssdr):
+def test_demod_host_pipeline_time_blocks(ssdr, engine):
     """A call large enough to be cut into several time blocks by the host pipeline (ssdr_demod_process: > 64 MiB of
     input) gives, per channel, exactly what one small call gives, into caller-owned output buffers."""
     modes = ["usb", "am", "nbfm", "cw"]
@@ -96,7 +109,7 @@ def test_demod_host_pipeline_time_blocks(ssdr):
     big.close(); small.close()
 
 
-def test_demod_wire_format_and_sideband_rejection(ssdr):
+def test_demod_wire_format_and_sideband_rejection(ssdr, engine):
     n = 512 * 16
     iq = tier_u.synth_demod_iq("usb", n, seed=4)
     iq = (np.rint(iq.real) + 1j * np.rint(iq.imag)).astype(np.complex64)
@@ -115,7 +128,7 @@ def test_demod_wire_format_and_sideband_rejection(ssdr):
     bank.close()
 
 
-def test_demod_silence_and_full_scale(ssdr):
+def test_demod_silence_and_full_scale(ssdr, engine):
     bank = ssdr.DemodBank(2, 1024)
     x = np.zeros((2, 1024), np.complex64)
     x[1] = 32767 * np.exp(2j * np.pi * 1000 * np.arange(1024) / 12000)
@@ -125,6 +138,28 @@ def test_demod_silence_and_full_scale(ssdr):
     assert _rel_rms(r["pcm_f32"][1], ref) < RMS_TOL and abs(r["rssi"][1, -1] - rr[-1]) < 1e-3
     with pytest.raises(ssdr.SsdrError):
         bank.process(np.zeros((2, 500), np.complex64))       # not a multiple of 512
+    bank.close()
+
+
+def test_demod_engines_agree_and_interleave(ssdr):
+    """The two engines share the per-channel state format: a stream processed alternately by one and the other stays
+    within the tolerance of the float64 oracle; channels with distinct filters (quads of one) and a batch that is not a
+    multiple of four are covered."""
+    modes = ["usb", "am", "cw", "nbfm", "lsb", "usb", "am"]
+    B, n = len(modes), 512 * 8
+    params = [ssdr.demod_params(m, hc=2700.0 + 100 * b) if m == "usb" else ssdr.demod_params(m) for b, m in enumerate(modes)]
+    iq = np.stack([tier_u.synth_demod_iq(m, n, seed=40 + b) for b, m in enumerate(modes)])
+    bank = ssdr.DemodBank(B, n)
+    bank.set_params(0, params)
+    parts = []
+    for i, eng in enumerate(["tcgen05", "ffma", "tcgen05", "tcgen05"]):
+        bank.set_engine(eng)
+        parts.append(bank.process(iq[:, i * 1024:(i + 1) * 1024].copy())["pcm_f32"])
+    got = np.concatenate(parts, 1)
+    for b, m in enumerate(modes):
+        p = tier_u.DemodParams(m, hc=2700.0 + 100 * b) if m == "usb" else tier_u.DemodParams(m)
+        ref, _ = tier_u.demod(iq[b], p, tier_u.DemodState())
+        assert _rel_rms(got[b], ref) < RMS_TOL, (b, m)
     bank.close()
 
 
