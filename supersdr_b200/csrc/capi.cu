@@ -103,7 +103,7 @@ struct ssdr_demod {
     int engine = SSDR_DEMOD_ENGINE_FFMA;
     std::vector<float> h_taps;     // host mirror of d_taps, [batch][127]
     bool quads_dirty = true;
-    int n_quads = 0;
+    int n_quads = 0;               // rounds of demod_tc_tiles() quads
     int4* d_quad_ch = nullptr;
     int* d_quad_fid = nullptr;
 };
@@ -591,16 +591,21 @@ static int demod_build_quads(ssdr_demod_t h) {
     });
     std::vector<int4> qc;
     std::vector<int> qf;
+    const size_t tiles = (size_t)demod_tc_tiles();
     int fid = -1, fill = 4;
     for (int i = 0; i < B; ++i) {
         const int ch = order[(size_t)i];
         const bool same = i > 0 && !std::memcmp(t + (size_t)ch * SSDR_FIR_TAPS, t + (size_t)order[(size_t)i - 1] * SSDR_FIR_TAPS, tb);
-        if (!same) { ++fid; fill = 4; }
+        if (!same) {                                         // a new filter starts a new round
+            while (qc.size() % tiles) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(fid); }
+            ++fid; fill = 4;
+        }
         if (fill == 4) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(fid); fill = 0; }
         int4& q = qc.back();
         (fill == 0 ? q.x : fill == 1 ? q.y : fill == 2 ? q.z : q.w) = ch;
         ++fill;
     }
+    while (qc.size() % tiles) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(fid); }
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid);
     h->d_quad_ch = nullptr; h->d_quad_fid = nullptr;
@@ -609,7 +614,7 @@ static int demod_build_quads(ssdr_demod_t h) {
     if ((rc = dev_alloc(&h->d_quad_fid, qf.size()))) return rc;
     SSDR_CUDA(cudaMemcpy(h->d_quad_ch, qc.data(), sizeof(int4) * qc.size(), cudaMemcpyHostToDevice));
     SSDR_CUDA(cudaMemcpy(h->d_quad_fid, qf.data(), sizeof(int) * qf.size(), cudaMemcpyHostToDevice));
-    h->n_quads = (int)qc.size();
+    h->n_quads = (int)(qc.size() / tiles);                  // rounds
     h->quads_dirty = false;
     return SSDR_OK;
 }

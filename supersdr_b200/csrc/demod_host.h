@@ -63,8 +63,10 @@ struct DemodLaunch {
 
 int demod_launch(const DemodLaunch& a, cudaStream_t st);
 
-// tcgen05 engine (demod_tc_kernels.cu).  quad_ch[q] = four channels that share one filter (slot 0 valid, unused slots -1),
-// quad_fid[q] = id of that filter; consecutive quads of one filter are adjacent so a CTA rebuilds its B operand rarely.
-int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_quads, cudaStream_t st);
+// tcgen05 engine (demod_tc_kernels.cu).  quad_ch[q] = four channels that share one filter (slots filled in order, unused
+// slots -1), quad_fid[q] = id of that filter.  A CTA takes demod_tc_tiles() consecutive quads per round on one B operand:
+// the quads of a round share the filter (a round is padded with empty quads), rounds of one filter are adjacent.
+int demod_tc_tiles();
+int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_rounds, cudaStream_t st);
 
 }  // namespace ssdr

@@ -6,8 +6,10 @@
 // Formulation.  Cut the mixed signal z of a channel into 32-sample blocks.  The 32 FIR outputs of block i are
 //     y[32 i + n] = sum_k Z_i[k] T[k][n],   Z_i[k] = z[32 (i - 4) + k],  k < 160,   T[k][n] = h[128 + n - k]  (0 outside 0..126)
 // i.e. D[128 x 32] = A[128 x 160] B[160 x 32] with one ROW per (block, re | im) and the taps as a Toeplitz B operand.
-// A CTA step covers one 512-sample frame of FOUR channels that share a filter (host-side grouping): 4 channels x
+// A tile step covers one 512-sample frame of FOUR channels that share a filter (host-side grouping): 4 channels x
 // {re, im} x 16 blocks = 128 rows = one M = 128 tile, and warp w reads back exactly its own channel (TMEM lanes 32 w ..).
+// A CTA runs TILES such tiles side by side (4 warps each, own operand buffer, own TMEM columns, own barriers) on one
+// shared B operand: the mixer / detector / AGC code is latency-bound, so the SM needs the 12 warps.
 //
 //   * One copy of the signal serves all five K chunks: K chunk c of row i is block i - 4 + c, i.e. the same array read
 //     c rows further up.  The operand is stored as "mini-streams" of 12 rows (4 history blocks + 8 blocks) per 8-row
@@ -16,8 +18,8 @@
 //   * float32 accuracy from TF32 tensor cores: x = hi + lo (cvt.rna.tf32), D = A_hi [B_hi | B_lo] + A_lo B_hi -- two MMAs
 //     per K step (N = 64 and N = 32; the A operand is the larger one, so it is read twice, not three times), the two
 //     column halves are added after the TMEM read-back.  Relative RMS error vs float64 ~9e-7 (tolerance 1e-5).
-//   * MMAs are issued by one thread, completion comes back through tcgen05.commit -> mbarrier; the other CTAs of the SM
-//     mix / detect while this CTA's tile is in the tensor pipe.
+//   * MMAs are issued by one thread per tile, completion comes back through tcgen05.commit -> mbarrier; the other tiles
+//     of the CTA mix / detect while this tile is in the tensor pipe.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -34,7 +36,8 @@ constexpr int T = SSDR_FIR_TAPS;          // 127
 constexpr int H = T - 1;                  // 126 history samples kept per channel
 constexpr int FR = SSDR_FRAME;            // 512
 constexpr int SPL = kDemodSpl;            // 16
-constexpr int WARPS = 4;                  // channels per CTA step
+constexpr int WARPS = 4;                  // channels (warps) per tile
+constexpr int TILES = 3;                  // tiles per CTA
 constexpr int KCH = 5;                    // K chunks of 32 samples (160 = 128 history + 32)
 constexpr unsigned ROWB = 128;            // one 32-sample block of floats
 constexpr unsigned GROWS = 12;            // rows per mini-stream: 4 history blocks + 8 blocks
@@ -43,8 +46,8 @@ constexpr unsigned CHB = 4 * GRPB;        // per channel: re octets 0, 1 then im
 constexpr unsigned A_BYTES = WARPS * CHB; // 24576 per precision part
 constexpr unsigned B_ATOM = 8 * 1024;     // per K chunk: 32 rows of B_hi (4 groups) then 32 rows of B_lo
 constexpr unsigned B_BYTES = KCH * B_ATOM;
-constexpr unsigned SMEM_BYTES = 2 * A_BYTES + B_BYTES + 1024;   // + alignment slack
-constexpr unsigned TMEM_COLS = 64;
+constexpr unsigned SMEM_BYTES = TILES * 2 * A_BYTES + B_BYTES + 1024;   // + alignment slack
+constexpr unsigned TMEM_COLS = 256;       // 64 columns per tile, allocation is a power of two
 
 __device__ __forceinline__ unsigned swz(unsigned off) { return off ^ (((off >> 7) & 7u) << 4); }   // off from a 1024-aligned base
 __device__ __forceinline__ float tf32_hi(float x) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
@@ -81,37 +84,38 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
 }
 
 struct alignas(8) TcShared {
-    unsigned long long bar;
+    unsigned long long bar[TILES];
     unsigned tmem_base;
 };
 
 template <int FMT>
-__global__ void __launch_bounds__(WARPS * 32, 2)
-demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, const int* __restrict__ quad_fid, int n_quads) {
+__global__ void __launch_bounds__(TILES * WARPS * 32, 1)
+demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, const int* __restrict__ quad_fid, int n_rounds) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ TcShared sh;
     const unsigned raw = (unsigned)__cvta_generic_to_shared(smem_raw);
     unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);          // 1024-aligned: swizzle phase = offset bits
-    unsigned char* sAh = base;
-    unsigned char* sAl = base + A_BYTES;
-    unsigned char* sB = base + 2 * A_BYTES;
-    const unsigned aAh = (unsigned)__cvta_generic_to_shared(sAh), aAl = aAh + A_BYTES, aB = aAh + 2 * A_BYTES;
-    const unsigned barp = (unsigned)__cvta_generic_to_shared(&sh.bar);
+    const int tid = threadIdx.x, lane = tid & 31, tile = tid >> 7, warp = (tid >> 5) & 3;     // warp = TMEM lane quarter
+    unsigned char* sB = base;
+    unsigned char* sAh = base + B_BYTES + (unsigned)tile * 2 * A_BYTES;
+    unsigned char* sAl = sAh + A_BYTES;
+    const unsigned aB = (unsigned)__cvta_generic_to_shared(sB), aAh = aB + B_BYTES + (unsigned)tile * 2 * A_BYTES, aAl = aAh + A_BYTES;
+    const unsigned barp = (unsigned)__cvta_generic_to_shared(&sh.bar[tile]);
+    const bool issuer = (tid & 127) == 0;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barp));
-    if (warp == 0) {
+    if (issuer) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barp));
+    if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&sh.tmem_base)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tm = sh.tmem_base;
+    const unsigned tm = sh.tmem_base + (unsigned)tile * 64u;
     unsigned phase = 0;
 
     const int nblk = kp.n_samples / FR;
-    const int q0 = (int)((long long)blockIdx.x * n_quads / gridDim.x), q1 = (int)((long long)(blockIdx.x + 1) * n_quads / gridDim.x);
+    const int r0 = (int)((long long)blockIdx.x * n_rounds / gridDim.x), r1 = (int)((long long)(blockIdx.x + 1) * n_rounds / gridDim.x);
     const unsigned wch = (unsigned)warp * CHB;              // this warp's channel slot inside A_hi / A_lo
     int cur_fid = -1;
 
@@ -121,16 +125,13 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
         *reinterpret_cast<float*>(sAl + off) = x - hi;      // exact; the tensor core keeps its leading 11 bits
     };
 
-    for (int q = q0; q < q1; ++q) {
-        const int4 q4 = quad_ch[q];
-        const int ch = (warp == 0) ? q4.x : (warp == 1) ? q4.y : (warp == 2) ? q4.z : q4.w;
-        const bool active = ch >= 0;
-        // ---- the quad's filter as a Toeplitz B operand (rebuilt only when the filter changes) ----------------------
-        const int fid = quad_fid[q];
-        if (fid != cur_fid) {                               // CTA-uniform; the previous quad's MMAs have completed
+    for (int rd = r0; rd < r1; ++rd) {
+        // ---- the round's filter as a Toeplitz B operand (rebuilt only when the filter changes) ---------------------
+        const int fid = quad_fid[rd * TILES];
+        if (fid != cur_fid) {                               // CTA-uniform; every tile has finished the previous round
             cur_fid = fid;
-            const float* taps = kp.taps + (size_t)q4.x * T;
-            for (int e = tid; e < 32 * 160; e += WARPS * 32) {
+            const float* taps = kp.taps + (size_t)quad_ch[rd * TILES].x * T;
+            for (int e = tid; e < 32 * 160; e += TILES * WARPS * 32) {
                 const int n = e / 160, k = e - n * 160, tau = 128 + n - k;
                 const float x = (tau >= 0 && tau < T) ? __ldg(taps + tau) : 0.f, hi = tf32_hi(x);
                 const int c = k >> 5, kk = k & 31;
@@ -139,7 +140,12 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 *reinterpret_cast<float*>(sB + off) = hi;
                 *reinterpret_cast<float*>(sB + off + 4096u) = x - hi;
             }
+            __syncthreads();                                // the per-step fence below publishes B to the tensor core
         }
+        const int4 q4 = quad_ch[rd * TILES + tile];
+        const int ch = (warp == 0) ? q4.x : (warp == 1) ? q4.y : (warp == 2) ? q4.z : q4.w;
+        const bool active = ch >= 0;
+        const bool tile_active = q4.x >= 0;                 // slot 0 of a quad is filled first
         // ---- per-channel state; FIR history = blocks -4 .. -1 of the re / im mini-streams of octet 0 ------------
         DemodChan cp = {};
         DemodState* stp = nullptr;
@@ -157,7 +163,7 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 put(swz(off + 2 * GRPB), z.y);
             }
         }
-        for (int b = 0; b < nblk; ++b) {
+        for (int b = 0; tile_active && b < nblk; ++b) {
             const size_t s0 = active ? (size_t)ch * kp.pitch + (size_t)b * FR : 0;
             if (active) {
                 // ---- mixer: lane-strided, coalesced; block r of the frame = one 128-byte row, lane = position -----------
@@ -184,9 +190,9 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             // generic-proxy writes -> visible to the tensor core (async proxy); order this step's TMEM reads before the MMAs
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
+            asm volatile("bar.sync %0, 128;" ::"r"(tile + 1) : "memory");        // the tile's four warps
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (tid == 0) {
+            if (issuer) {
                 constexpr unsigned i64 = idesc_tf32(128, 64), i32 = idesc_tf32(128, 32);
 #pragma unroll 1
                 for (int c = 0; c < KCH; ++c) {
@@ -254,16 +260,18 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             }
             demod_regs_store(st, stp, lane);
         }
-        __syncwarp();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                    // tiles re-converge: B may change, TMEM reads are complete
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(TMEM_COLS));
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "n"(TMEM_COLS));
 }
 
 }  // namespace
 
-int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_quads, cudaStream_t st) {
+int demod_tc_tiles() { return TILES; }
+
+int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_rounds, cudaStream_t st) {
     DemodKernelParams kp;
     kp.iq = a.iq; kp.chan = a.chan; kp.state = a.state; kp.hist = a.hist; kp.taps = a.taps;
     kp.pcm_f32 = a.pcm_f32; kp.pcm_i16 = a.pcm_i16; kp.rssi = a.rssi;
@@ -271,13 +279,10 @@ int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_f
     for (int s = 0; s < 5; ++s) kp.am_pow16[s] = a.am_pow16[s];
     auto kern = (a.iq_format == SSDR_IQ_CF32) ? demod_tc_kernel<SSDR_IQ_CF32> : demod_tc_kernel<SSDR_IQ_S16BE>;
     SSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    int occ = 0;
-    SSDR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, SMEM_BYTES));
-    if (occ < 1) occ = 1;
-    int grid = sm_count() * occ;
-    if (grid > n_quads) grid = n_quads;
+    int grid = sm_count();                                  // one CTA per SM (shared memory), TILES x 4 warps
+    if (grid > n_rounds) grid = n_rounds;
     if (grid < 1) return SSDR_OK;
-    kern<<<grid, WARPS * 32, SMEM_BYTES, st>>>(kp, quad_ch, quad_fid, n_quads);
+    kern<<<grid, TILES * WARPS * 32, SMEM_BYTES, st>>>(kp, quad_ch, quad_fid, n_rounds);
     count_launch();
     SSDR_CUDA(cudaGetLastError());
     return SSDR_OK;
