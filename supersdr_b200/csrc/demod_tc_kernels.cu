@@ -18,8 +18,9 @@
 //   * float32 accuracy from TF32 tensor cores: x = hi + lo (cvt.rna.tf32), D = A_hi [B_hi | B_lo] + A_lo B_hi -- two MMAs
 //     per K step (N = 64 and N = 32; the A operand is the larger one, so it is read twice, not three times), the two
 //     column halves are added after the TMEM read-back.  Relative RMS error vs float64 ~9e-7 (tolerance 1e-5).
-//   * MMAs are issued by one thread per tile, completion comes back through tcgen05.commit -> mbarrier; the other tiles
-//     of the CTA mix / detect while this tile is in the tensor pipe.
+//   * MMAs are issued by one thread per tile, completion comes back through tcgen05.commit -> mbarrier.  Two TMEM
+//     accumulators per tile: while the MMAs of frame b run, the tile's warps run the back end of frame b - 1, and the
+//     other tiles of the CTA mix / detect as well.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -47,7 +48,7 @@ constexpr unsigned A_BYTES = WARPS * CHB; // 24576 per precision part
 constexpr unsigned B_ATOM = 8 * 1024;     // per K chunk: 32 rows of B_hi (4 groups) then 32 rows of B_lo
 constexpr unsigned B_BYTES = KCH * B_ATOM;
 constexpr unsigned SMEM_BYTES = TILES * 2 * A_BYTES + B_BYTES + 1024;   // + alignment slack
-constexpr unsigned TMEM_COLS = 256;       // 64 columns per tile, allocation is a power of two
+constexpr unsigned TMEM_COLS = 512;       // two accumulators of 64 columns per tile (3 x 128), allocation is a power of two
 
 __device__ __forceinline__ unsigned swz(unsigned off) { return off ^ (((off >> 7) & 7u) << 4); }   // off from a 1024-aligned base
 __device__ __forceinline__ float tf32_hi(float x) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
@@ -111,7 +112,7 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tm = sh.tmem_base + (unsigned)tile * 64u;
+    const unsigned tm = sh.tmem_base + (unsigned)tile * 128u;
     unsigned phase = 0;
 
     const int nblk = kp.n_samples / FR;
@@ -163,49 +164,85 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 put(swz(off + 2 * GRPB), z.y);
             }
         }
-        for (int b = 0; tile_active && b < nblk; ++b) {
-            const size_t s0 = active ? (size_t)ch * kp.pitch + (size_t)b * FR : 0;
-            if (active) {
-                // ---- mixer: lane-strided, coalesced; block r of the frame = one 128-byte row, lane = position -----------
-                float2 xin[SPL];
+        // ---- frame pipeline of the tile: mix(b) -> MMAs(b) in flight while the back end of frame b - 1 runs (its
+        // accumulator is the other TMEM buffer) -> wait -> history rows -> mix(b + 1)
+        unsigned ph1_mix = st.ph1;                          // the back end advances st.ph1 one frame later than the mixer
+        auto mix = [&](int b) {
+            // lane-strided, coalesced loads; block r of the frame = one 128-byte row, lane = position in the row
+            const size_t s0 = (size_t)ch * kp.pitch + (size_t)b * FR;
+            float2 xin[SPL];
 #pragma unroll
-                for (int r = 0; r < SPL; ++r) xin[r] = demod_ld_iq<FMT>(kp.iq, s0 + lane + 32 * r);
+            for (int r = 0; r < SPL; ++r) xin[r] = demod_ld_iq<FMT>(kp.iq, s0 + lane + 32 * r);
+            if (b + 1 < nblk) {                             // next frame -> L2 (one 128-byte line per lane)
+                const char* nx = static_cast<const char*>(kp.iq) + (s0 + FR) * (FMT == SSDR_IQ_CF32 ? 8 : 4) + lane * 128;
+                if (FMT == SSDR_IQ_CF32 || lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+            }
 #pragma unroll
-                for (int r = 0; r < SPL; ++r) {
-                    const int k = lane + 32 * r;
-                    const float2 x = xin[r];
-                    float c, s;
-                    nco(st.ph1 + (unsigned)k * cp.inc1, c, s);
-                    const float2 y = make_float2(x.x * c + x.y * s, x.y * c - x.x * s);      // x exp(-j theta)
-                    const unsigned off = wch + (unsigned)(r >> 3) * GRPB + (unsigned)(4 + (r & 7)) * ROWB + (unsigned)lane * 4u;
-                    put(swz(off), y.x);
-                    put(swz(off + 2 * GRPB), y.y);
-                    if (r >= 4 && r < 8) {                  // blocks 4..7 are also the history of octet 1
-                        const unsigned offh = wch + GRPB + (unsigned)(r - 4) * ROWB + (unsigned)lane * 4u;
-                        put(swz(offh), y.x);
-                        put(swz(offh + 2 * GRPB), y.y);
-                    }
+            for (int r = 0; r < SPL; ++r) {
+                const int k = lane + 32 * r;
+                const float2 x = xin[r];
+                float c, s;
+                nco(ph1_mix + (unsigned)k * cp.inc1, c, s);
+                const float2 y = make_float2(x.x * c + x.y * s, x.y * c - x.x * s);      // x exp(-j theta)
+                const unsigned off = wch + (unsigned)(r >> 3) * GRPB + (unsigned)(4 + (r & 7)) * ROWB + (unsigned)lane * 4u;
+                put(swz(off), y.x);
+                put(swz(off + 2 * GRPB), y.y);
+                if (r >= 4 && r < 8) {                      // blocks 4..7 are also the history of octet 1
+                    const unsigned offh = wch + GRPB + (unsigned)(r - 4) * ROWB + (unsigned)lane * 4u;
+                    put(swz(offh), y.x);
+                    put(swz(offh + 2 * GRPB), y.y);
                 }
             }
-            // generic-proxy writes -> visible to the tensor core (async proxy); order this step's TMEM reads before the MMAs
+            ph1_mix += (unsigned)FR * cp.inc1;
+        };
+        auto back_end = [&](int b) {
+            // read back: lane i < 16 has the real parts of block i, lane 16 + i its imaginary parts; every warp of the tile
+            // takes part in the (warp-collective) TMEM loads
+            float v[32];
+            {
+                float w[32];
+                const unsigned taddr = tm + (unsigned)(b & 1) * 64u + ((unsigned)(warp * 32) << 16);
+                tmem_ld32(taddr, v);
+                tmem_ld32(taddr + 32u, w);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += w[i];
+            }
+            if (!active) return;
+            // pair exchange: lanes p and p ^ 16 swap the halves they do not keep
+            float2 acc[SPL];
+            const bool lo16 = lane < 16;
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+                const float send = lo16 ? v[16 + i] : v[i];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+                acc[i] = lo16 ? make_float2(v[i], recv) : make_float2(recv, v[16 + i]);
+            }
+            demod_frame_tail<LanesPaired>(acc, cp, kp, ch, b, (size_t)ch * kp.pitch + (size_t)b * FR, st);
+        };
+        if (tile_active && active) mix(0);
+        for (int b = 0; tile_active && b < nblk; ++b) {
+            // generic-proxy writes -> visible to the tensor core (async proxy); order earlier TMEM reads before the MMAs
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync %0, 128;" ::"r"(tile + 1) : "memory");        // the tile's four warps
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (issuer) {
                 constexpr unsigned i64 = idesc_tf32(128, 64), i32 = idesc_tf32(128, 32);
+                const unsigned td = tm + (unsigned)(b & 1) * 64u;
 #pragma unroll 1
                 for (int c = 0; c < KCH; ++c) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {           // K step of 8 samples = 32 bytes inside the swizzled row
                         const unsigned oa = (unsigned)c * ROWB + (unsigned)j * 32u, ob = aB + (unsigned)c * B_ATOM + (unsigned)j * 32u;
                         const uint64_t db = desc_sw128(ob, 1024u);
-                        mma_tf32(tm, desc_sw128(aAh + oa, GRPB), db, i64, (c | j) != 0);       // A_hi [B_hi | B_lo] -> columns 0..63
-                        mma_tf32(tm, desc_sw128(aAl + oa, GRPB), db, i32, 1u);                  // A_lo B_hi -> columns 0..31
+                        mma_tf32(td, desc_sw128(aAh + oa, GRPB), db, i64, (c | j) != 0);       // A_hi [B_hi | B_lo] -> columns 0..63
+                        mma_tf32(td, desc_sw128(aAl + oa, GRPB), db, i32, 1u);                  // A_lo B_hi -> columns 0..31
                     }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(barp) : "memory");
             }
+            if (b > 0) back_end(b - 1);                     // overlaps the MMAs of frame b
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
                 "WAIT_%=:\n\t"
@@ -213,41 +250,21 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 "@!p bra WAIT_%=;\n\t}" ::"r"(barp), "r"(phase) : "memory");
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // ---- read back: lane i < 16 has the real parts of block i, lane 16 + i its imaginary parts ---------------------
-            float v[32];
-            {
-                float w[32];
-                const unsigned taddr = tm + ((unsigned)(warp * 32) << 16);
-                tmem_ld32(taddr, v);
-                tmem_ld32(taddr + 32u, w);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += w[i];
-            }
             if (active) {
-                // ---- the frame's last four blocks become the history of the next frame (all MMAs have completed) ------------
-                {
-                    const unsigned row = (unsigned)lane >> 3, chunk = (unsigned)lane & 7u;
+                // the frame's last four blocks become the history of the next frame (the MMAs of frame b have completed)
+                const unsigned row = (unsigned)lane >> 3, chunk = (unsigned)lane & 7u;
 #pragma unroll
-                    for (int part = 0; part < 2; ++part) {
-                        const unsigned src = swz(wch + (unsigned)part * 2 * GRPB + GRPB + (8 + row) * ROWB + chunk * 16u);
-                        const unsigned dst = swz(wch + (unsigned)part * 2 * GRPB + row * ROWB + chunk * 16u);
-                        *reinterpret_cast<float4*>(sAh + dst) = *reinterpret_cast<const float4*>(sAh + src);
-                        *reinterpret_cast<float4*>(sAl + dst) = *reinterpret_cast<const float4*>(sAl + src);
-                    }
+                for (int part = 0; part < 2; ++part) {
+                    const unsigned src = swz(wch + (unsigned)part * 2 * GRPB + GRPB + (8 + row) * ROWB + chunk * 16u);
+                    const unsigned dst = swz(wch + (unsigned)part * 2 * GRPB + row * ROWB + chunk * 16u);
+                    *reinterpret_cast<float4*>(sAh + dst) = *reinterpret_cast<const float4*>(sAh + src);
+                    *reinterpret_cast<float4*>(sAl + dst) = *reinterpret_cast<const float4*>(sAl + src);
                 }
-                // ---- pair exchange: lanes p and p ^ 16 swap the halves they do not keep ------------------------------------
-                float2 acc[SPL];
-                const bool lo16 = lane < 16;
-#pragma unroll
-                for (int i = 0; i < SPL; ++i) {
-                    const float send = lo16 ? v[16 + i] : v[i];
-                    const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-                    acc[i] = lo16 ? make_float2(v[i], recv) : make_float2(recv, v[16 + i]);
-                }
-                demod_frame_tail<LanesPaired>(acc, cp, kp, ch, b, s0, st);
+                __syncwarp();
+                if (b + 1 < nblk) mix(b + 1);
             }
         }
+        if (tile_active) back_end(nblk - 1);
         if (active) {
             // ---- store per-channel state: the last 126 mixed samples (hi + lo is exact) --------------------------------
             __syncwarp();
