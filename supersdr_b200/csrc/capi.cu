@@ -102,10 +102,12 @@ struct ssdr_demod {
     // FIR engine (ssdr_demod_set_engine) and, for the tcgen05 engine, the channels grouped in quads that share a filter
     int engine = SSDR_DEMOD_ENGINE_FFMA;
     std::vector<float> h_taps;     // host mirror of d_taps, [batch][127]
+    std::vector<int> h_work;       // per channel: detector / AGC variant (channels of one quad should cost the same)
     bool quads_dirty = true;
     int n_quads = 0;               // rounds of demod_tc_tiles() quads
     int4* d_quad_ch = nullptr;
     int* d_quad_fid = nullptr;
+    int* d_round_ctr = nullptr;    // work counter of the tcgen05 kernel (dynamic round scheduling)
 };
 
 struct ssdr_interp {
@@ -499,6 +501,7 @@ int ssdr_demod_create(ssdr_demod_t* out, int batch, int max_samples) {
     cudaMemset(h->d_chan, 0, sizeof(DemodChan) * (size_t)batch);
     cudaMemset(h->d_taps, 0, sizeof(float) * (size_t)batch * SSDR_FIR_TAPS);
     h->h_taps.assign((size_t)batch * SSDR_FIR_TAPS, 0.0f);
+    h->h_work.assign((size_t)batch, 0);
     if (const char* e = std::getenv("SSDR_DEMOD_ENGINE")) {      // developer override of the default engine
         if (!std::strcmp(e, "tcgen05")) h->engine = SSDR_DEMOD_ENGINE_TCGEN05;
         else if (!std::strcmp(e, "ffma")) h->engine = SSDR_DEMOD_ENGINE_FFMA;
@@ -515,7 +518,7 @@ int ssdr_demod_destroy(ssdr_demod_t h) {
     if (h->copy_out) cudaStreamSynchronize(h->copy_out);
     cudaFree(h->d_chan); cudaFree(h->d_state); cudaFree(h->d_hist); cudaFree(h->d_taps);
     cudaFree(h->d_in); cudaFree(h->d_f32); cudaFree(h->d_i16); cudaFree(h->d_rssi);
-    cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid);
+    cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid); cudaFree(h->d_round_ctr);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->ev_copied) cudaEventDestroy(h->ev_copied);
@@ -566,6 +569,7 @@ int ssdr_demod_set(ssdr_demod_t h, int first, int count, const ssdr_demod_params
     SSDR_CUDA(cudaMemcpy(h->d_chan + first, chan.data(), sizeof(DemodChan) * (size_t)count, cudaMemcpyHostToDevice));
     SSDR_CUDA(cudaMemcpy(h->d_taps + (size_t)first * SSDR_FIR_TAPS, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice));
     std::memcpy(h->h_taps.data() + (size_t)first * SSDR_FIR_TAPS, taps.data(), sizeof(float) * taps.size());
+    for (int i = 0; i < count; ++i) h->h_work[(size_t)(first + i)] = chan[(size_t)i].mode * 4 + chan[(size_t)i].agc_on * 2 + chan[(size_t)i].agc_hang;
     h->quads_dirty = true;
     return SSDR_OK;
 }
@@ -586,8 +590,11 @@ static int demod_build_quads(ssdr_demod_t h) {
     std::vector<int> order((size_t)B);
     for (int i = 0; i < B; ++i) order[(size_t)i] = i;
     const float* t = h->h_taps.data();
+    // by filter, then by detector / AGC variant: the four warps of a tile advance in lock step, so a quad of equal cost
+    // wastes nothing
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return std::memcmp(t + (size_t)a * SSDR_FIR_TAPS, t + (size_t)b * SSDR_FIR_TAPS, tb) < 0;
+        const int c = std::memcmp(t + (size_t)a * SSDR_FIR_TAPS, t + (size_t)b * SSDR_FIR_TAPS, tb);
+        return c != 0 ? c < 0 : h->h_work[(size_t)a] < h->h_work[(size_t)b];
     });
     std::vector<int4> qc;
     std::vector<int> qf;
@@ -606,12 +613,26 @@ static int demod_build_quads(ssdr_demod_t h) {
         ++fill;
     }
     while (qc.size() % tiles) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(fid); }
+    // dearest rounds first (NBFM: atan2; AM: float64 carrier tracker), the cheap ones fill the tail
+    {
+        const size_t nr = qc.size() / tiles;
+        auto cost = [&](size_t r) { const int m = h->h_work[(size_t)qc[r * tiles].x] / 4; return m == SSDR_MODE_NBFM ? 2 : m == SSDR_MODE_AM ? 1 : 0; };
+        std::vector<size_t> ro(nr);
+        for (size_t r = 0; r < nr; ++r) ro[r] = r;
+        std::stable_sort(ro.begin(), ro.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
+        std::vector<int4> qc2(qc.size());
+        std::vector<int> qf2(qf.size());
+        for (size_t r = 0; r < nr; ++r)
+            for (size_t k = 0; k < tiles; ++k) { qc2[r * tiles + k] = qc[ro[r] * tiles + k]; qf2[r * tiles + k] = qf[ro[r] * tiles + k]; }
+        qc.swap(qc2); qf.swap(qf2);
+    }
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid);
     h->d_quad_ch = nullptr; h->d_quad_fid = nullptr;
     int rc;
     if ((rc = dev_alloc(&h->d_quad_ch, qc.size()))) return rc;
     if ((rc = dev_alloc(&h->d_quad_fid, qf.size()))) return rc;
+    if (!h->d_round_ctr && (rc = dev_alloc(&h->d_round_ctr, (size_t)1))) return rc;
     SSDR_CUDA(cudaMemcpy(h->d_quad_ch, qc.data(), sizeof(int4) * qc.size(), cudaMemcpyHostToDevice));
     SSDR_CUDA(cudaMemcpy(h->d_quad_fid, qf.data(), sizeof(int) * qf.size(), cudaMemcpyHostToDevice));
     h->n_quads = (int)(qc.size() / tiles);                  // rounds
@@ -627,7 +648,7 @@ static int demod_launch_block(ssdr_demod_t h, const void* iq_dev, int iq_format,
     for (int s = 0; s < 5; ++s) a.am_pow16[s] = h->am_pow16[s];
     if (h->engine == SSDR_DEMOD_ENGINE_TCGEN05) {
         if (h->quads_dirty) { int rc = demod_build_quads(h); if (rc) return rc; }
-        return demod_tc_launch(a, h->d_quad_ch, h->d_quad_fid, h->n_quads, h->compute);
+        return demod_tc_launch(a, h->d_quad_ch, h->d_quad_fid, h->n_quads, h->d_round_ctr, h->compute);
     }
     return demod_launch(a, h->compute);
 }

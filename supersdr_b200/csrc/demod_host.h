@@ -65,8 +65,9 @@ int demod_launch(const DemodLaunch& a, cudaStream_t st);
 
 // tcgen05 engine (demod_tc_kernels.cu).  quad_ch[q] = four channels that share one filter (slots filled in order, unused
 // slots -1), quad_fid[q] = id of that filter.  A CTA takes demod_tc_tiles() consecutive quads per round on one B operand:
-// the quads of a round share the filter (a round is padded with empty quads), rounds of one filter are adjacent.
+// the quads of a round share the filter (a round is padded with empty quads).  CTAs pull rounds from *round_ctr (zeroed
+// by the launch) in array order, so the host puts the dearest rounds first.
 int demod_tc_tiles();
-int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_rounds, cudaStream_t st);
+int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_rounds, int* round_ctr, cudaStream_t st);
 
 }  // namespace ssdr

@@ -29,6 +29,14 @@
 #include "demod_host.h"
 #include "demod_post.cuh"
 
+// Developer switches for timing experiments (scripts/exp_tc_variants.sh); the defaults are the measured optimum.
+#ifndef SSDR_TC_LASTARRIVER
+#define SSDR_TC_LASTARRIVER 1     // 1: the last warp of a tile to arrive issues the MMAs; 0: tile barrier, fixed issuer thread
+#endif
+#ifndef SSDR_TC_EARLYMIX
+#define SSDR_TC_EARLYMIX 0        // 1: mixer arithmetic of frame b + 1 before the wait for the MMAs of frame b; 0: after it
+#endif
+
 namespace ssdr {
 
 namespace {
@@ -85,13 +93,16 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
 }
 
 struct alignas(8) TcShared {
-    unsigned long long bar[TILES];
+    unsigned long long bar[TILES];     // MMAs of the tile's current frame have completed (tcgen05.commit)
+    unsigned arrived[TILES];           // warps of the tile whose operand rows of the next frame are in place (running count)
     unsigned tmem_base;
+    int round;                         // the round this CTA is working on (dynamic scheduling)
 };
 
 template <int FMT>
 __global__ void __launch_bounds__(TILES * WARPS * 32, 1)
-demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, const int* __restrict__ quad_fid, int n_rounds) {
+demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, const int* __restrict__ quad_fid, int n_rounds,
+                int* __restrict__ round_ctr) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ TcShared sh;
     const unsigned raw = (unsigned)__cvta_generic_to_shared(smem_raw);
@@ -102,9 +113,12 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
     unsigned char* sAl = sAh + A_BYTES;
     const unsigned aB = (unsigned)__cvta_generic_to_shared(sB), aAh = aB + B_BYTES + (unsigned)tile * 2 * A_BYTES, aAl = aAh + A_BYTES;
     const unsigned barp = (unsigned)__cvta_generic_to_shared(&sh.bar[tile]);
-    const bool issuer = (tid & 127) == 0;
+    const bool issuer = (tid & 127) == 0;                   // initialises the tile's barrier
 
-    if (issuer) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barp));
+    if (issuer) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barp));
+        sh.arrived[tile] = 0u;
+    }
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&sh.tmem_base)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -116,7 +130,6 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
     unsigned phase = 0;
 
     const int nblk = kp.n_samples / FR;
-    const int r0 = (int)((long long)blockIdx.x * n_rounds / gridDim.x), r1 = (int)((long long)(blockIdx.x + 1) * n_rounds / gridDim.x);
     const unsigned wch = (unsigned)warp * CHB;              // this warp's channel slot inside A_hi / A_lo
     int cur_fid = -1;
 
@@ -126,7 +139,12 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
         *reinterpret_cast<float*>(sAl + off) = x - hi;      // exact; the tensor core keeps its leading 11 bits
     };
 
-    for (int rd = r0; rd < r1; ++rd) {
+    // Rounds differ in cost (detector / AGC variant), so CTAs pull them from a counter in the host's order (dearest first)
+    for (;;) {
+        if (tid == 0) sh.round = atomicAdd(round_ctr, 1);
+        __syncthreads();                                    // the barrier that ends a round protects sh.round
+        const int rd = sh.round;
+        if (rd >= n_rounds) break;
         // ---- the round's filter as a Toeplitz B operand (rebuilt only when the filter changes) ---------------------
         const int fid = quad_fid[rd * TILES];
         if (fid != cur_fid) {                               // CTA-uniform; every tile has finished the previous round
@@ -164,11 +182,12 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 put(swz(off + 2 * GRPB), z.y);
             }
         }
-        // ---- frame pipeline of the tile: mix(b) -> MMAs(b) in flight while the back end of frame b - 1 runs (its
-        // accumulator is the other TMEM buffer) -> wait -> history rows -> mix(b + 1)
+        // ---- frame pipeline of a warp: rows of frame b in place -> (last warp of the tile issues the MMAs of frame b) ->
+        // back end of frame b - 1 (its accumulator is the other TMEM buffer) and the mixer arithmetic of frame b + 1 while
+        // the MMAs run -> wait for them -> history rows -> store the rows of frame b + 1
         unsigned ph1_mix = st.ph1;                          // the back end advances st.ph1 one frame later than the mixer
-        auto mix = [&](int b) {
-            // lane-strided, coalesced loads; block r of the frame = one 128-byte row, lane = position in the row
+        // mixer, part 1: lane-strided, coalesced loads; block r of the frame = one 128-byte operand row, lane = position
+        auto mix_compute = [&](int b, float2 (&y)[SPL]) {
             const size_t s0 = (size_t)ch * kp.pitch + (size_t)b * FR;
             float2 xin[SPL];
 #pragma unroll
@@ -183,17 +202,23 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 const float2 x = xin[r];
                 float c, s;
                 nco(ph1_mix + (unsigned)k * cp.inc1, c, s);
-                const float2 y = make_float2(x.x * c + x.y * s, x.y * c - x.x * s);      // x exp(-j theta)
-                const unsigned off = wch + (unsigned)(r >> 3) * GRPB + (unsigned)(4 + (r & 7)) * ROWB + (unsigned)lane * 4u;
-                put(swz(off), y.x);
-                put(swz(off + 2 * GRPB), y.y);
-                if (r >= 4 && r < 8) {                      // blocks 4..7 are also the history of octet 1
-                    const unsigned offh = wch + GRPB + (unsigned)(r - 4) * ROWB + (unsigned)lane * 4u;
-                    put(swz(offh), y.x);
-                    put(swz(offh + 2 * GRPB), y.y);
-                }
+                y[r] = make_float2(x.x * c + x.y * s, x.y * c - x.x * s);      // x exp(-j theta)
             }
             ph1_mix += (unsigned)FR * cp.inc1;
+        };
+        // mixer, part 2: (hi, lo) split into the operand rows -- only after the MMAs that read the previous frame are done
+        auto mix_store = [&](const float2 (&y)[SPL]) {
+#pragma unroll
+            for (int r = 0; r < SPL; ++r) {
+                const unsigned off = wch + (unsigned)(r >> 3) * GRPB + (unsigned)(4 + (r & 7)) * ROWB + (unsigned)lane * 4u;
+                put(swz(off), y[r].x);
+                put(swz(off + 2 * GRPB), y[r].y);
+                if (r >= 4 && r < 8) {                      // blocks 4..7 are also the history of octet 1
+                    const unsigned offh = wch + GRPB + (unsigned)(r - 4) * ROWB + (unsigned)lane * 4u;
+                    put(swz(offh), y[r].x);
+                    put(swz(offh + 2 * GRPB), y[r].y);
+                }
+            }
         };
         auto back_end = [&](int b) {
             // read back: lane i < 16 has the real parts of block i, lane 16 + i its imaginary parts; every warp of the tile
@@ -220,29 +245,46 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             }
             demod_frame_tail<LanesPaired>(acc, cp, kp, ch, b, (size_t)ch * kp.pitch + (size_t)b * FR, st);
         };
-        if (tile_active && active) mix(0);
+        float2 y[SPL];
+        if (tile_active && active) { mix_compute(0, y); mix_store(y); }
         for (int b = 0; tile_active && b < nblk; ++b) {
-            // generic-proxy writes -> visible to the tensor core (async proxy); order earlier TMEM reads before the MMAs
+            // This warp's rows of frame b are in place: publish them to the tensor core (async proxy), order this warp's
+            // earlier TMEM reads before the MMAs, and count the warp in.  No warp waits for another one here: the LAST
+            // of the tile's four warps to arrive issues the tile's MMAs.
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#if SSDR_TC_LASTARRIVER
+            __syncwarp();
+            if (lane == 0) {
+                unsigned old;
+                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(&sh.arrived[tile])) : "memory");
+                if ((old & 3u) == 3u) {
+#else
             asm volatile("bar.sync %0, 128;" ::"r"(tile + 1) : "memory");        // the tile's four warps
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (issuer) {
-                constexpr unsigned i64 = idesc_tf32(128, 64), i32 = idesc_tf32(128, 32);
-                const unsigned td = tm + (unsigned)(b & 1) * 64u;
+            {
+                if (issuer) {
+#endif
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    constexpr unsigned i64 = idesc_tf32(128, 64), i32 = idesc_tf32(128, 32);
+                    const unsigned td = tm + (unsigned)(b & 1) * 64u;
 #pragma unroll 1
-                for (int c = 0; c < KCH; ++c) {
+                    for (int c = 0; c < KCH; ++c) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {           // K step of 8 samples = 32 bytes inside the swizzled row
-                        const unsigned oa = (unsigned)c * ROWB + (unsigned)j * 32u, ob = aB + (unsigned)c * B_ATOM + (unsigned)j * 32u;
-                        const uint64_t db = desc_sw128(ob, 1024u);
-                        mma_tf32(td, desc_sw128(aAh + oa, GRPB), db, i64, (c | j) != 0);       // A_hi [B_hi | B_lo] -> columns 0..63
-                        mma_tf32(td, desc_sw128(aAl + oa, GRPB), db, i32, 1u);                  // A_lo B_hi -> columns 0..31
+                        for (int j = 0; j < 4; ++j) {       // K step of 8 samples = 32 bytes inside the swizzled row
+                            const unsigned oa = (unsigned)c * ROWB + (unsigned)j * 32u, ob = aB + (unsigned)c * B_ATOM + (unsigned)j * 32u;
+                            const uint64_t db = desc_sw128(ob, 1024u);
+                            mma_tf32(td, desc_sw128(aAh + oa, GRPB), db, i64, (c | j) != 0);       // A_hi [B_hi | B_lo] -> columns 0..63
+                            mma_tf32(td, desc_sw128(aAl + oa, GRPB), db, i32, 1u);                  // A_lo B_hi -> columns 0..31
+                        }
                     }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(barp) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(barp) : "memory");
             }
+            __syncwarp();
             if (b > 0) back_end(b - 1);                     // overlaps the MMAs of frame b
+#if SSDR_TC_EARLYMIX
+            if (active && b + 1 < nblk) mix_compute(b + 1, y);
+#endif
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
                 "WAIT_%=:\n\t"
@@ -261,7 +303,10 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                     *reinterpret_cast<float4*>(sAl + dst) = *reinterpret_cast<const float4*>(sAl + src);
                 }
                 __syncwarp();
-                if (b + 1 < nblk) mix(b + 1);
+#if !SSDR_TC_EARLYMIX
+                if (b + 1 < nblk) mix_compute(b + 1, y);
+#endif
+                if (b + 1 < nblk) mix_store(y);
             }
         }
         if (tile_active) back_end(nblk - 1);
@@ -288,7 +333,7 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
 
 int demod_tc_tiles() { return TILES; }
 
-int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_rounds, cudaStream_t st) {
+int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_fid, int n_rounds, int* round_ctr, cudaStream_t st) {
     DemodKernelParams kp;
     kp.iq = a.iq; kp.chan = a.chan; kp.state = a.state; kp.hist = a.hist; kp.taps = a.taps;
     kp.pcm_f32 = a.pcm_f32; kp.pcm_i16 = a.pcm_i16; kp.rssi = a.rssi;
@@ -299,7 +344,8 @@ int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_f
     int grid = sm_count();                                  // one CTA per SM (shared memory), TILES x 4 warps
     if (grid > n_rounds) grid = n_rounds;
     if (grid < 1) return SSDR_OK;
-    kern<<<grid, TILES * WARPS * 32, SMEM_BYTES, st>>>(kp, quad_ch, quad_fid, n_rounds);
+    SSDR_CUDA(cudaMemsetAsync(round_ctr, 0, sizeof(int), st));
+    kern<<<grid, TILES * WARPS * 32, SMEM_BYTES, st>>>(kp, quad_ch, quad_fid, n_rounds, round_ctr);
     count_launch();
     SSDR_CUDA(cudaGetLastError());
     return SSDR_OK;
