@@ -626,6 +626,29 @@ static int demod_build_quads(ssdr_demod_t h) {
             for (size_t k = 0; k < tiles; ++k) { qc2[r * tiles + k] = qc[ro[r] * tiles + k]; qf2[r * tiles + k] = qf[ro[r] * tiles + k]; }
         qc.swap(qc2); qf.swap(qf2);
     }
+    // The last, partial wave: with one CTA per SM, n_rounds = w * n_sm + tail leaves n_sm - tail SMs idle while `tail`
+    // CTAs run full rounds.  Spread the quads of those rounds over more, narrower rounds (fewer tiles per CTA finish
+    // sooner: the tiles of a CTA share the tensor pipe and the issue slots).
+    if (std::getenv("SSDR_DEMOD_NO_TAIL_SPLIT") == nullptr) {
+        const size_t nsm = (size_t)sm_count(), nr = qc.size() / tiles, tail = nr % nsm;
+        if (tail > 0 && nr > tail) {
+            std::vector<int4> tq;
+            std::vector<int> tf;
+            for (size_t i = (nr - tail) * tiles; i < qc.size(); ++i)
+                if (qc[i].x >= 0) { tq.push_back(qc[i]); tf.push_back(qf[i]); }
+            const size_t per = (tq.size() + nsm - 1) / nsm;           // quads per narrow round
+            if (per < tiles) {
+                qc.resize((nr - tail) * tiles); qf.resize((nr - tail) * tiles);
+                size_t i = 0;
+                while (i < tq.size()) {
+                    size_t k = 0;
+                    const int f = tf[i];
+                    for (; k < per && i < tq.size() && tf[i] == f; ++k, ++i) { qc.push_back(tq[i]); qf.push_back(f); }
+                    for (; k < tiles; ++k) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(f); }
+                }
+            }
+        }
+    }
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid);
     h->d_quad_ch = nullptr; h->d_quad_fid = nullptr;

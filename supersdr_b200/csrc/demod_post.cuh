@@ -134,12 +134,20 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
             a[r] = (float)((double)mag[r] - d);
         }
     } else {
+        // one NCO evaluation per four samples (the phase accumulator is exact), the other three by rotation
+        float c2, s2;
+        nco(cp.inc2, c2, s2);
 #pragma unroll
-        for (int r = 0; r < SPL; ++r) {
-            const int k = SPL * lane + r;
+        for (int r4 = 0; r4 < SPL; r4 += 4) {
             float c, s;
-            nco(st.ph2 + (unsigned)k * cp.inc2, c, s);
-            a[r] = acc[r].x * c - acc[r].y * s;       // Re(z * exp(+j theta2))
+            nco(st.ph2 + (unsigned)(SPL * lane + r4) * cp.inc2, c, s);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[r4 + i] = acc[r4 + i].x * c - acc[r4 + i].y * s;       // Re(z * exp(+j theta2))
+                const float cn = c * c2 - s * s2;
+                s = s * c2 + c * s2;
+                c = cn;
+            }
         }
     }
     // ---- AGC ---------------------------------------------------------------------------------
@@ -245,6 +253,24 @@ __device__ __forceinline__ float2 demod_ld_iq(const void* base, size_t idx) {
         const unsigned sw = __byte_perm(v, 0u, 0x2301);   // swap the bytes of both 16-bit halves
         const int i = (int)(short)(sw & 0xffffu), q = (int)sw >> 16;
         return make_float2((float)i, (float)q);
+    }
+}
+
+// four consecutive samples (idx a multiple of 4: 32 / 16 bytes, aligned)
+template <int FMT>
+__device__ __forceinline__ void demod_ld_iq4(const void* base, size_t idx, float2* x) {
+    if constexpr (FMT == SSDR_IQ_CF32) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(base) + idx);
+        const float4 a = __ldcs(p), b = __ldcs(p + 1);
+        x[0] = make_float2(a.x, a.y); x[1] = make_float2(a.z, a.w); x[2] = make_float2(b.x, b.y); x[3] = make_float2(b.z, b.w);
+    } else {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned*>(base) + idx));
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const unsigned sw = __byte_perm(w[i], 0u, 0x2301);
+            x[i] = make_float2((float)(int)(short)(sw & 0xffffu), (float)((int)sw >> 16));
+        }
     }
 }
 

@@ -186,37 +186,52 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
         // back end of frame b - 1 (its accumulator is the other TMEM buffer) and the mixer arithmetic of frame b + 1 while
         // the MMAs run -> wait for them -> history rows -> store the rows of frame b + 1
         unsigned ph1_mix = st.ph1;                          // the back end advances st.ph1 one frame later than the mixer
-        // mixer, part 1: lane-strided, coalesced loads; block r of the frame = one 128-byte operand row, lane = position
+        // mixer, part 1: every lane takes four consecutive samples of each quarter frame (coalesced 16 / 32-byte loads):
+        // y[4 q + i] = sample 128 q + 4 lane + i.  One NCO evaluation per four samples, the other three by rotation.
+        float rc1, rs1;
+        nco(cp.inc1, rc1, rs1);
         auto mix_compute = [&](int b, float2 (&y)[SPL]) {
             const size_t s0 = (size_t)ch * kp.pitch + (size_t)b * FR;
             float2 xin[SPL];
 #pragma unroll
-            for (int r = 0; r < SPL; ++r) xin[r] = demod_ld_iq<FMT>(kp.iq, s0 + lane + 32 * r);
+            for (int q = 0; q < 4; ++q) demod_ld_iq4<FMT>(kp.iq, s0 + 128 * q + 4 * lane, &xin[4 * q]);
             if (b + 1 < nblk) {                             // next frame -> L2 (one 128-byte line per lane)
                 const char* nx = static_cast<const char*>(kp.iq) + (s0 + FR) * (FMT == SSDR_IQ_CF32 ? 8 : 4) + lane * 128;
                 if (FMT == SSDR_IQ_CF32 || lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
             }
 #pragma unroll
-            for (int r = 0; r < SPL; ++r) {
-                const int k = lane + 32 * r;
-                const float2 x = xin[r];
+            for (int q = 0; q < 4; ++q) {
                 float c, s;
-                nco(ph1_mix + (unsigned)k * cp.inc1, c, s);
-                y[r] = make_float2(x.x * c + x.y * s, x.y * c - x.x * s);      // x exp(-j theta)
+                nco(ph1_mix + (unsigned)(128 * q + 4 * lane) * cp.inc1, c, s);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 x = xin[4 * q + i];
+                    y[4 * q + i] = make_float2(x.x * c + x.y * s, x.y * c - x.x * s);      // x exp(-j theta)
+                    const float cn = c * rc1 - s * rs1;
+                    s = s * rc1 + c * rs1;
+                    c = cn;
+                }
             }
             ph1_mix += (unsigned)FR * cp.inc1;
         };
-        // mixer, part 2: (hi, lo) split into the operand rows -- only after the MMAs that read the previous frame are done
+        // mixer, part 2: (hi, lo) split into the operand rows -- only after the MMAs that read the previous frame are done.
+        // Four samples = one 16-byte chunk of a row: block 4 q + (lane >> 3), chunk lane & 7.
+        auto put4 = [&](unsigned off, float a0, float a1, float a2, float a3) {
+            const float h0 = tf32_hi(a0), h1 = tf32_hi(a1), h2 = tf32_hi(a2), h3 = tf32_hi(a3);
+            *reinterpret_cast<float4*>(sAh + off) = make_float4(h0, h1, h2, h3);
+            *reinterpret_cast<float4*>(sAl + off) = make_float4(a0 - h0, a1 - h1, a2 - h2, a3 - h3);
+        };
         auto mix_store = [&](const float2 (&y)[SPL]) {
+            const unsigned row = (unsigned)lane >> 3, chunk = ((unsigned)lane & 7u) * 16u;
 #pragma unroll
-            for (int r = 0; r < SPL; ++r) {
-                const unsigned off = wch + (unsigned)(r >> 3) * GRPB + (unsigned)(4 + (r & 7)) * ROWB + (unsigned)lane * 4u;
-                put(swz(off), y[r].x);
-                put(swz(off + 2 * GRPB), y[r].y);
-                if (r >= 4 && r < 8) {                      // blocks 4..7 are also the history of octet 1
-                    const unsigned offh = wch + GRPB + (unsigned)(r - 4) * ROWB + (unsigned)lane * 4u;
-                    put(swz(offh), y[r].x);
-                    put(swz(offh + 2 * GRPB), y[r].y);
+            for (int q = 0; q < 4; ++q) {
+                const unsigned off = swz(wch + (unsigned)(q >> 1) * GRPB + (4u + 4u * (q & 1) + row) * ROWB + chunk);
+                put4(off, y[4 * q].x, y[4 * q + 1].x, y[4 * q + 2].x, y[4 * q + 3].x);
+                put4(off + 2 * GRPB, y[4 * q].y, y[4 * q + 1].y, y[4 * q + 2].y, y[4 * q + 3].y);
+                if (q == 1) {                               // blocks 4..7 are also the history of octet 1
+                    const unsigned offh = swz(wch + GRPB + row * ROWB + chunk);
+                    put4(offh, y[4].x, y[5].x, y[6].x, y[7].x);
+                    put4(offh + 2 * GRPB, y[4].y, y[5].y, y[6].y, y[7].y);
                 }
             }
         };
