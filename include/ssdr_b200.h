@@ -182,11 +182,14 @@ int ssdr_demod_destroy(ssdr_demod_t h);
 int ssdr_demod_set(ssdr_demod_t h, int first_channel, int count, const ssdr_demod_params_t* params);
 int ssdr_demod_reset(ssdr_demod_t h);   /* zero all per-channel streaming state */
 /* FIR engine of the fused kernel.  FFMA: direct form on the fp32 pipe (one warp per channel).  TCGEN05: the FIR as a
- * Toeplitz GEMM on the 5th-generation tensor cores (3 x TF32 split, accumulators in TMEM); channels are grouped four at a
- * time by filter, so it pays when many channels share a pass-band width.  Same state, same outputs to the demodulator's
- * tolerance (1e-5 relative RMS); engines may be switched between calls.  No reference counterpart (the DSP is remote). */
+ * Toeplitz GEMM on the 5th-generation tensor cores (3 x TF32 split, accumulators in TMEM); four channels that share a
+ * filter (bitwise-equal taps) make one tile, so it pays when channels share pass-band widths.  AUTO (default): TCGEN05
+ * when at least half of the tile rows would carry a channel, else FFMA.  Same per-channel state, same outputs to the
+ * demodulator's tolerance (1e-5 relative RMS); engines may be switched between calls.  No reference counterpart (the
+ * DSP is remote, utils_supersdr.py:1022-1029). */
 #define SSDR_DEMOD_ENGINE_FFMA    0
 #define SSDR_DEMOD_ENGINE_TCGEN05 1
+#define SSDR_DEMOD_ENGINE_AUTO    2
 int ssdr_demod_set_engine(ssdr_demod_t h, int engine);
 /* n_samples per channel, multiple of SSDR_FRAME.  iq [batch][n_samples]; outputs (NULL = skip):
  * pcm_f32 [batch][n_samples], pcm_i16 [batch][n_samples] (rint + saturate),

@@ -18,11 +18,13 @@ for N, B, n in ((256, 9, 2), (1024, 3, 2), (4096, 3, 2), (8192, 2, 2), (16384, 2
         bank.colorrow(lines)
     bank.close()
     print("waterfall", N, "ok", flush=True)
-dm = S.DemodBank(5, 512 * 4)
-dm.set_params(0, [S.demod_params(m) for m in ("am", "lsb", "usb", "cw", "nbfm")])
-x = np.stack([tier_u.synth_demod_iq(m, 512 * 4, seed=1) for m in ("am", "lsb", "usb", "cw", "nbfm")])
-dm.process(x); dm.process(x)
-dm.close()
+modes = ("am", "lsb", "usb", "cw", "nbfm", "usb", "usb")      # 7 channels: partial quads, three filters
+x = np.stack([tier_u.synth_demod_iq(m, 512 * 4, seed=1) for m in modes])
+for eng in ("ffma", "tcgen05"):
+    dm = S.DemodBank(len(modes), 512 * 4, engine=eng)
+    dm.set_params(0, [S.demod_params(m) for m in modes])
+    dm.process(x); dm.process(x)
+    dm.close()
 print("demod ok", flush=True)
 ib = S.InterpBank(3, 4, max_samples=512)
 ib.process(rng.integers(-20000, 20000, (3, 512)).astype(np.int16), volume=80, balance=0.2)

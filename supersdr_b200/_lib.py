@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SSDR_B200_LIB") or os.path.join(_HERE, "libssdr_b200.so")
 
 SSDR_IQ_CF32, SSDR_IQ_S16BE = 0, 1
-SSDR_DEMOD_ENGINE_FFMA, SSDR_DEMOD_ENGINE_TCGEN05 = 0, 1
+SSDR_DEMOD_ENGINE_FFMA, SSDR_DEMOD_ENGINE_TCGEN05, SSDR_DEMOD_ENGINE_AUTO = 0, 1, 2
 MODE_AM, MODE_USB, MODE_LSB, MODE_CW, MODE_NBFM = 0, 1, 2, 3, 4
 FS = 32768.0
 WF_CAL_DB = -10.0

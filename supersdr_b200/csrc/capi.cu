@@ -100,7 +100,8 @@ struct ssdr_demod {
     int16_t* d_i16 = nullptr;
     float* d_rssi = nullptr;
     // FIR engine (ssdr_demod_set_engine) and, for the tcgen05 engine, the channels grouped in quads that share a filter
-    int engine = SSDR_DEMOD_ENGINE_FFMA;
+    int engine = SSDR_DEMOD_ENGINE_AUTO;
+    double quad_fill = 0.0;        // channels / (4 x non-empty quads): how full the tensor-core tiles are
     std::vector<float> h_taps;     // host mirror of d_taps, [batch][127]
     std::vector<int> h_work;       // per channel: detector / AGC variant (channels of one quad should cost the same)
     bool quads_dirty = true;
@@ -505,6 +506,7 @@ int ssdr_demod_create(ssdr_demod_t* out, int batch, int max_samples) {
     if (const char* e = std::getenv("SSDR_DEMOD_ENGINE")) {      // developer override of the default engine
         if (!std::strcmp(e, "tcgen05")) h->engine = SSDR_DEMOD_ENGINE_TCGEN05;
         else if (!std::strcmp(e, "ffma")) h->engine = SSDR_DEMOD_ENGINE_FFMA;
+        else if (!std::strcmp(e, "auto")) h->engine = SSDR_DEMOD_ENGINE_AUTO;
     }
     *out = h;
     if ((rc = ssdr_demod_reset(h))) { *out = nullptr; return fail(rc); }
@@ -576,7 +578,8 @@ int ssdr_demod_set(ssdr_demod_t h, int first, int count, const ssdr_demod_params
 
 int ssdr_demod_set_engine(ssdr_demod_t h, int engine) {
     SSDR_ARG(h != nullptr, "null handle");
-    SSDR_ARG(engine == SSDR_DEMOD_ENGINE_FFMA || engine == SSDR_DEMOD_ENGINE_TCGEN05, "unknown demodulator engine %d", engine);
+    SSDR_ARG(engine == SSDR_DEMOD_ENGINE_FFMA || engine == SSDR_DEMOD_ENGINE_TCGEN05 || engine == SSDR_DEMOD_ENGINE_AUTO,
+             "unknown demodulator engine %d", engine);
     h->engine = engine;
     return SSDR_OK;
 }
@@ -613,6 +616,11 @@ static int demod_build_quads(ssdr_demod_t h) {
         ++fill;
     }
     while (qc.size() % tiles) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(fid); }
+    {
+        size_t used = 0;
+        for (const int4& q : qc) used += q.x >= 0;
+        h->quad_fill = used ? (double)B / (4.0 * (double)used) : 0.0;
+    }
     // dearest rounds first (NBFM: atan2; AM: float64 carrier tracker), the cheap ones fill the tail
     {
         const size_t nr = qc.size() / tiles;
@@ -669,8 +677,8 @@ static int demod_launch_block(ssdr_demod_t h, const void* iq_dev, int iq_format,
     a.iq = iq_dev; a.iq_format = iq_format; a.chan = h->d_chan; a.state = h->d_state; a.hist = h->d_hist; a.taps = h->d_taps;
     a.pcm_f32 = pcm_f32_dev; a.pcm_i16 = pcm_i16_dev; a.rssi = rssi_dev; a.batch = h->batch; a.n_samples = n_samples; a.pitch = pitch;
     for (int s = 0; s < 5; ++s) a.am_pow16[s] = h->am_pow16[s];
-    if (h->engine == SSDR_DEMOD_ENGINE_TCGEN05) {
-        if (h->quads_dirty) { int rc = demod_build_quads(h); if (rc) return rc; }
+    if (h->engine != SSDR_DEMOD_ENGINE_FFMA && h->quads_dirty) { int rc = demod_build_quads(h); if (rc) return rc; }
+    if (h->engine == SSDR_DEMOD_ENGINE_TCGEN05 || (h->engine == SSDR_DEMOD_ENGINE_AUTO && h->quad_fill >= 0.5)) {
         return demod_tc_launch(a, h->d_quad_ch, h->d_quad_fid, h->n_quads, h->d_round_ctr, h->compute);
     }
     return demod_launch(a, h->compute);

@@ -64,7 +64,7 @@ def demod_params(mode="usb", lc=None, hc=None, f_off=0.0, on=True, hang=False, t
 class DemodBank:
     """B channels of IQ @12 kHz -> PCM @12 kHz (float32 + int16) and per-frame RSSI."""
 
-    ENGINES = {"ffma": _lib.SSDR_DEMOD_ENGINE_FFMA, "tcgen05": _lib.SSDR_DEMOD_ENGINE_TCGEN05}
+    ENGINES = {"ffma": _lib.SSDR_DEMOD_ENGINE_FFMA, "tcgen05": _lib.SSDR_DEMOD_ENGINE_TCGEN05, "auto": _lib.SSDR_DEMOD_ENGINE_AUTO}
 
     def __init__(self, batch=1, max_samples=_lib.FRAME * 64, device=None, engine=None):
         _lib.init(device)
@@ -81,7 +81,8 @@ class DemodBank:
         check(lib.ssdr_demod_set(self._h, int(first), len(params), arr))
 
     def set_engine(self, engine):
-        """FIR engine of the fused kernel: "ffma" (fp32 pipe) or "tcgen05" (tensor cores); switchable between calls."""
+        """FIR engine of the fused kernel: "ffma" (fp32 pipe), "tcgen05" (tensor cores) or "auto" (default: tensor cores
+        when channels share filters); switchable between calls."""
         check(lib.ssdr_demod_set_engine(self._h, self.ENGINES[engine] if isinstance(engine, str) else int(engine)))
 
     def set_all(self, **kw):
