@@ -33,6 +33,9 @@
 #ifndef SSDR_TC_LASTARRIVER
 #define SSDR_TC_LASTARRIVER 1     // 1: the last warp of a tile to arrive issues the MMAs; 0: tile barrier, fixed issuer thread
 #endif
+#ifndef SSDR_TC_TILES
+#define SSDR_TC_TILES 3           // tiles (groups of four warps) per CTA
+#endif
 #ifndef SSDR_TC_EARLYMIX
 #define SSDR_TC_EARLYMIX 0        // 1: mixer arithmetic of frame b + 1 before the wait for the MMAs of frame b; 0: after it
 #endif
@@ -46,7 +49,7 @@ constexpr int H = T - 1;                  // 126 history samples kept per channe
 constexpr int FR = SSDR_FRAME;            // 512
 constexpr int SPL = kDemodSpl;            // 16
 constexpr int WARPS = 4;                  // channels (warps) per tile
-constexpr int TILES = 3;                  // tiles per CTA
+constexpr int TILES = SSDR_TC_TILES;      // tiles per CTA
 constexpr int KCH = 5;                    // K chunks of 32 samples (160 = 128 history + 32)
 constexpr unsigned ROWB = 128;            // one 32-sample block of floats
 constexpr unsigned GROWS = 12;            // rows per mini-stream: 4 history blocks + 8 blocks
@@ -56,7 +59,7 @@ constexpr unsigned A_BYTES = WARPS * CHB; // 24576 per precision part
 constexpr unsigned B_ATOM = 8 * 1024;     // per K chunk: 32 rows of B_hi (4 groups) then 32 rows of B_lo
 constexpr unsigned B_BYTES = KCH * B_ATOM;
 constexpr unsigned SMEM_BYTES = TILES * 2 * A_BYTES + B_BYTES + 1024;   // + alignment slack
-constexpr unsigned TMEM_COLS = 512;       // two accumulators of 64 columns per tile (3 x 128), allocation is a power of two
+constexpr unsigned TMEM_COLS = TILES > 2 ? 512 : 256;       // two accumulators of 64 columns per tile, allocation is a power of two
 
 __device__ __forceinline__ unsigned swz(unsigned off) { return off ^ (((off >> 7) & 7u) << 4); }   // off from a 1024-aligned base
 __device__ __forceinline__ float tf32_hi(float x) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
