@@ -764,7 +764,7 @@ wf_fft_kernel(const WfKernelParams kp) {
             // from here each warp owns a contiguous 1024-point (NP == 3) / 32-point sub-transform: warp-local
             if constexpr (C::STAGGER > 0) {
                 const int lvl = (LG == 14) ? ((threadIdx.x >> 7) & 3) : (LG == 13) ? ((threadIdx.x >> 6) & 3) : ((threadIdx.x >> 5) & 3);     // four levels
-                if (lvl) { const long long c0 = clock64(); while (clock64() - c0 < lvl * C::STAGGER) { } }
+                if (lvl) { const long long c0 = clock64(); while (clock64() - c0 < lvl * C::STAGGER) { } }   // (__nanosleep is too coarse: 2.08 ms)
             }
 #if !(SSDR_EXP & 16)
             if constexpr (C::NP == 3) {
