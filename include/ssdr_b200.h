@@ -191,6 +191,14 @@ int ssdr_demod_reset(ssdr_demod_t h);   /* zero all per-channel streaming state 
 #define SSDR_DEMOD_ENGINE_TCGEN05 1
 #define SSDR_DEMOD_ENGINE_AUTO    2
 int ssdr_demod_set_engine(ssdr_demod_t h, int engine);
+/* Work plan of the TCGEN05 engine, host only (needs no device; exposed for tests and capacity planning).  taps
+ * [batch][SSDR_FIR_TAPS], work [batch] = mode * 4 + agc_on * 2 + agc_hang.  Channels are grouped by bitwise-equal taps, then
+ * by `work`, into quads (one tensor-core tile: four channels, unused slots -1); `*tiles_per_round` consecutive quads of one
+ * filter form a round (padded with empty quads), the dearest detectors first, and the last partial wave over `n_sm` SMs is
+ * spread over narrower rounds.  Writes quad_ch [n_quads][4] and quad_fid [n_quads] (filter id) when both are non-NULL
+ * (capacity `cap_quads` entries), always *n_quads; *fill = batch / (4 x non-empty quads). */
+int ssdr_demod_plan(const float* taps, const int32_t* work, int batch, int n_sm, int32_t* quad_ch, int32_t* quad_fid,
+                    int cap_quads, int* n_quads, int* tiles_per_round, float* fill);
 /* n_samples per channel, multiple of SSDR_FRAME.  iq [batch][n_samples]; outputs (NULL = skip):
  * pcm_f32 [batch][n_samples], pcm_i16 [batch][n_samples] (rint + saturate),
  * rssi_dbm [batch][n_samples/512] (what the SND header's s-meter carries, utils:1068-1069). */

@@ -85,6 +85,7 @@ _PROTOS = {
     "ssdr_demod_set": (_i, [_vp, _i, _i, C.POINTER(DemodParams)]),
     "ssdr_demod_reset": (_i, [_vp]),
     "ssdr_demod_set_engine": (_i, [_vp, _i]),
+    "ssdr_demod_plan": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_f)]),
     "ssdr_demod_process": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ssdr_demod_process_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "ssdr_demod_sync": (_i, [_vp]),

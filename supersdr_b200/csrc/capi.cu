@@ -586,45 +586,42 @@ int ssdr_demod_set_engine(ssdr_demod_t h, int engine) {
 
 // tcgen05 engine: one M = 128 tile is four channels x one frame and all four share the B operand (the taps), so channels
 // are grouped by filter (bitwise-equal taps) into quads; a filter with n channels takes ceil(n / 4) quads, the last one
-// padded with -1.  The streaming state stays per channel, so regrouping between calls is free.
-static int demod_build_quads(ssdr_demod_t h) {
-    const int B = h->batch;
+// padded with -1.  `tiles` quads of one filter make a round (padded with empty quads).  Pure host code (no device):
+// ssdr_demod_plan exposes it to the CPU tests.  The streaming state stays per channel, so regrouping between calls is free.
+static void demod_plan_rounds(const float* t, const int* work, int B, size_t tiles, size_t nsm, bool split_tail,
+                              std::vector<int4>& qc, std::vector<int>& qf, double* fill) {
     const size_t tb = sizeof(float) * SSDR_FIR_TAPS;
+    const int4 empty = make_int4(-1, -1, -1, -1);
     std::vector<int> order((size_t)B);
     for (int i = 0; i < B; ++i) order[(size_t)i] = i;
-    const float* t = h->h_taps.data();
     // by filter, then by detector / AGC variant: the four warps of a tile advance in lock step, so a quad of equal cost
     // wastes nothing
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         const int c = std::memcmp(t + (size_t)a * SSDR_FIR_TAPS, t + (size_t)b * SSDR_FIR_TAPS, tb);
-        return c != 0 ? c < 0 : h->h_work[(size_t)a] < h->h_work[(size_t)b];
+        return c != 0 ? c < 0 : work[a] < work[b];
     });
-    std::vector<int4> qc;
-    std::vector<int> qf;
-    const size_t tiles = (size_t)demod_tc_tiles();
-    int fid = -1, fill = 4;
+    qc.clear(); qf.clear();
+    int fid = -1, fill4 = 4;
     for (int i = 0; i < B; ++i) {
         const int ch = order[(size_t)i];
         const bool same = i > 0 && !std::memcmp(t + (size_t)ch * SSDR_FIR_TAPS, t + (size_t)order[(size_t)i - 1] * SSDR_FIR_TAPS, tb);
         if (!same) {                                         // a new filter starts a new round
-            while (qc.size() % tiles) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(fid); }
-            ++fid; fill = 4;
+            while (qc.size() % tiles) { qc.push_back(empty); qf.push_back(fid); }
+            ++fid; fill4 = 4;
         }
-        if (fill == 4) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(fid); fill = 0; }
+        if (fill4 == 4) { qc.push_back(empty); qf.push_back(fid); fill4 = 0; }
         int4& q = qc.back();
-        (fill == 0 ? q.x : fill == 1 ? q.y : fill == 2 ? q.z : q.w) = ch;
-        ++fill;
+        (fill4 == 0 ? q.x : fill4 == 1 ? q.y : fill4 == 2 ? q.z : q.w) = ch;
+        ++fill4;
     }
-    while (qc.size() % tiles) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(fid); }
-    {
-        size_t used = 0;
-        for (const int4& q : qc) used += q.x >= 0;
-        h->quad_fill = used ? (double)B / (4.0 * (double)used) : 0.0;
-    }
+    while (qc.size() % tiles) { qc.push_back(empty); qf.push_back(fid); }
+    size_t used = 0;
+    for (const int4& q : qc) used += q.x >= 0;
+    *fill = used ? (double)B / (4.0 * (double)used) : 0.0;
     // dearest rounds first (NBFM: atan2; AM: float64 carrier tracker), the cheap ones fill the tail
     {
         const size_t nr = qc.size() / tiles;
-        auto cost = [&](size_t r) { const int m = h->h_work[(size_t)qc[r * tiles].x] / 4; return m == SSDR_MODE_NBFM ? 2 : m == SSDR_MODE_AM ? 1 : 0; };
+        auto cost = [&](size_t r) { const int m = work[qc[r * tiles].x] / 4; return m == SSDR_MODE_NBFM ? 2 : m == SSDR_MODE_AM ? 1 : 0; };
         std::vector<size_t> ro(nr);
         for (size_t r = 0; r < nr; ++r) ro[r] = r;
         std::stable_sort(ro.begin(), ro.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
@@ -637,26 +634,52 @@ static int demod_build_quads(ssdr_demod_t h) {
     // The last, partial wave: with one CTA per SM, n_rounds = w * n_sm + tail leaves n_sm - tail SMs idle while `tail`
     // CTAs run full rounds.  Spread the quads of those rounds over more, narrower rounds (fewer tiles per CTA finish
     // sooner: the tiles of a CTA share the tensor pipe and the issue slots).
-    if (std::getenv("SSDR_DEMOD_NO_TAIL_SPLIT") == nullptr) {
-        const size_t nsm = (size_t)sm_count(), nr = qc.size() / tiles, tail = nr % nsm;
-        if (tail > 0 && nr > tail) {
-            std::vector<int4> tq;
-            std::vector<int> tf;
-            for (size_t i = (nr - tail) * tiles; i < qc.size(); ++i)
-                if (qc[i].x >= 0) { tq.push_back(qc[i]); tf.push_back(qf[i]); }
-            const size_t per = (tq.size() + nsm - 1) / nsm;           // quads per narrow round
-            if (per < tiles) {
-                qc.resize((nr - tail) * tiles); qf.resize((nr - tail) * tiles);
-                size_t i = 0;
-                while (i < tq.size()) {
-                    size_t k = 0;
-                    const int f = tf[i];
-                    for (; k < per && i < tq.size() && tf[i] == f; ++k, ++i) { qc.push_back(tq[i]); qf.push_back(f); }
-                    for (; k < tiles; ++k) { qc.push_back(make_int4(-1, -1, -1, -1)); qf.push_back(f); }
-                }
+    const size_t nr = qc.size() / tiles, tail = nsm ? nr % nsm : 0;
+    if (split_tail && tail > 0 && nr > tail) {
+        std::vector<int4> tq;
+        std::vector<int> tf;
+        for (size_t i = (nr - tail) * tiles; i < qc.size(); ++i)
+            if (qc[i].x >= 0) { tq.push_back(qc[i]); tf.push_back(qf[i]); }
+        const size_t per = (tq.size() + nsm - 1) / nsm;           // quads per narrow round
+        if (per < tiles) {
+            qc.resize((nr - tail) * tiles); qf.resize((nr - tail) * tiles);
+            size_t i = 0;
+            while (i < tq.size()) {
+                size_t k = 0;
+                const int f = tf[i];
+                for (; k < per && i < tq.size() && tf[i] == f; ++k, ++i) { qc.push_back(tq[i]); qf.push_back(f); }
+                for (; k < tiles; ++k) { qc.push_back(empty); qf.push_back(f); }
             }
         }
     }
+}
+
+int ssdr_demod_plan(const float* taps, const int32_t* work, int batch, int n_sm, int32_t* quad_ch, int32_t* quad_fid, int cap_quads,
+                    int* n_quads, int* tiles_per_round, float* fill) {
+    SSDR_ARG(taps && work && n_quads && batch >= 1 && n_sm >= 1, "bad argument");
+    std::vector<int4> qc;
+    std::vector<int> qf;
+    double f = 0.0;
+    demod_plan_rounds(taps, work, batch, (size_t)demod_tc_tiles(), (size_t)n_sm, true, qc, qf, &f);
+    *n_quads = (int)qc.size();
+    if (tiles_per_round) *tiles_per_round = demod_tc_tiles();
+    if (fill) *fill = (float)f;
+    if (quad_ch && quad_fid) {
+        SSDR_ARG((size_t)cap_quads >= qc.size(), "capacity %d < %zu quads", cap_quads, qc.size());
+        for (size_t i = 0; i < qc.size(); ++i) {
+            quad_ch[4 * i] = qc[i].x; quad_ch[4 * i + 1] = qc[i].y; quad_ch[4 * i + 2] = qc[i].z; quad_ch[4 * i + 3] = qc[i].w;
+            quad_fid[i] = qf[i];
+        }
+    }
+    return SSDR_OK;
+}
+
+static int demod_build_quads(ssdr_demod_t h) {
+    std::vector<int4> qc;
+    std::vector<int> qf;
+    const size_t tiles = (size_t)demod_tc_tiles();
+    demod_plan_rounds(h->h_taps.data(), h->h_work.data(), h->batch, tiles, (size_t)sm_count(),
+                      std::getenv("SSDR_DEMOD_NO_TAIL_SPLIT") == nullptr, qc, qf, &h->quad_fill);
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid);
     h->d_quad_ch = nullptr; h->d_quad_fid = nullptr;

@@ -61,6 +61,19 @@ def demod_params(mode="usb", lc=None, hc=None, f_off=0.0, on=True, hang=False, t
     return p
 
 
+def demod_plan(params, n_sm=148):
+    """Work plan of the tcgen05 FIR engine for a list of ``demod_params`` (host only, no device needed): returns
+    ``(quad_ch int32[n_quads, 4], quad_fid int32[n_quads], tiles_per_round, fill)`` -- see ``ssdr_demod_plan``."""
+    B = len(params)
+    taps = np.ascontiguousarray([[p.taps[i] for i in range(_lib.FIR_TAPS)] for p in params], np.float32)
+    work = np.ascontiguousarray([p.mode * 4 + p.agc_on * 2 + p.agc_hang for p in params], np.int32)
+    n, tiles, fill = C.c_int(), C.c_int(), C.c_float()
+    check(lib.ssdr_demod_plan(ptr(taps), ptr(work), B, int(n_sm), None, None, 0, C.byref(n), C.byref(tiles), C.byref(fill)))
+    qc, qf = np.empty((n.value, 4), np.int32), np.empty(n.value, np.int32)
+    check(lib.ssdr_demod_plan(ptr(taps), ptr(work), B, int(n_sm), ptr(qc), ptr(qf), n.value, C.byref(n), C.byref(tiles), C.byref(fill)))
+    return qc, qf, tiles.value, fill.value
+
+
 class DemodBank:
     """B channels of IQ @12 kHz -> PCM @12 kHz (float32 + int16) and per-frame RSSI."""
 
