@@ -15,12 +15,15 @@
 //     c rows further up.  The operand is stored as "mini-streams" of 12 rows (4 history blocks + 8 blocks) per 8-row
 //     group, 128-byte swizzle applied on absolute address bits, and the descriptor start address moves by c * 128 bytes
 //     with SBO = 12 rows (scripts/ubench/tcgen05_shift_probe.cu pins that this is what the hardware computes).
-//   * float32 accuracy from TF32 tensor cores: x = hi + lo (cvt.rna.tf32), D = A_hi [B_hi | B_lo] + A_lo B_hi -- two MMAs
-//     per K step (N = 64 and N = 32; the A operand is the larger one, so it is read twice, not three times), the two
-//     column halves are added after the TMEM read-back.  Relative RMS error vs float64 ~9e-7 (tolerance 1e-5).
+//   * float32 accuracy from TF32 tensor cores: x = hi + lo (cvt.rna.tf32), D = A_hi [B_hi | B_lo] + A_lo B_hi.  The first
+//     product is one kind::tf32 MMA per K step of 8 (N = 64; the two column halves are added after the TMEM read-back).
+//     The correction A_lo B_hi is ~2^-12 of the result and needs only a few bits: both factors go to the tensor core
+//     as bfloat16 (kind::f16, K step of 16, same fp32 accumulator) -- half the operand bytes of a TF32 MMA and a
+//     12 KB instead of a 24 KB copy of the rows.  Relative RMS error vs float64 ~1e-6 (tolerance 1e-5).
 //   * MMAs are issued by one thread per tile, completion comes back through tcgen05.commit -> mbarrier.  Two TMEM
 //     accumulators per tile: while the MMAs of frame b run, the tile's warps run the back end of frame b - 1, and the
 //     other tiles of the CTA mix / detect as well.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -55,10 +58,17 @@ constexpr unsigned ROWB = 128;            // one 32-sample block of floats
 constexpr unsigned GROWS = 12;            // rows per mini-stream: 4 history blocks + 8 blocks
 constexpr unsigned GRPB = GROWS * ROWB;   // 1536 bytes = SBO of the A operand
 constexpr unsigned CHB = 4 * GRPB;        // per channel: re octets 0, 1 then im octets 0, 1
-constexpr unsigned A_BYTES = WARPS * CHB; // 24576 per precision part
+constexpr unsigned A_BYTES = WARPS * CHB; // 24576: the hi (TF32) part of the rows, 128-byte swizzle
+// the lo part of the rows as bfloat16, no swizzle: 16-byte K chunks (8 samples) in four planes, row r of a plane at r * 16
+constexpr unsigned A16_ROWS = 4 * WARPS * GROWS;          // 192 rows per tile
+constexpr unsigned A16_LBO = A16_ROWS * 16 + 16;          // plane pitch (3088: +16 spreads the planes over the banks)
+constexpr unsigned A16_BYTES = 13 * 1024;                 // 4 planes, rounded so that the next tile's hi part stays 1024-aligned
+constexpr unsigned TILE_BYTES = A_BYTES + A16_BYTES;
+constexpr unsigned B16_LBO = 4 * 128;                     // B_hi as bfloat16, no swizzle: K chunk of 8 -> 32 rows x 16 bytes
+constexpr unsigned B16_BYTES = 20 * B16_LBO;              // 10240
 constexpr unsigned B_ATOM = 8 * 1024;     // per K chunk: 32 rows of B_hi (4 groups) then 32 rows of B_lo
 constexpr unsigned B_BYTES = KCH * B_ATOM;
-constexpr unsigned SMEM_BYTES = TILES * 2 * A_BYTES + B_BYTES + 1024;   // + alignment slack
+constexpr unsigned SMEM_BYTES = B_BYTES + B16_BYTES + TILES * TILE_BYTES + 1024;   // + alignment slack
 constexpr unsigned TMEM_COLS = TILES > 2 ? 512 : 256;       // two accumulators of 64 columns per tile, allocation is a power of two
 
 __device__ __forceinline__ unsigned swz(unsigned off) { return off ^ (((off >> 7) & 7u) << 4); }   // off from a 1024-aligned base
@@ -73,9 +83,28 @@ __device__ __forceinline__ uint64_t desc_sw128(unsigned addr, unsigned sbo) {
     d |= (uint64_t)2 << 61;                                   // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint64_t desc_none(unsigned addr, unsigned lbo, unsigned sbo) {     // no swizzle, K-major
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;               // LBO: next 16-byte K chunk
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;               // SBO: next 8-row group
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32 (2) or BF16 (1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 __device__ __forceinline__ constexpr unsigned idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+__device__ __forceinline__ constexpr unsigned idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(unsigned tmem, uint64_t da, uint64_t db, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ unsigned pack_bf16(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const unsigned*>(&v);
 }
 __device__ __forceinline__ void mma_tf32(unsigned tmem, uint64_t da, uint64_t db, unsigned idesc, unsigned accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -112,9 +141,11 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
     unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);          // 1024-aligned: swizzle phase = offset bits
     const int tid = threadIdx.x, lane = tid & 31, tile = tid >> 7, warp = (tid >> 5) & 3;     // warp = TMEM lane quarter
     unsigned char* sB = base;
-    unsigned char* sAh = base + B_BYTES + (unsigned)tile * 2 * A_BYTES;
-    unsigned char* sAl = sAh + A_BYTES;
-    const unsigned aB = (unsigned)__cvta_generic_to_shared(sB), aAh = aB + B_BYTES + (unsigned)tile * 2 * A_BYTES, aAl = aAh + A_BYTES;
+    unsigned char* sB16 = base + B_BYTES;
+    unsigned char* sAh = base + B_BYTES + B16_BYTES + (unsigned)tile * TILE_BYTES;
+    unsigned char* sA16 = sAh + A_BYTES;
+    const unsigned aB = (unsigned)__cvta_generic_to_shared(sB), aB16 = aB + B_BYTES, aAh = aB16 + B16_BYTES + (unsigned)tile * TILE_BYTES,
+                   aA16 = aAh + A_BYTES;
     const unsigned barp = (unsigned)__cvta_generic_to_shared(&sh.bar[tile]);
     const bool issuer = (tid & 127) == 0;                   // initialises the tile's barrier
 
@@ -133,13 +164,16 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
     unsigned phase = 0;
 
     const int nblk = kp.n_samples / FR;
-    const unsigned wch = (unsigned)warp * CHB;              // this warp's channel slot inside A_hi / A_lo
+    const unsigned wch = (unsigned)warp * CHB;              // this warp's channel slot in the array of 128-byte rows
     int cur_fid = -1;
 
-    auto put = [&](unsigned off, float x) {                 // x -> (hi, lo) at swizzled offset off of both A parts
+    // off = byte offset of a sample in the (unswizzled) array of 128-byte rows; its bfloat16 twin lives in plane
+    // (sample >> 3) at row * 16 + (sample & 7) * 2
+    auto a16 = [](unsigned off) -> unsigned { return ((off >> 5) & 3u) * A16_LBO + (off >> 7) * 16u + ((off >> 2) & 7u) * 2u; };
+    auto put = [&](unsigned off, float x) {                 // x -> hi (TF32) into the swizzled rows, lo (bfloat16) into the planes
         const float hi = tf32_hi(x);
-        *reinterpret_cast<float*>(sAh + off) = hi;
-        *reinterpret_cast<float*>(sAl + off) = x - hi;      // exact; the tensor core keeps its leading 11 bits
+        *reinterpret_cast<float*>(sAh + swz(off)) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(sA16 + a16(off)) = __float2bfloat16_rn(x - hi);      // x - hi is exact
     };
 
     // Rounds differ in cost (detector / AGC variant), so CTAs pull them from a counter in the host's order (dearest first)
@@ -161,6 +195,8 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                                      (unsigned)(((kk >> 2) ^ (n & 7)) << 4) + (unsigned)(kk & 3) * 4u;
                 *reinterpret_cast<float*>(sB + off) = hi;
                 *reinterpret_cast<float*>(sB + off + 4096u) = x - hi;
+                *reinterpret_cast<__nv_bfloat16*>(sB16 + (unsigned)(k >> 3) * B16_LBO + (unsigned)(n >> 3) * 128u + (unsigned)(n & 7) * 16u +
+                                                  (unsigned)(k & 7) * 2u) = __float2bfloat16_rn(x);
             }
             __syncthreads();                                // the per-step fence below publishes B to the tensor core
         }
@@ -181,8 +217,8 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 const int idx = 32 * row + lane - 2;        // sample -128 + 32 row + lane; the 126 kept samples start at -126
                 const float2 z = (idx >= 0) ? kp.hist[(size_t)ch * H + idx] : make_float2(0.f, 0.f);
                 const unsigned off = wch + (unsigned)row * ROWB + (unsigned)lane * 4u;
-                put(swz(off), z.x);
-                put(swz(off + 2 * GRPB), z.y);
+                put(off, z.x);
+                put(off + 2 * GRPB, z.y);
             }
         }
         // ---- frame pipeline of a warp: rows of frame b in place -> (last warp of the tile issues the MMAs of frame b) ->
@@ -221,18 +257,18 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
         // Four samples = one 16-byte chunk of a row: block 4 q + (lane >> 3), chunk lane & 7.
         auto put4 = [&](unsigned off, float a0, float a1, float a2, float a3) {
             const float h0 = tf32_hi(a0), h1 = tf32_hi(a1), h2 = tf32_hi(a2), h3 = tf32_hi(a3);
-            *reinterpret_cast<float4*>(sAh + off) = make_float4(h0, h1, h2, h3);
-            *reinterpret_cast<float4*>(sAl + off) = make_float4(a0 - h0, a1 - h1, a2 - h2, a3 - h3);
+            *reinterpret_cast<float4*>(sAh + swz(off)) = make_float4(h0, h1, h2, h3);
+            *reinterpret_cast<uint2*>(sA16 + a16(off)) = make_uint2(pack_bf16(a0 - h0, a1 - h1), pack_bf16(a2 - h2, a3 - h3));
         };
         auto mix_store = [&](const float2 (&y)[SPL]) {
             const unsigned row = (unsigned)lane >> 3, chunk = ((unsigned)lane & 7u) * 16u;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const unsigned off = swz(wch + (unsigned)(q >> 1) * GRPB + (4u + 4u * (q & 1) + row) * ROWB + chunk);
+                const unsigned off = wch + (unsigned)(q >> 1) * GRPB + (4u + 4u * (q & 1) + row) * ROWB + chunk;
                 put4(off, y[4 * q].x, y[4 * q + 1].x, y[4 * q + 2].x, y[4 * q + 3].x);
                 put4(off + 2 * GRPB, y[4 * q].y, y[4 * q + 1].y, y[4 * q + 2].y, y[4 * q + 3].y);
                 if (q == 1) {                               // blocks 4..7 are also the history of octet 1
-                    const unsigned offh = swz(wch + GRPB + row * ROWB + chunk);
+                    const unsigned offh = wch + GRPB + row * ROWB + chunk;
                     put4(offh, y[4].x, y[5].x, y[6].x, y[7].x);
                     put4(offh + 2 * GRPB, y[4].y, y[5].y, y[6].y, y[7].y);
                 }
@@ -283,16 +319,19 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 if (issuer) {
 #endif
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    constexpr unsigned i64 = idesc_tf32(128, 64), i32 = idesc_tf32(128, 32);
+                    constexpr unsigned i64 = idesc_tf32(128, 64), i16 = idesc_bf16(128, 32);
                     const unsigned td = tm + (unsigned)(b & 1) * 64u;
 #pragma unroll 1
                     for (int c = 0; c < KCH; ++c) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {       // K step of 8 samples = 32 bytes inside the swizzled row
+                        for (int j = 0; j < 4; ++j) {       // TF32 K step of 8 samples = 32 bytes inside the swizzled row
                             const unsigned oa = (unsigned)c * ROWB + (unsigned)j * 32u, ob = aB + (unsigned)c * B_ATOM + (unsigned)j * 32u;
-                            const uint64_t db = desc_sw128(ob, 1024u);
-                            mma_tf32(td, desc_sw128(aAh + oa, GRPB), db, i64, (c | j) != 0);       // A_hi [B_hi | B_lo] -> columns 0..63
-                            mma_tf32(td, desc_sw128(aAl + oa, GRPB), db, i32, 1u);                  // A_lo B_hi -> columns 0..31
+                            mma_tf32(td, desc_sw128(aAh + oa, GRPB), desc_sw128(ob, 1024u), i64, (c | j) != 0);     // A_hi [B_hi | B_lo] -> columns 0..63
+                        }
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {       // bfloat16 K step of 16 samples = two planes; rows shifted by c like the hi part
+                            mma_f16(td, desc_none(aA16 + (unsigned)(2 * j) * A16_LBO + (unsigned)c * 16u, A16_LBO, GROWS * 16u),
+                                    desc_none(aB16 + (unsigned)(4 * c + 2 * j) * B16_LBO, B16_LBO, 128u), i16, 1u);               // A_lo B_hi -> columns 0..31
                         }
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(barp) : "memory");
@@ -312,13 +351,20 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (active) {
                 // the frame's last four blocks become the history of the next frame (the MMAs of frame b have completed)
-                const unsigned row = (unsigned)lane >> 3, chunk = (unsigned)lane & 7u;
+                {
+                    const unsigned row = (unsigned)lane >> 3, chunk = (unsigned)lane & 7u;
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {
-                    const unsigned src = swz(wch + (unsigned)part * 2 * GRPB + GRPB + (8 + row) * ROWB + chunk * 16u);
-                    const unsigned dst = swz(wch + (unsigned)part * 2 * GRPB + row * ROWB + chunk * 16u);
-                    *reinterpret_cast<float4*>(sAh + dst) = *reinterpret_cast<const float4*>(sAh + src);
-                    *reinterpret_cast<float4*>(sAl + dst) = *reinterpret_cast<const float4*>(sAl + src);
+                    for (int part = 0; part < 2; ++part) {
+                        const unsigned src = swz(wch + (unsigned)part * 2 * GRPB + GRPB + (8 + row) * ROWB + chunk * 16u);
+                        const unsigned dst = swz(wch + (unsigned)part * 2 * GRPB + row * ROWB + chunk * 16u);
+                        *reinterpret_cast<float4*>(sAh + dst) = *reinterpret_cast<const float4*>(sAh + src);
+                    }
+                }
+                {                                           // bfloat16 planes: 2 parts x 4 rows x 4 planes = one 16-byte chunk per lane
+                    const unsigned part = (unsigned)lane >> 4, row = ((unsigned)lane >> 2) & 3u, plane = (unsigned)lane & 3u;
+                    const unsigned g0 = (unsigned)warp * 4u + part * 2u;
+                    *reinterpret_cast<uint4*>(sA16 + plane * A16_LBO + (g0 * GROWS + row) * 16u) =
+                        *reinterpret_cast<const uint4*>(sA16 + plane * A16_LBO + ((g0 + 1u) * GROWS + 8u + row) * 16u);
                 }
                 __syncwarp();
 #if !SSDR_TC_EARLYMIX
@@ -329,14 +375,12 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
         }
         if (tile_active) back_end(nblk - 1);
         if (active) {
-            // ---- store per-channel state: the last 126 mixed samples (hi + lo is exact) --------------------------------
-            __syncwarp();
-            for (int i = lane; i < H; i += 32) {
-                const int m = i + 2;
-                const unsigned off = swz(wch + (unsigned)(m >> 5) * ROWB + (unsigned)(m & 31) * 4u);
-                const unsigned offi = swz(wch + 2 * GRPB + (unsigned)(m >> 5) * ROWB + (unsigned)(m & 31) * 4u);
-                kp.hist[(size_t)ch * H + i] = make_float2(*reinterpret_cast<const float*>(sAh + off) + *reinterpret_cast<const float*>(sAl + off),
-                                                          *reinterpret_cast<const float*>(sAh + offi) + *reinterpret_cast<const float*>(sAl + offi));
+            // ---- store per-channel state: the last 126 mixed samples, exact, from the mixer output of the last frame
+            // (y[12 + i] = sample 384 + 4 lane + i)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = 4 * lane + i - 2;
+                if (idx >= 0) kp.hist[(size_t)ch * H + idx] = y[12 + i];
             }
             demod_regs_store(st, stp, lane);
         }
