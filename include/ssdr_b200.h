@@ -182,7 +182,7 @@ int ssdr_demod_destroy(ssdr_demod_t h);
 int ssdr_demod_set(ssdr_demod_t h, int first_channel, int count, const ssdr_demod_params_t* params);
 int ssdr_demod_reset(ssdr_demod_t h);   /* zero all per-channel streaming state */
 /* FIR engine of the fused kernel.  FFMA: direct form on the fp32 pipe (one warp per channel).  TCGEN05: the FIR as a
- * Toeplitz GEMM on the 5th-generation tensor cores (3 x TF32 split, accumulators in TMEM); four channels that share a
+ * Toeplitz GEMM on the 5th-generation tensor cores (TF32 + bfloat16 split, accumulators in TMEM); four channels that share a
  * filter (bitwise-equal taps) make one tile, so it pays when channels share pass-band widths.  AUTO (default): TCGEN05
  * when at least half of the tile rows would carry a channel, else FFMA.  Same per-channel state, same outputs to the
  * demodulator's tolerance (1e-5 relative RMS); engines may be switched between calls.  No reference counterpart (the

@@ -40,7 +40,8 @@
 #define SSDR_TC_TILES 3           // tiles (groups of four warps) per CTA
 #endif
 #ifndef SSDR_TC_EARLYMIX
-#define SSDR_TC_EARLYMIX 0        // 1: mixer arithmetic of frame b + 1 before the wait for the MMAs of frame b; 0: after it
+#define SSDR_TC_EARLYMIX 0        // 1: mixer arithmetic of frame b + 1 before the wait for the MMAs of frame b (parked in
+                                  //    shared memory across the wait); 0: after it.  Measured: 1 is 13 % slower.
 #endif
 
 namespace ssdr {
@@ -68,7 +69,8 @@ constexpr unsigned B16_LBO = 4 * 128;                     // B_hi as bfloat16, n
 constexpr unsigned B16_BYTES = 20 * B16_LBO;              // 10240
 constexpr unsigned B_ATOM = 8 * 1024;     // per K chunk: 32 rows of B_hi (4 groups) then 32 rows of B_lo
 constexpr unsigned B_BYTES = KCH * B_ATOM;
-constexpr unsigned SMEM_BYTES = B_BYTES + B16_BYTES + TILES * TILE_BYTES + 1024;   // + alignment slack
+constexpr unsigned PARK_BYTES = SSDR_TC_EARLYMIX ? 32 * SPL * 8 : 0;      // per warp: the mixer output of the next frame, thread-private
+constexpr unsigned SMEM_BYTES = B_BYTES + B16_BYTES + TILES * (TILE_BYTES + WARPS * PARK_BYTES) + 1024;   // + alignment slack
 constexpr unsigned TMEM_COLS = TILES > 2 ? 512 : 256;       // two accumulators of 64 columns per tile, allocation is a power of two
 
 __device__ __forceinline__ unsigned swz(unsigned off) { return off ^ (((off >> 7) & 7u) << 4); }   // off from a 1024-aligned base
@@ -144,6 +146,7 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
     unsigned char* sB16 = base + B_BYTES;
     unsigned char* sAh = base + B_BYTES + B16_BYTES + (unsigned)tile * TILE_BYTES;
     unsigned char* sA16 = sAh + A_BYTES;
+    float2* park = reinterpret_cast<float2*>(base + B_BYTES + B16_BYTES + TILES * TILE_BYTES + (unsigned)(tid >> 5) * PARK_BYTES) + lane;
     const unsigned aB = (unsigned)__cvta_generic_to_shared(sB), aB16 = aB + B_BYTES, aAh = aB16 + B16_BYTES + (unsigned)tile * TILE_BYTES,
                    aA16 = aAh + A_BYTES;
     const unsigned barp = (unsigned)__cvta_generic_to_shared(&sh.bar[tile]);
@@ -300,7 +303,14 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             demod_frame_tail<LanesPaired>(acc, cp, kp, ch, b, (size_t)ch * kp.pitch + (size_t)b * FR, st);
         };
         float2 y[SPL];
-        if (tile_active && active) { mix_compute(0, y); mix_store(y); }
+        if (tile_active && active) {
+            mix_compute(0, y);
+            mix_store(y);
+#if SSDR_TC_EARLYMIX
+#pragma unroll
+            for (int i = 12; i < SPL; ++i) park[32 * i] = y[i];       // the slots always hold the newest frame's tail (history)
+#endif
+        }
         for (int b = 0; tile_active && b < nblk; ++b) {
             // This warp's rows of frame b are in place: publish them to the tensor core (async proxy), order this warp's
             // earlier TMEM reads before the MMAs, and count the warp in.  No warp waits for another one here: the LAST
@@ -340,7 +350,11 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             __syncwarp();
             if (b > 0) back_end(b - 1);                     // overlaps the MMAs of frame b
 #if SSDR_TC_EARLYMIX
-            if (active && b + 1 < nblk) mix_compute(b + 1, y);
+            if (active && b + 1 < nblk) {                   // ... and so does the mixer of frame b + 1; its output waits in shared
+                mix_compute(b + 1, y);                      // memory (thread-private slots), not in registers
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) park[32 * i] = y[i];
+            }
 #endif
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
@@ -367,10 +381,15 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                         *reinterpret_cast<const uint4*>(sA16 + plane * A16_LBO + ((g0 + 1u) * GROWS + 8u + row) * 16u);
                 }
                 __syncwarp();
-#if !SSDR_TC_EARLYMIX
-                if (b + 1 < nblk) mix_compute(b + 1, y);
+                if (b + 1 < nblk) {
+#if SSDR_TC_EARLYMIX
+#pragma unroll
+                    for (int i = 0; i < SPL; ++i) y[i] = park[32 * i];
+#else
+                    mix_compute(b + 1, y);
 #endif
-                if (b + 1 < nblk) mix_store(y);
+                    mix_store(y);
+                }
             }
         }
         if (tile_active) back_end(nblk - 1);
@@ -380,7 +399,11 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int idx = 4 * lane + i - 2;
+#if SSDR_TC_EARLYMIX
+                if (idx >= 0) kp.hist[(size_t)ch * H + idx] = park[32 * (12 + i)];
+#else
                 if (idx >= 0) kp.hist[(size_t)ch * H + idx] = y[12 + i];
+#endif
             }
             demod_regs_store(st, stp, lane);
         }
