@@ -8,8 +8,8 @@
 // i.e. D[128 x 32] = A[128 x 160] B[160 x 32] with one ROW per (block, re | im) and the taps as a Toeplitz B operand.
 // A tile step covers one 512-sample frame of FOUR channels that share a filter (host-side grouping): 4 channels x
 // {re, im} x 16 blocks = 128 rows = one M = 128 tile, and warp w reads back exactly its own channel (TMEM lanes 32 w ..).
-// A CTA runs TILES such tiles side by side (4 warps each, own operand buffer, own TMEM columns, own barriers) on one
-// shared B operand: the mixer / detector / AGC code is latency-bound, so the SM needs the 12 warps.
+// A CTA runs TILES = 4 such tiles side by side (4 warps each, own operand buffer, own TMEM columns, own barriers) on one
+// shared B operand: the mixer / detector / AGC code is latency-bound, so the SM needs the 16 warps (128 registers each).
 //
 //   * One copy of the signal serves all five K chunks: K chunk c of row i is block i - 4 + c, i.e. the same array read
 //     c rows further up.  The operand is stored as "mini-streams" of 12 rows (4 history blocks + 8 blocks) per 8-row
@@ -37,7 +37,7 @@
 #define SSDR_TC_LASTARRIVER 1     // 1: the last warp of a tile to arrive issues the MMAs; 0: tile barrier, fixed issuer thread
 #endif
 #ifndef SSDR_TC_TILES
-#define SSDR_TC_TILES 3           // tiles (groups of four warps) per CTA
+#define SSDR_TC_TILES 4           // tiles (groups of four warps) per CTA: 16 warps at 128 registers
 #endif
 #ifndef SSDR_TC_EARLYMIX
 #define SSDR_TC_EARLYMIX 0        // 1: mixer arithmetic of frame b + 1 before the wait for the MMAs of frame b (parked in
@@ -146,7 +146,9 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
     unsigned char* sB16 = base + B_BYTES;
     unsigned char* sAh = base + B_BYTES + B16_BYTES + (unsigned)tile * TILE_BYTES;
     unsigned char* sA16 = sAh + A_BYTES;
+#if SSDR_TC_EARLYMIX
     float2* park = reinterpret_cast<float2*>(base + B_BYTES + B16_BYTES + TILES * TILE_BYTES + (unsigned)(tid >> 5) * PARK_BYTES) + lane;
+#endif
     const unsigned aB = (unsigned)__cvta_generic_to_shared(sB), aB16 = aB + B_BYTES, aAh = aB16 + B16_BYTES + (unsigned)tile * TILE_BYTES,
                    aA16 = aAh + A_BYTES;
     const unsigned barp = (unsigned)__cvta_generic_to_shared(&sh.bar[tile]);

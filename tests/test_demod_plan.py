@@ -38,9 +38,13 @@ def test_plan_uniform_batch_splits_the_tail_wave():
     assert fill == 1.0 and len(set(qf.tolist())) == 1
     rounds = qc.reshape(-1, tiles, 4)
     per_round = (rounds[:, :, 0] >= 0).sum(1)
-    full = int((per_round == tiles).sum())
-    assert full == (B // (4 * tiles)) // n_sm * n_sm                      # whole waves of full rounds ...
-    assert np.all(per_round[full:] == 1) and len(per_round) - full == B // 4 - full * tiles   # ... then one quad per CTA
+    n_quads = B // 4
+    full = (n_quads // tiles) // n_sm * n_sm                              # whole waves of full rounds ...
+    assert np.all(per_round[:full] == tiles)
+    tail_quads = n_quads - full * tiles                                  # ... then the rest spread over (nearly) all SMs
+    per = -(-tail_quads // n_sm)
+    assert per < tiles and np.all(per_round[full:] <= per) and per_round[full:].sum() == tail_quads
+    assert len(per_round) - full == -(-tail_quads // per)
 
 
 def test_plan_mixed_modes_cost_order_and_padding():
