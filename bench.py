@@ -374,8 +374,8 @@ def main():
             d = {"workload": workload, "value": world * ns / dms / 1e3, "unit": "Msamples/s", "ms_per_step": dms,
                  "hbm_gbs": ns * 12 / dms / 1e6, "engine": best, "engines": per_engine,
                  "bound": "HBM bound 12 B/sample; ffma engine: fp32 pipe (direct-form 127-tap FIR, 4*127+~30 flop/sample); tcgen05 "
-                          "engine: FIR as a 3xTF32 Toeplitz GEMM (shared-memory operand reads of the tensor core) + the fp32/MUFU "
-                          "mixer, detector and AGC"}
+                          "engine: FIR as a split-precision (TF32 + bfloat16) Toeplitz GEMM (bound by the tensor core's shared-memory operand "
+                          "reads) + the fp32/MUFU mixer, detector and AGC"}
             if not args.no_e2e:
                 hq = S.PinnedArray((B, ns_ch), np.complex64)
                 ho = S.PinnedArray((B, ns_ch), np.float32)
