@@ -367,7 +367,8 @@ def main():
                     db.time_dev(dq.ptr, S.SSDR_IQ_CF32, ns_ch, dout.ptr, None, 1)
                 barrier()
                 ems = max_over_ranks(db.time_dev(dq.ptr, S.SSDR_IQ_CF32, ns_ch, dout.ptr, None, 5) / 5)
-                per_engine[eng] = {"value": world * ns / ems / 1e3, "unit": "Msamples/s", "ms_per_step": ems, "hbm_gbs": ns * 12 / ems / 1e6}
+                per_engine[eng] = {"value": world * ns / ems / 1e3, "unit": "Msamples/s", "ms_per_step": ems, "hbm_gbs": ns * 12 / ems / 1e6,
+                                   "hbm_frac": ns * 12 / ems / 1e6 / peaks()[0]}
             best = args.demod_engine
             db.set_engine(best)
             dms = per_engine[best]["ms_per_step"]

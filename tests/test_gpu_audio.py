@@ -163,6 +163,26 @@ def test_demod_engines_agree_and_interleave(ssdr):
     bank.close()
 
 
+def test_demod_auto_engine_picks_by_tile_fill(ssdr):
+    """The default engine ("auto") is the tcgen05 kernel when the tensor-core tiles are at least half full (channels that
+    share a filter) and the FFMA kernel otherwise -- bit for bit the explicit engine's output in both cases."""
+    n = 512 * 4
+    for params, expect in (([ssdr.demod_params("usb")] * 8, "tcgen05"),
+                           ([ssdr.demod_params("usb", hc=2500.0 + 100 * b) for b in range(3)], "ffma")):
+        B = len(params)
+        iq = np.stack([tier_u.synth_demod_iq("usb", n, seed=70 + b) for b in range(B)])
+        out = {}
+        for eng in ("auto", "ffma", "tcgen05"):
+            bank = ssdr.DemodBank(B, n, engine=eng)
+            bank.set_params(0, params)
+            out[eng] = bank.process(iq)["pcm_f32"]
+            bank.close()
+        other = "ffma" if expect == "tcgen05" else "tcgen05"
+        assert np.array_equal(out["auto"], out[expect])
+        assert not np.array_equal(out["auto"], out[other])          # the engines differ in the last bits
+        assert _rel_rms(out["ffma"].astype(np.float64), out["tcgen05"].astype(np.float64)) < RMS_TOL
+
+
 def test_interp_reference_golden(ssdr):
     """kiwi_sound.play_buffer (utils_supersdr.py:1121-1138) fixtures from the unmodified reference:
     int16 stereo within 1 LSB (np.convolve's summation order is BLAS-dependent)."""
