@@ -20,9 +20,13 @@
 //     The correction A_lo B_hi is ~2^-12 of the result and needs only a few bits: both factors go to the tensor core
 //     as bfloat16 (kind::f16, K step of 16, same fp32 accumulator) -- half the operand bytes of a TF32 MMA and a
 //     12 KB instead of a 24 KB copy of the rows.  Relative RMS error vs float64 ~1e-6 (tolerance 1e-5).
-//   * MMAs are issued by one thread per tile, completion comes back through tcgen05.commit -> mbarrier.  Two TMEM
-//     accumulators per tile: while the MMAs of frame b run, the tile's warps run the back end of frame b - 1, and the
-//     other tiles of the CTA mix / detect as well.
+//     tests/test_tc_split_model.py restates this arithmetic on the CPU (error budget; why bfloat16 and not float16).
+//   * No warp waits for another one to hand a frame over: each warp publishes its rows and counts itself in, the LAST
+//     of the tile's four warps to arrive issues the tile's 30 MMAs (one thread); completion comes back through
+//     tcgen05.commit -> mbarrier.  Two TMEM accumulators per tile: while the MMAs of frame b run, the tile's warps run
+//     the back end of frame b - 1, and the other tiles of the CTA mix / detect as well.
+//   * Rounds (four quads of one filter) are pulled from a global counter in the host's order: dearest detector first,
+//     the last partial wave as narrower rounds (capi.cu: demod_plan_rounds).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
