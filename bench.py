@@ -37,6 +37,25 @@ DEMOD_B, DEMOD_S = 4096, 512 * 64
 METRIC = "IQ Msamples/s, batched 16384-pt waterfall FFT + log-mag + 10x time-binning + colour row"
 WORKLOAD = "config[1]: batch=4096 ch/GPU x 10 frames x 16384-pt complex64 IQ -> uint8 pixel rows"
 
+# 64-bit sums of the float32 bit patterns of the demodulator output for the bench inputs (seed 99 + rank 0, state reset,
+# one call), per engine -- pinned after tests/test_gpu_bench_shapes.py verified those very outputs against the float64
+# oracle on a B200.  bench.py prints the checksum it measures and whether it equals the pinned one.
+DEMOD_CHECKSUMS = {
+    "config3_usb": {"ffma": None, "tcgen05": None},
+    "config4_mixed": {"ffma": None, "tcgen05": None},
+}
+
+
+def config_dict(channels):
+    """The workload description both arms print (identical keys and values for the same workload)."""
+    return {"workload": WORKLOAD, "channels_per_gpu": channels, "n_avg": N_AVG, "nfft": NFFT,
+            "iq_format": "complex64, int16-count units (8 B/sample)",
+            "sharding": "channels across ranks, no collective", "l2": "input batch 5.4 GB per GPU >> 126 MB L2"}
+
+
+def pcm_checksum(f32):
+    return int(np.ascontiguousarray(f32).view(np.uint32).astype(np.uint64).sum())
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -100,11 +119,14 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU statement of the workload (oracle/ -- allowed here only as the reported baseline)
 # ---------------------------------------------------------------------------------------------------
-def cpu_waterfall_rows(iq, threads):
-    """numpy/scipy path: window -> scipy.fft (all cores) -> |X|^2 -> 10 log10 -> Kiwi byte -> mean over
-    frames -> the reference's spectrum_db2col arithmetic per row (oracle.tier_p)."""
+def cpu_waterfall_rows(iq, threads=1, wire=False):
+    """numpy/scipy path: [K6 unpack ->] window -> scipy.fft -> |X|^2 -> 10 log10 -> Kiwi byte -> mean over frames -> the
+    reference's spectrum_db2col arithmetic per row (oracle.tier_p)."""
     import scipy.fft
     from oracle import tier_p, tier_u
+    if wire:                                                  # big-endian int16 I,Q (kiwi/client.py:449-453)
+        raw = np.frombuffer(iq, dtype=">i2").reshape(iq.shape[:-1] + (2,)).astype(np.float32)
+        iq = raw[..., 0] + 1j * raw[..., 1]
     B, n, N = iq.shape
     w = tier_u.hann(N).astype(np.float32)
     X = scipy.fft.fft(iq * w, axis=-1, workers=threads)
@@ -120,49 +142,118 @@ def cpu_waterfall_rows(iq, threads):
     return px
 
 
+_POOL_TILE = {}
+
+
+def _pool_init(ch_per_task, wire):
+    """Worker start-up: every worker synthesises its own tile (nothing big crosses the pipe)."""
+    from oracle import tier_u
+    base = tier_u.synth_batch(4, N_AVG, NFFT, seed=1 + os.getpid() % 97, quantise=wire)
+    tile = np.tile(base, (max(ch_per_task // 4, 1), 1, 1))[:ch_per_task]
+    if wire:
+        tile = np.ascontiguousarray(np.stack([tile.real, tile.imag], -1).astype(">i2")).view(np.uint8).reshape(tile.shape + (4,))
+    _POOL_TILE["t"], _POOL_TILE["wire"] = tile, wire
+    cpu_waterfall_rows(tile[:2], 1, wire)                    # imports, FFT plans
+
+
+def _pool_task(_):
+    px = cpu_waterfall_rows(_POOL_TILE["t"], 1, _POOL_TILE["wire"])
+    return int(px[0, 0])
+
+
+def cpu_pool_throughput(target_s, cores, wire=False, ch_per_task=16, max_channels=None):
+    """Channel shards over a process pool (one single-threaded numpy/scipy pipeline per host core), so
+    that the FFT AND the epilogue run on every core.  Returns (Msamples/s, channels done, seconds)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores, initializer=_pool_init, initargs=(ch_per_task, wire)) as pool:
+        pool.map(_pool_task, range(cores))                   # every worker warm
+        done, t0 = 0, time.perf_counter()
+        while True:
+            pool.map(_pool_task, range(2 * cores), chunksize=1)
+            done += 2 * cores * ch_per_task
+            dt = time.perf_counter() - t0
+            if dt >= target_s or (max_channels and done >= max_channels):
+                break
+    return done * N_AVG * NFFT / dt / 1e6, done, dt
+
+
+def cpu_config1_us(reps=2000):
+    """BASELINE config 1: ONE 1024-point FFT + log-magnitude byte line of one 12 kHz IQ frame, numpy on one core
+    (rng seed 1234, three tones + noise).  Returns microseconds per frame."""
+    from oracle import tier_u
+    x = tier_u.synth_iq(1024, seed=1234)[0]
+    w = tier_u.hann(1024).astype(np.float32)
+    ref = np.float32((1024 * tier_u.FS * 0.5) ** 2)
+
+    def one():
+        X = np.fft.fft(x * w)
+        P = X.real ** 2 + X.imag ** 2
+        with np.errstate(divide="ignore"):
+            return np.fft.fftshift(np.clip(np.rint(10.0 * np.log10(P / ref) + (tier_u.WF_CAL_DB + 255.0)), 0, 255).astype(np.uint8))
+    for _ in range(50):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one()
+    return (time.perf_counter() - t0) / reps * 1e6
+
+
 def cpu_baseline(target_s=12.0):
-    """The numpy/scipy statement on all host cores over a bounded sample: 256-channel tiles of the workload, repeated
-    until about ``target_s`` seconds of CPU work have been timed."""
+    """The numpy/scipy statement on all host cores over a bounded sample (process pool over channel shards) plus the
+    single-thread number and BASELINE config 1."""
     from oracle import tier_u
     cores = os.cpu_count() or 1
-    tile = np.tile(tier_u.synth_batch(8, N_AVG, NFFT, seed=1), (32, 1, 1))        # 256 channels x 10 x 16384
-    cpu_waterfall_rows(tile[:32], cores)                                           # warm-up (imports, FFT plans)
-    done, t0 = 0, time.perf_counter()
-    while True:
-        cpu_waterfall_rows(tile, cores)
-        done += tile.shape[0]
-        dt = time.perf_counter() - t0
-        if dt >= target_s or done >= B_PER_GPU:
-            break
-    return {"value": done * N_AVG * NFFT / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
-            "sample": "%d of 4096 channels x %d x %d (256-channel tiles), scipy.fft(workers=%d) + numpy epilogue + per-row "
-                      "spectrum_db2col restatement (oracle/tier_p.py); %.1f s of CPU work" % (done, N_AVG, NFFT, cores, dt)}
+    v, done, dt = cpu_pool_throughput(target_s, cores)
+    tile = tier_u.synth_batch(4, N_AVG, NFFT, seed=1)
+    cpu_waterfall_rows(tile[:1], 1)
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < 3.0:
+        cpu_waterfall_rows(tile, 1)
+        reps += 1
+    single = reps * 4 * N_AVG * NFFT / (time.perf_counter() - t0) / 1e6
+    return {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "single_thread": {"value": single, "unit": "Msamples/s", "cores": 1},
+            "config1_single_1024pt_frame_us": cpu_config1_us(),
+            "sample": "%d of 4096 channels x %d x %d: %d worker processes x 16-channel shards, each a single-threaded "
+                      "scipy.fft + numpy epilogue + per-row spectrum_db2col restatement (oracle/tier_p.py); %.1f s of CPU "
+                      "work" % (done, N_AVG, NFFT, cores, dt)}
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the CPU statement of the same path on all host cores, bounded sample per step."""
+    """Reference arm: the CPU statement of the same path on all host cores (process pool over channel shards), each
+    step a bounded sample of the workload."""
     if rank != 0:
         return
-    from oracle import tier_u
     cores = os.cpu_count() or 1
-    nch = 128
-    iq = np.tile(tier_u.synth_batch(8, N_AVG, NFFT, seed=7), (16, 1, 1))
-    for _ in range(max(args.warmup, 1)):
-        cpu_waterfall_rows(iq, cores)
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_waterfall_rows(iq, cores)
-    dt = time.perf_counter() - t
+    import multiprocessing as mp
+    ch_per_task = 8
+    nch = 2 * cores * ch_per_task                             # channels per step
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores, initializer=_pool_init, initargs=(ch_per_task, False)) as pool:
+        pool.map(_pool_task, range(cores))
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_pool_task, range(2 * cores), chunksize=1)
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_pool_task, range(2 * cores), chunksize=1)
+        dt = time.perf_counter() - t
     v = nch * N_AVG * NFFT * args.steps / dt / 1e6
-    sample = "%d of %d channels per step (bounded sample), numpy/scipy on %d host cores" % (nch, B_PER_GPU, cores)
+    wire_v, _, _ = cpu_pool_throughput(4.0, cores, wire=True, ch_per_task=ch_per_task)
+    sample = ("%d of %d channels per step (bounded sample): %d worker processes x %d-channel shards, single-threaded "
+              "numpy/scipy pipeline in each" % (nch, B_PER_GPU, cores, ch_per_task))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference repo has no FFT/log-mag code (SURVEY.md s0): this arm is "
-                   "the builder's numpy/scipy statement of the path + the reference's own colour-row arithmetic"},
+        "config": config_dict(args.channels),
+        "note": "the reference repo has no FFT/log-mag code (SURVEY.md s0): this arm is the builder's numpy/scipy statement "
+                "of the path + the reference's own colour-row arithmetic, on every host core",
         "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e_wire_s16be": {"value": wire_v, "unit": "Msamples/s", "note": "same path fed big-endian int16 I/Q (4 B/sample), unpack included"},
+        "config1_single_1024pt_frame_us": cpu_config1_us(),
         "gpu_launches": 0}))
 
 
@@ -179,6 +270,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="developer runs: skip the host-buffer arm")
     ap.add_argument("--no-scatter", action="store_true", help="multi-GPU runs: skip the root-scatter (NCCL) arm")
     ap.add_argument("--channels", type=int, default=B_PER_GPU, help="channels per GPU (default: the BASELINE config)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,6 +290,7 @@ def main():
 
     import supersdr_b200 as S
     S.init(local)
+    numa_node = None if args.no_numa_bind else S._lib.numa_bind()     # pinned buffers + threads next to this GPU's root complex
     B = args.channels
     n_samples = B * N_AVG * NFFT
     iq_dev = S.DeviceBuffer(n_samples * 8)
@@ -308,6 +401,7 @@ def main():
 
     # ---- end-to-end arm: pinned host IQ -> H2D -> kernel -> D2H pixels, every step ----------------------
     e2e = None
+    e2e_wire = None
     checksum = None
     if not args.no_e2e:
         host_iq = S.PinnedArray((B, N_AVG, NFFT), np.complex64)
@@ -326,7 +420,21 @@ def main():
         checksum = int(host_px.array[::257].astype(np.uint64).sum())
         e2e = {"value": world * n_samples * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": n_samples * 8, "d2h_bytes_per_step": B * NFFT + host_sc.nbytes, "steps": e2e_steps,
-               "api": "WaterfallBank.process -> ssdr_wf_process (pinned host buffers)"}
+               "api": "WaterfallBank.process -> ssdr_wf_process (pinned host buffers)",
+               "h2d_gbs_per_rank": n_samples * 8 * e2e_steps / e2e_s / 1e9, "numa_node": numa_node}
+        # the ceiling next to it: a bare pinned-host -> device cudaMemcpy of the same bytes, (a) every rank copying at
+        # once, (b) rank 0 alone (the others idle) -- what PCIe + host memory give, whatever the kernel does
+        def bare_copy():
+            t_ = time.perf_counter()
+            S._lib.check(S.lib.ssdr_memcpy_h2d(iq_dev.ptr, S._lib.ptr(host_iq.array), n_samples * 8))
+            return time.perf_counter() - t_
+        bare_copy()
+        barrier()
+        e2e["h2d_ceiling_all_ranks_gbs"] = n_samples * 8 / max_over_ranks(bare_copy()) / 1e9
+        barrier()
+        alone = bare_copy() if rank == 0 else 0.0
+        barrier()
+        e2e["h2d_ceiling_alone_gbs"] = n_samples * 8 / max_over_ranks(alone) / 1e9
         host_iq.free()
         # the same rows from the Kiwi wire format (big-endian int16 I/Q, kiwi/client.py:449-453): half the bytes over PCIe
         wire_dev = S.DeviceBuffer(n_samples * 4)
@@ -341,9 +449,11 @@ def main():
             bank.process(host_wire.array, want_colour=False, want_spectrum=False, out=out)
         w_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        e2e["wire_s16be"] = {"value": world * n_samples * e2e_steps / w_s / 1e6, "unit": "Msamples/s",
-                             "h2d_bytes_per_step": n_samples * 4, "note": "same workload fed in the Kiwi wire format "
-                             "(int16 big-endian I/Q, unpack fused into the kernel's loads)"}
+        e2e_wire = {"value": world * n_samples * e2e_steps / w_s / 1e6, "unit": "Msamples/s",
+                    "h2d_bytes_per_step": n_samples * 4, "d2h_bytes_per_step": B * NFFT + host_sc.nbytes,
+                    "h2d_gbs_per_rank": n_samples * 4 * e2e_steps / w_s / 1e9,
+                    "note": "same workload fed in the Kiwi wire format (int16 big-endian I/Q, kiwi/client.py:449-453: half "
+                            "the bytes over PCIe, unpack fused into the kernel's loads); the reference arm prints the same key"}
         host_wire.free(); host_px.free()
     clk = clocks.stop()
 
@@ -360,6 +470,28 @@ def main():
             except Exception as e:                        # noqa: BLE001 - reported, not hidden
                 demod[key] = {"workload": workload, "error": "%s: %s" % (type(e).__name__, e)}
 
+        def demod_rooflines(eng, gs):
+            """Both bounds of a demodulator line: HBM (12 B/sample) and the engine's arithmetic pipe."""
+            hbm = {"bound": "hbm", "achieved": gs * 12.0, "peak": peaks()[0], "unit": "GB/s", "frac": gs * 12.0 / peaks()[0]}
+            if eng == "ffma":
+                # 127 taps x (re, im) x 2 flop + ~30 (mixer, detector, AGC) per sample on the fp32 pipe;
+                # peak = 148 SMs x 128 lanes x 2 flop x max SM clock (nominal: no measured fp32 peak in MEASURED_PEAKS.json)
+                fl, pk = 4 * 127 + 30, 148 * 128 * 2 * 1.965e9 / 1e12
+                comp = {"bound": "fp32", "achieved": gs * fl / 1e3, "peak": pk, "unit": "TFLOP/s", "frac": gs * fl / 1e3 / pk,
+                        "peak_source": "nominal 148 x 128 FMA lanes x 1965 MHz"}
+            else:
+                # per frame tile (4 ch x 512 samples): 20 TF32 MMAs M128 N64 K8 + 10 bf16 MMAs M128 N32 K16 -> per sample
+                # 640 TF32 + 320 bf16 MACs = 800 TF32-equivalent MACs (bf16 runs at twice the TF32 rate)
+                fl = 2 * 800
+                pk = None
+                try:
+                    pk = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]) / 2
+                except Exception:
+                    pk = 1590.0 / 2
+                comp = {"bound": "tensor", "achieved": gs * fl / 1e3, "peak": pk, "unit": "TFLOP/s (TF32-equivalent, executed)",
+                        "frac": gs * fl / 1e3 / pk, "peak_source": "half the measured sustained bf16 cuBLAS rate (TF32 = bf16 / 2)"}
+            return {"hbm": hbm, "compute": comp}
+
         def demod_case_run(key, workload, B, ns_ch, params):
             dq = S.DeviceBuffer(B * ns_ch * 8)
             dout = S.DeviceBuffer(B * ns_ch * 4)
@@ -374,8 +506,21 @@ def main():
                     db.time_dev(dq.ptr, S.SSDR_IQ_CF32, ns_ch, dout.ptr, None, 1)
                 barrier()
                 ems = max_over_ranks(db.time_dev(dq.ptr, S.SSDR_IQ_CF32, ns_ch, dout.ptr, None, 5) / 5)
+                gs = ns / ems / 1e6                     # Gsamples/s on this GPU
                 per_engine[eng] = {"value": world * ns / ems / 1e3, "unit": "Msamples/s", "ms_per_step": ems, "hbm_gbs": ns * 12 / ems / 1e6,
-                                   "hbm_frac": ns * 12 / ems / 1e6 / peaks()[0]}
+                                   "hbm_frac": ns * 12 / ems / 1e6 / peaks()[0],
+                                   "roofline": demod_rooflines(eng, gs)}
+                db.reset()                              # checksum of ONE call from zero state (what the parity test verified)
+                db.process_dev(dq.ptr, S.SSDR_IQ_CF32, ns_ch, dout.ptr, None, None)
+                db.sync()
+                ck = pcm_checksum(dout.download(np.float32, (B, ns_ch)))
+                per_engine[eng]["pcm_checksum"] = ck
+                pinned = DEMOD_CHECKSUMS.get(key, {})
+                want = pinned.get(eng) if eng != "auto" else None
+                if eng == "auto":
+                    per_engine[eng]["pcm_checksum_is"] = [e_ for e_ in ("ffma", "tcgen05") if per_engine.get(e_, {}).get("pcm_checksum") == ck]
+                elif want is not None and rank == 0:
+                    per_engine[eng]["pcm_checksum_ok"] = bool(ck == want)
             best = args.demod_engine
             db.set_engine(best)
             dms = per_engine[best]["ms_per_step"]
@@ -426,13 +571,11 @@ def main():
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "channels_per_gpu": B, "n_avg": N_AVG, "nfft": NFFT,
-                   "sharding": "channels across ranks, no collective", "l2": "input batch 5.4 GB per GPU >> 126 MB L2",
-                   "pixel_checksum": checksum},
+        "config": config_dict(B), "pixel_checksum": checksum,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "wf_fft_kernel<14>",
                      "algorithmic_bytes_per_launch": alg_bytes},
-        "e2e": e2e,
+        "e2e": e2e, "e2e_wire_s16be": e2e_wire,
         "gpu_launches": launches, "clocks": clk,
     }
     if scatter is not None:

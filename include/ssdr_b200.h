@@ -12,7 +12,10 @@
  * Conventions: every function returns 0 on success or a negative SSDR_E_* code and records a
  * message retrievable with ssdr_last_error() (thread-local).  Handles are opaque, own their device
  * buffers, per-channel state and one CUDA stream; a handle may be used from any thread but not
- * concurrently.  "host" pointers are ordinary (ideally pinned) host memory, "dev" pointers are
+ * concurrently (every entry point binds the calling thread to the handle's device -- the device current when the
+ * handle was created, i.e. the one ssdr_init selected -- so this holds on every GPU, not only on device 0).
+ * Device pointers passed to the *_dev entry points must be 16-byte aligned (ssdr_dev_alloc returns 256-byte
+ * aligned memory; offset sub-buffers must keep 16-byte alignment), else SSDR_E_ARG.  "host" pointers are ordinary (ideally pinned) host memory, "dev" pointers are
  * device memory obtained from ssdr_dev_alloc() or owned by the caller.  There is NO CPU fallback:
  * without a CUDA device every compute call fails with SSDR_E_CUDA.
  */
@@ -67,6 +70,9 @@ const char* ssdr_last_error(void);
 /* Select the CUDA device for this process (one process per GPU). */
 int ssdr_init(int device);
 int ssdr_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes, char* name, int name_len);
+/* PCI bus id ("0000:1b:00.0") of the selected device: lets a host process place its pinned buffers and threads on the
+ * GPU's NUMA node (/sys/bus/pci/devices/<id>/numa_node) -- supersdr_b200.numa_bind(). */
+int ssdr_device_pci_bus_id(char* bus_id, int len);
 /* Number of kernels this library has launched since load (all handles). */
 uint64_t ssdr_launch_count(void);
 

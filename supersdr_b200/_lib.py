@@ -55,6 +55,7 @@ _PROTOS = {
     "ssdr_last_error": (C.c_char_p, []),
     "ssdr_init": (_i, [_i]),
     "ssdr_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz), C.c_char_p, _i]),
+    "ssdr_device_pci_bus_id": (_i, [C.c_char_p, _i]),
     "ssdr_launch_count": (C.c_uint64, []),
     "ssdr_ipc_export": (_i, [_vp, _vp]),
     "ssdr_ipc_open": (_i, [_vp, _pvp]),
@@ -143,6 +144,30 @@ def init(device=None):
         device = int(os.environ.get("LOCAL_RANK", "0"))
     check(lib.ssdr_init(int(device)))
     _initialised = True
+
+
+def numa_bind():
+    """Pin this process's threads to the CPUs of the selected GPU's NUMA node, so that pinned host buffers allocated
+    afterwards (first touch) and the threads that fill them sit next to the GPU's PCIe root complex.  With several
+    ranks on one host this keeps each rank's H2D stream off the inter-socket link.  Returns the node (or None when the
+    platform does not say / has one node)."""
+    buf = C.create_string_buffer(32)
+    check(lib.ssdr_device_pci_bus_id(buf, 32))
+    bus = buf.value.decode().lower()
+    try:
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError):
+        return None
 
 
 def ptr(a):

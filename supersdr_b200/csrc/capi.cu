@@ -22,6 +22,27 @@ namespace ssdr {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 static int g_sm_count = 0;
+// The CUDA device is a per-thread setting of the runtime.  ssdr_init records the process's selection; every handle
+// records the device it was created on; every entry point binds the calling thread to that device first, so a handle
+// (and the stateless entry points) work from any thread -- the reference's waterfall / sound / PortAudio-callback
+// threads (utils_supersdr.py:879,1106,1150) included -- not only from the thread that called ssdr_init.
+std::atomic<int> g_device{-1};
+
+int bind_device(int device) {
+    if (device < 0) return SSDR_OK;              // ssdr_init was never called: the runtime's default (device 0)
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e == cudaSuccess && cur != device) e = cudaSetDevice(device);
+    if (e != cudaSuccess) { set_error("cannot bind the calling thread to device %d: %s", device, cudaGetErrorString(e)); return SSDR_E_CUDA; }
+    return SSDR_OK;
+}
+#define SSDR_BIND(dev)                                       \
+    do {                                                     \
+        int rc_bind__ = ssdr::bind_device(dev);              \
+        if (rc_bind__) return rc_bind__;                     \
+    } while (0)
+#define SSDR_BIND_H(h) SSDR_BIND((h)->device)
+#define SSDR_BIND_G() SSDR_BIND(ssdr::g_device.load())
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -57,6 +78,7 @@ using namespace ssdr;
 // handles
 // =============================================================================================
 struct ssdr_wf {
+    int device = -1;                  // the device this handle lives on (bound at every entry point)
     int nfft = 0, batch = 0, n_avg = 1, window = 1, p_lo = 0;
     int remote_input = 0;             // device inputs live in a peer GPU's memory (ssdr_wf_set_remote_input)
     float p_gamma = 0.f;
@@ -85,6 +107,7 @@ struct ssdr_wf {
 };
 
 struct ssdr_demod {
+    int device = -1;                  // the device this handle lives on (bound at every entry point)
     int batch = 0, max_samples = 0;
     DemodChan* d_chan = nullptr;
     DemodState* d_state = nullptr;
@@ -112,6 +135,7 @@ struct ssdr_demod {
 };
 
 struct ssdr_interp {
+    int device = -1;                  // the device this handle lives on (bound at every entry point)
     int batch = 0, ratio = 0, n_taps = 0, max_samples = 0, hs = 0, cur = 0;
     double* d_taps = nullptr;
     double* d_hist[2] = {nullptr, nullptr};
@@ -124,6 +148,7 @@ struct ssdr_interp {
 };
 
 struct ssdr_wf_image {
+    int device = -1;                  // the device this handle lives on (bound at every entry point)
     int batch = 0, H = 0, W = 0, head = 0;
     long long run_index = 0;
     float* d_ring = nullptr;          // [batch][H][W]
@@ -157,10 +182,12 @@ int ssdr_init(int device) {
     if (p.major != 10) { set_error("libssdr_b200 is built for sm_100a only; device %d is sm_%d%d", device, p.major, p.minor); return SSDR_E_CUDA; }
     g_sm_count = p.multiProcessorCount;
     SSDR_CUDA(cudaFree(0));
+    g_device.store(device);
     return SSDR_OK;
 }
 
 int ssdr_device_info(int* sms, int* cc_major, int* cc_minor, size_t* hbm_bytes, char* name, int name_len) {
+    SSDR_BIND_G();
     int dev = 0;
     SSDR_CUDA(cudaGetDevice(&dev));
     cudaDeviceProp p;
@@ -173,20 +200,31 @@ int ssdr_device_info(int* sms, int* cc_major, int* cc_minor, size_t* hbm_bytes, 
     return SSDR_OK;
 }
 
+int ssdr_device_pci_bus_id(char* bus_id, int len) {
+    SSDR_ARG(bus_id && len >= 16, "bus_id buffer of at least 16 bytes");
+    SSDR_BIND_G();
+    int dev = 0;
+    SSDR_CUDA(cudaGetDevice(&dev));
+    SSDR_CUDA(cudaDeviceGetPCIBusId(bus_id, len, dev));
+    return SSDR_OK;
+}
+
 int ssdr_dev_alloc(void** dev, size_t bytes) {
     SSDR_ARG(dev != nullptr, "null pointer");
+    SSDR_BIND_G();
     return dev_alloc(reinterpret_cast<unsigned char**>(dev), bytes);
 }
-int ssdr_dev_free(void* dev) { SSDR_CUDA(cudaFree(dev)); return SSDR_OK; }
-int ssdr_host_alloc(void** host, size_t bytes) { SSDR_ARG(host != nullptr, "null pointer"); SSDR_CUDA(cudaMallocHost(host, bytes)); return SSDR_OK; }
-int ssdr_host_free(void* host) { SSDR_CUDA(cudaFreeHost(host)); return SSDR_OK; }
-int ssdr_memcpy_h2d(void* dev, const void* host, size_t bytes) { SSDR_CUDA(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice)); return SSDR_OK; }
-int ssdr_memcpy_d2h(void* host, const void* dev, size_t bytes) { SSDR_CUDA(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost)); return SSDR_OK; }
-int ssdr_dev_memset(void* dev, int value, size_t bytes) { SSDR_CUDA(cudaMemset(dev, value, bytes)); return SSDR_OK; }
-int ssdr_device_sync(void) { SSDR_CUDA(cudaDeviceSynchronize()); return SSDR_OK; }
+int ssdr_dev_free(void* dev) { SSDR_BIND_G(); SSDR_CUDA(cudaFree(dev)); return SSDR_OK; }
+int ssdr_host_alloc(void** host, size_t bytes) { SSDR_BIND_G(); SSDR_ARG(host != nullptr, "null pointer"); SSDR_CUDA(cudaMallocHost(host, bytes)); return SSDR_OK; }
+int ssdr_host_free(void* host) { SSDR_BIND_G(); SSDR_CUDA(cudaFreeHost(host)); return SSDR_OK; }
+int ssdr_memcpy_h2d(void* dev, const void* host, size_t bytes) { SSDR_BIND_G(); SSDR_CUDA(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice)); return SSDR_OK; }
+int ssdr_memcpy_d2h(void* host, const void* dev, size_t bytes) { SSDR_BIND_G(); SSDR_CUDA(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost)); return SSDR_OK; }
+int ssdr_dev_memset(void* dev, int value, size_t bytes) { SSDR_BIND_G(); SSDR_CUDA(cudaMemset(dev, value, bytes)); return SSDR_OK; }
+int ssdr_device_sync(void) { SSDR_BIND_G(); SSDR_CUDA(cudaDeviceSynchronize()); return SSDR_OK; }
 
 int ssdr_ipc_export(void* dev, void* handle64) {
     SSDR_ARG(dev && handle64, "null argument");
+    SSDR_BIND_G();
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t h;
     SSDR_CUDA(cudaIpcGetMemHandle(&h, dev));
@@ -196,6 +234,7 @@ int ssdr_ipc_export(void* dev, void* handle64) {
 
 int ssdr_ipc_open(const void* handle64, void** dev) {
     SSDR_ARG(handle64 && dev, "null argument");
+    SSDR_BIND_G();
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle64, 64);
     SSDR_CUDA(cudaIpcOpenMemHandle(dev, h, cudaIpcMemLazyEnablePeerAccess));
@@ -204,12 +243,14 @@ int ssdr_ipc_open(const void* handle64, void** dev) {
 
 int ssdr_ipc_close(void* dev) {
     SSDR_ARG(dev != nullptr, "null argument");
+    SSDR_BIND_G();
     SSDR_CUDA(cudaIpcCloseMemHandle(dev));
     return SSDR_OK;
 }
 
 int ssdr_synth_iq_dev(void* iq_dev, int iq_format, int batch, int frames, int nfft, uint32_t seed) {
     SSDR_ARG(iq_dev && batch > 0 && frames > 0 && nfft > 0, "bad synth arguments");
+    SSDR_BIND_G();
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
     int rc = synth_launch(iq_dev, iq_format, batch, frames, nfft, seed, 0);
     if (rc) return rc;
@@ -221,6 +262,7 @@ int ssdr_synth_iq_dev(void* iq_dev, int iq_format, int batch, int frames, int nf
 // waterfall
 // =============================================================================================
 static size_t iq_sample_bytes(int fmt) { return fmt == SSDR_IQ_CF32 ? 8 : 4; }
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, double cal_db, int p_lo, float p_gamma) {
     SSDR_ARG(out != nullptr, "null handle pointer");
@@ -232,7 +274,9 @@ int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, d
     SSDR_ARG(p_lo >= 0 && p_lo < nfft && p_gamma >= 0.f && p_gamma < 1.f, "bad percentile index (%d, %g)", p_lo, (double)p_gamma);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    SSDR_BIND_G();
     ssdr_wf* h = new ssdr_wf();
+    if (cudaGetDevice(&h->device) != cudaSuccess) h->device = -1;
     h->nfft = nfft; h->batch = batch; h->n_avg = n_avg; h->window = window ? 1 : 0; h->cal_db = cal_db;
     h->p_lo = p_lo; h->p_gamma = p_gamma;
     // spec tables: twiddles W_N^k = (cos, -sin)(2 pi k / N) and the byte thresholds
@@ -293,6 +337,7 @@ int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, d
 
 int ssdr_wf_destroy(ssdr_wf_t h) {
     if (!h) return SSDR_OK;
+    bind_device(h->device);
     if (h->compute) cudaStreamSynchronize(h->compute);
     if (h->copy) cudaStreamSynchronize(h->copy);
     cudaFree(h->d_wtab); cudaFree(h->d_win); cudaFree(h->d_wtab_sub); cudaFree(h->d_scratch); cudaFree(h->d_sums); cudaFree(h->d_thr); cudaFree(h->d_disp); cudaFree(h->d_in[0]); cudaFree(h->d_in[1]);
@@ -308,6 +353,7 @@ int ssdr_wf_destroy(ssdr_wf_t h) {
 
 int ssdr_wf_set_display(ssdr_wf_t h, int first, int count, const ssdr_wf_display_t* params) {
     SSDR_ARG(h && params, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(first >= 0 && count >= 0 && first + count <= h->batch, "channel range [%d, %d) outside batch %d", first, first + count, h->batch);
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     SSDR_CUDA(cudaMemcpy(h->d_disp + first, params, sizeof(ssdr_wf_display_t) * (size_t)count, cudaMemcpyHostToDevice));
@@ -358,6 +404,7 @@ static int wf_ensure_scratch(ssdr_wf_t h, int channels) {
 int ssdr_wf_process_dev(ssdr_wf_t h, const void* iq_dev, int iq_format, uint8_t* pixels_dev, float* colour_dev,
                         float* spectrum_dev, ssdr_wf_scalars_t* scalars_dev) {
     SSDR_ARG(h && iq_dev, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
     int rcs = wf_ensure_scratch(h, h->batch);
     if (rcs) return rcs;
@@ -371,6 +418,7 @@ int ssdr_wf_process_dev(ssdr_wf_t h, const void* iq_dev, int iq_format, uint8_t*
 int ssdr_wf_colorrow_u8_dev(ssdr_wf_t h, const uint8_t* lines_dev, uint8_t* pixels_dev, float* colour_dev,
                             float* spectrum_dev, ssdr_wf_scalars_t* scalars_dev) {
     SSDR_ARG(h && lines_dev, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(h->nfft <= 16384, "the uint8-line entry supports nfft <= 16384 (got %d)", h->nfft);
     WfLaunch a = wf_base(h);
     a.lines = lines_dev; a.disp = h->d_disp; a.batch = h->batch;
@@ -380,6 +428,7 @@ int ssdr_wf_colorrow_u8_dev(ssdr_wf_t h, const uint8_t* lines_dev, uint8_t* pixe
 
 int ssdr_wf_sync(ssdr_wf_t h) {
     SSDR_ARG(h != nullptr, "null handle");
+    SSDR_BIND_H(h);
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     SSDR_CUDA(cudaStreamSynchronize(h->copy));
     return SSDR_OK;
@@ -391,7 +440,10 @@ static int wf_ensure_staging(ssdr_wf_t h, size_t bytes_per_channel, bool want_co
         cudaFree(h->d_in[0]); cudaFree(h->d_in[1]);
         h->d_in[0] = h->d_in[1] = nullptr;
         // ~256 MiB per chunk: large enough to fill the GPU, small enough to overlap copy and compute
-        size_t ch = std::max<size_t>(1, ((size_t)256 << 20) / bytes_per_channel);
+        // (SSDR_WF_CHUNK_MB: developer override for the end-to-end experiments of DESIGN.md section 7)
+        size_t chunk_mb = 256;
+        if (const char* e = std::getenv("SSDR_WF_CHUNK_MB")) { const long v = std::atol(e); if (v >= 1 && v <= 4096) chunk_mb = (size_t)v; }
+        size_t ch = std::max<size_t>(1, (chunk_mb << 20) / bytes_per_channel);
         const size_t wave = (size_t)sm_count();
         if (ch >= wave) ch = ch / wave * wave;
         ch = std::min<size_t>(ch, (size_t)h->batch);
@@ -448,6 +500,7 @@ static int wf_process_host(ssdr_wf_t h, const void* in_host, size_t bytes_per_ch
 int ssdr_wf_process(ssdr_wf_t h, const void* iq_host, int iq_format, uint8_t* pixels, float* colour, float* spectrum,
                     ssdr_wf_scalars_t* scalars) {
     SSDR_ARG(h && iq_host, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
     return wf_process_host(h, iq_host, (size_t)h->n_avg * h->nfft * iq_sample_bytes(iq_format), iq_format, false,
                            pixels, colour, spectrum, scalars);
@@ -456,12 +509,14 @@ int ssdr_wf_process(ssdr_wf_t h, const void* iq_host, int iq_format, uint8_t* pi
 int ssdr_wf_colorrow_u8(ssdr_wf_t h, const uint8_t* lines_host, uint8_t* pixels, float* colour, float* spectrum,
                         ssdr_wf_scalars_t* scalars) {
     SSDR_ARG(h && lines_host, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(h->nfft <= 16384, "the uint8-line entry supports nfft <= 16384 (got %d)", h->nfft);
     return wf_process_host(h, lines_host, (size_t)h->n_avg * h->nfft, 0, true, pixels, colour, spectrum, scalars);
 }
 
 int ssdr_wf_time_dev(ssdr_wf_t h, const void* iq_dev, int iq_format, uint8_t* pixels_dev, int iters, float* total_ms) {
     SSDR_ARG(h && iq_dev && total_ms && iters >= 1, "bad argument");
+    SSDR_BIND_H(h);
     SSDR_CUDA(cudaEventRecord(h->ev_t0, h->compute));
     for (int i = 0; i < iters; ++i) {
         int rc = ssdr_wf_process_dev(h, iq_dev, iq_format, pixels_dev, nullptr, nullptr, nullptr);
@@ -483,7 +538,9 @@ int ssdr_demod_create(ssdr_demod_t* out, int batch, int max_samples) {
     SSDR_ARG(max_samples >= SSDR_FRAME && max_samples % SSDR_FRAME == 0, "max_samples_per_call %d must be a positive multiple of %d", max_samples, SSDR_FRAME);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    SSDR_BIND_G();
     ssdr_demod* h = new ssdr_demod();
+    if (cudaGetDevice(&h->device) != cudaSuccess) h->device = -1;
     h->batch = batch; h->max_samples = max_samples;
     double om16 = std::pow(1.0 - kDemodAmBeta, 16.0);
     for (int s = 0; s < 5; ++s) { h->am_pow16[s] = om16; om16 *= om16; }
@@ -515,6 +572,7 @@ int ssdr_demod_create(ssdr_demod_t* out, int batch, int max_samples) {
 
 int ssdr_demod_destroy(ssdr_demod_t h) {
     if (!h) return SSDR_OK;
+    bind_device(h->device);
     if (h->compute) cudaStreamSynchronize(h->compute);
     if (h->copy_in) cudaStreamSynchronize(h->copy_in);
     if (h->copy_out) cudaStreamSynchronize(h->copy_out);
@@ -534,6 +592,7 @@ int ssdr_demod_destroy(ssdr_demod_t h) {
 
 int ssdr_demod_reset(ssdr_demod_t h) {
     SSDR_ARG(h != nullptr, "null handle");
+    SSDR_BIND_H(h);
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     SSDR_CUDA(cudaMemset(h->d_state, 0, sizeof(DemodState) * (size_t)h->batch));
     SSDR_CUDA(cudaMemset(h->d_hist, 0, sizeof(float2) * (size_t)h->batch * (SSDR_FIR_TAPS - 1)));
@@ -548,6 +607,7 @@ static unsigned phase_inc(double f_hz) {
 
 int ssdr_demod_set(ssdr_demod_t h, int first, int count, const ssdr_demod_params_t* p) {
     SSDR_ARG(h && p, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(first >= 0 && count >= 0 && first + count <= h->batch, "channel range [%d, %d) outside batch %d", first, first + count, h->batch);
     std::vector<DemodChan> chan((size_t)count);
     std::vector<float> taps((size_t)count * SSDR_FIR_TAPS);
@@ -555,7 +615,11 @@ int ssdr_demod_set(ssdr_demod_t h, int first, int count, const ssdr_demod_params
         const ssdr_demod_params_t& q = p[i];
         SSDR_ARG(q.mode >= SSDR_MODE_AM && q.mode <= SSDR_MODE_NBFM, "channel %d: unknown mode %d", first + i, q.mode);
         SSDR_ARG(q.high_cut_hz > q.low_cut_hz, "channel %d: high_cut %g <= low_cut %g", first + i, (double)q.high_cut_hz, (double)q.low_cut_hz);
-        SSDR_ARG(q.agc_decay_ms > 0.f, "channel %d: decay %g ms", first + i, (double)q.agc_decay_ms);
+        // the AGC scan forms 2^(+-k c2), k < 512, in float32: a decay under 1 ms would overflow it (inf * 0 = NaN, which
+        // would then poison the channel's envelope state).  The reference UI keeps decay in 400..8000 ms (utils_supersdr.py:1009-1019).
+        SSDR_ARG(q.agc_decay_ms >= 1.0f && q.agc_decay_ms <= 1.0e6f, "channel %d: AGC decay %g ms outside 1 .. 1e6 ms", first + i, (double)q.agc_decay_ms);
+        SSDR_ARG(std::isfinite(q.agc_thresh_dbm) && std::isfinite(q.agc_slope_db) && std::isfinite(q.agc_man_gain_db) &&
+                 std::isfinite(q.freq_offset_hz), "channel %d: non-finite AGC / tuning parameter", first + i);
         DemodChan& c = chan[(size_t)i];
         const double fc = ((double)q.low_cut_hz + (double)q.high_cut_hz) / 2.0;
         c.mode = q.mode; c.agc_on = q.agc_on ? 1 : 0; c.agc_hang = q.agc_hang ? 1 : 0;
@@ -710,8 +774,12 @@ static int demod_launch_block(ssdr_demod_t h, const void* iq_dev, int iq_format,
 int ssdr_demod_process_dev(ssdr_demod_t h, const void* iq_dev, int iq_format, int n_samples, float* pcm_f32_dev,
                            int16_t* pcm_i16_dev, float* rssi_dev) {
     SSDR_ARG(h && iq_dev, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
     SSDR_ARG(n_samples > 0 && n_samples % SSDR_FRAME == 0, "n_samples %d must be a positive multiple of %d", n_samples, SSDR_FRAME);
+    // the kernels move IQ and PCM as 16-byte vectors
+    SSDR_ARG(aligned16(iq_dev) && aligned16(pcm_f32_dev) && aligned16(pcm_i16_dev) && aligned16(rssi_dev),
+             "device pointers of ssdr_demod_process_dev must be 16-byte aligned");
     return demod_launch_block(h, iq_dev, iq_format, n_samples, n_samples, pcm_f32_dev, pcm_i16_dev, rssi_dev);
 }
 
@@ -722,6 +790,7 @@ int ssdr_demod_process_dev(ssdr_demod_t h, const void* iq_dev, int iq_format, in
 int ssdr_demod_process(ssdr_demod_t h, const void* iq_host, int iq_format, int n_samples, float* pcm_f32, int16_t* pcm_i16,
                        float* rssi_dbm) {
     SSDR_ARG(h && iq_host, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
     SSDR_ARG(n_samples > 0 && n_samples % SSDR_FRAME == 0 && n_samples <= h->max_samples,
              "n_samples %d must be a multiple of %d and <= %d", n_samples, SSDR_FRAME, h->max_samples);
@@ -765,6 +834,7 @@ int ssdr_demod_process(ssdr_demod_t h, const void* iq_host, int iq_format, int n
 
 int ssdr_demod_sync(ssdr_demod_t h) {
     SSDR_ARG(h != nullptr, "null handle");
+    SSDR_BIND_H(h);
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     return SSDR_OK;
 }
@@ -772,6 +842,7 @@ int ssdr_demod_sync(ssdr_demod_t h) {
 int ssdr_demod_time_dev(ssdr_demod_t h, const void* iq_dev, int iq_format, int n_samples, float* pcm_f32_dev,
                         int16_t* pcm_i16_dev, int iters, float* total_ms) {
     SSDR_ARG(h && iq_dev && total_ms && iters >= 1, "bad argument");
+    SSDR_BIND_H(h);
     SSDR_CUDA(cudaEventRecord(h->ev_t0, h->compute));
     for (int i = 0; i < iters; ++i) {
         int rc = ssdr_demod_process_dev(h, iq_dev, iq_format, n_samples, pcm_f32_dev, pcm_i16_dev, nullptr);
@@ -790,11 +861,14 @@ int ssdr_interp_create(ssdr_interp_t* out, int batch, int ratio, const double* t
     SSDR_ARG(out != nullptr, "null handle pointer");
     *out = nullptr;
     SSDR_ARG(batch >= 1 && ratio >= 1 && taps && max_samples >= 1, "bad argument");
+    SSDR_ARG(batch <= 65535, "batch %d > 65535 channels per interpolator handle (grid y dimension)", batch);
     SSDR_ARG(n_taps >= 1 && n_taps <= SSDR_INTERP_TAPS_MAX && (n_taps - 1) % ratio == 0,
              "n_taps %d must be <= %d with (n_taps - 1) a multiple of the ratio %d", n_taps, SSDR_INTERP_TAPS_MAX, ratio);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    SSDR_BIND_G();
     ssdr_interp* h = new ssdr_interp();
+    if (cudaGetDevice(&h->device) != cudaSuccess) h->device = -1;
     h->batch = batch; h->ratio = ratio; h->n_taps = n_taps; h->max_samples = max_samples; h->hs = (n_taps - 1) / ratio;
     int rc;
     auto fail = [&](int code) { ssdr_interp_destroy(h); return code; };
@@ -811,6 +885,7 @@ int ssdr_interp_create(ssdr_interp_t* out, int batch, int ratio, const double* t
 
 int ssdr_interp_destroy(ssdr_interp_t h) {
     if (!h) return SSDR_OK;
+    bind_device(h->device);
     if (h->compute) cudaStreamSynchronize(h->compute);
     cudaFree(h->d_taps); cudaFree(h->d_hist[0]); cudaFree(h->d_hist[1]); cudaFree(h->d_in); cudaFree(h->d_vol);
     cudaFree(h->d_bal); cudaFree(h->d_out); cudaFree(h->d_mono);
@@ -821,6 +896,7 @@ int ssdr_interp_destroy(ssdr_interp_t h) {
 
 int ssdr_interp_reset(ssdr_interp_t h) {
     SSDR_ARG(h != nullptr, "null handle");
+    SSDR_BIND_H(h);
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     for (int i = 0; i < 2; ++i) SSDR_CUDA(cudaMemset(h->d_hist[i], 0, sizeof(double) * (size_t)h->batch * std::max(h->hs, 1)));
     return SSDR_OK;
@@ -829,7 +905,10 @@ int ssdr_interp_reset(ssdr_interp_t h) {
 int ssdr_interp_process_dev(ssdr_interp_t h, const int16_t* pcm_dev, int n, const float* volume_dev, const float* balance_dev,
                             int16_t* stereo_dev, double* mono_dev) {
     SSDR_ARG(h && pcm_dev && volume_dev && balance_dev && stereo_dev, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(n >= h->hs, "n %d shorter than the filter history %d", n, h->hs);
+    SSDR_ARG(((uintptr_t)stereo_dev & 3u) == 0 && ((uintptr_t)pcm_dev & 1u) == 0 && (!mono_dev || ((uintptr_t)mono_dev & 7u) == 0),
+             "ssdr_interp_process_dev: stereo_dev must be 4-byte, pcm_dev 2-byte, mono_dev 8-byte aligned");
     InterpLaunch a;
     a.kp.pcm = pcm_dev; a.kp.volume = volume_dev; a.kp.balance = balance_dev; a.kp.taps = h->d_taps;
     a.kp.hist_in = h->d_hist[h->cur]; a.kp.hist_out = h->d_hist[h->cur ^ 1];
@@ -844,6 +923,7 @@ int ssdr_interp_process_dev(ssdr_interp_t h, const int16_t* pcm_dev, int n, cons
 int ssdr_interp_process(ssdr_interp_t h, const int16_t* pcm_host, int n, const float* volume, const float* balance,
                         int16_t* stereo_out, double* mono_f64) {
     SSDR_ARG(h && pcm_host && volume && balance && stereo_out, "null argument");
+    SSDR_BIND_H(h);
     SSDR_ARG(n >= 1 && n <= h->max_samples, "n %d outside 1..%d", n, h->max_samples);
     const size_t cap = (size_t)h->batch * h->max_samples, tot = (size_t)h->batch * n;
     int rc;
@@ -862,6 +942,7 @@ int ssdr_interp_process(ssdr_interp_t h, const int16_t* pcm_host, int n, const f
 
 int ssdr_interp_sync(ssdr_interp_t h) {
     SSDR_ARG(h != nullptr, "null handle");
+    SSDR_BIND_H(h);
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
     return SSDR_OK;
 }
@@ -869,7 +950,9 @@ int ssdr_interp_sync(ssdr_interp_t h) {
 int ssdr_resample_line(const int16_t* pcm_host, int batch, int n, const float* volume, const float* balance, const double* h,
                        int n_h, int up, int down, int first, int n_keep, int16_t* stereo_out, double* mono_f64) {
     SSDR_ARG(pcm_host && volume && balance && h && stereo_out, "null argument");
+    SSDR_BIND_G();
     SSDR_ARG(batch >= 1 && n >= 1 && n_h >= 1 && up >= 1 && down >= 1 && first >= 0 && n_keep >= 0, "bad argument");
+    SSDR_ARG(batch <= 65535, "batch %d > 65535 channels per call (grid y dimension)", batch);
     // the kept samples must exist: upfirdn produces ((n - 1) up + n_h - 1) / down + 1 samples
     SSDR_ARG((long long)(first + n_keep) <= ((long long)(n - 1) * up + n_h - 1) / down + 1, "first + n_keep exceeds the upfirdn output length");
     if (n_keep == 0) return SSDR_OK;
@@ -903,6 +986,7 @@ int ssdr_resample_line(const int16_t* pcm_host, int batch, int n, const float* v
 
 int ssdr_fir_valid_f64(const double* x_host, size_t n, const double* taps, int n_taps, double* out_host) {
     SSDR_ARG(x_host && taps && out_host && n_taps >= 1, "bad argument");
+    SSDR_BIND_G();
     if (n < (size_t)n_taps) return SSDR_OK;
     const size_t n_out = n - (size_t)n_taps + 1;
     double *d_x = nullptr, *d_h = nullptr, *d_o = nullptr;
@@ -931,7 +1015,9 @@ int ssdr_wf_image_create(ssdr_wf_image_t* out, int batch, int height, int width,
     SSDR_ARG(batch >= 1 && height >= 1 && width >= 1 && palette_rgb, "bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
+    SSDR_BIND_G();
     ssdr_wf_image* h = new ssdr_wf_image();
+    if (cudaGetDevice(&h->device) != cudaSuccess) h->device = -1;
     h->batch = batch; h->H = height; h->W = width;
     int rc;
     auto fail = [&](int code) { ssdr_wf_image_destroy(h); return code; };
@@ -950,6 +1036,7 @@ int ssdr_wf_image_create(ssdr_wf_image_t* out, int batch, int height, int width,
 
 int ssdr_wf_image_destroy(ssdr_wf_image_t h) {
     if (!h) return SSDR_OK;
+    bind_device(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
     cudaFree(h->d_ring); cudaFree(h->d_delay); cudaFree(h->d_row); cudaFree(h->d_pal); cudaFree(h->d_rgb); cudaFree(h->d_f64); cudaFree(h->d_y);
     if (h->st) cudaStreamDestroy(h->st);
@@ -979,16 +1066,19 @@ static int wf_image_push_any(ssdr_wf_image_t h, const float* src, cudaMemcpyKind
 
 int ssdr_wf_image_push(ssdr_wf_image_t h, const float* colour_host) {
     SSDR_ARG(h && colour_host, "null argument");
+    SSDR_BIND_H(h);
     return wf_image_push_any(h, colour_host, cudaMemcpyHostToDevice);
 }
 
 int ssdr_wf_image_push_dev(ssdr_wf_image_t h, const float* colour_dev) {
     SSDR_ARG(h && colour_dev, "null argument");
+    SSDR_BIND_H(h);
     return wf_image_push_any(h, colour_dev, cudaMemcpyDeviceToDevice);
 }
 
 int ssdr_wf_image_white(ssdr_wf_image_t h) {
     SSDR_ARG(h != nullptr, "null handle");
+    SSDR_BIND_H(h);
     for (int ch = 0; ch < h->batch; ++ch)
         SSDR_CUDA(cudaMemcpyAsync(h->d_ring + ((size_t)ch * h->H + h->head) * h->W, h->d_row, sizeof(float) * h->W,
                                   cudaMemcpyDeviceToDevice, h->st));
@@ -998,6 +1088,7 @@ int ssdr_wf_image_white(ssdr_wf_image_t h) {
 
 int ssdr_wf_image_get(ssdr_wf_image_t h, uint8_t* rgb, double* wf_data) {
     SSDR_ARG(h != nullptr, "null handle");
+    SSDR_BIND_H(h);
     const size_t px = (size_t)h->batch * h->H * h->W;
     int rc;
     if (rgb) {
@@ -1016,6 +1107,7 @@ int ssdr_wf_image_get(ssdr_wf_image_t h, uint8_t* rgb, double* wf_data) {
 
 int ssdr_wf_image_trace(ssdr_wf_image_t h, int t_avg, int spectrum_height, double* v, int32_t* y) {
     SSDR_ARG(h != nullptr && t_avg >= 1 && spectrum_height >= 1, "bad argument");
+    SSDR_BIND_H(h);
     const size_t n = (size_t)h->batch * h->W;
     int rc;
     if (!h->d_f64 && (rc = dev_alloc(&h->d_f64, (size_t)h->batch * h->H * h->W))) return rc;
@@ -1029,6 +1121,7 @@ int ssdr_wf_image_trace(ssdr_wf_image_t h, int t_avg, int spectrum_height, doubl
 
 int ssdr_adpcm_decode(const uint8_t* data_host, int batch, int n_bytes, int32_t* state, int16_t* pcm_out) {
     SSDR_ARG(data_host && state && pcm_out && batch >= 1 && n_bytes >= 0, "bad argument");
+    SSDR_BIND_G();
     if (n_bytes == 0) return SSDR_OK;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (libssdr_b200 has no CPU fallback)"); return SSDR_E_CUDA; }
@@ -1055,6 +1148,7 @@ int ssdr_adpcm_decode(const uint8_t* data_host, int batch, int n_bytes, int32_t*
 // =============================================================================================
 int ssdr_unpack_iq_s16be_dev(const void* s16be_dev, float* cf32_dev, size_t n_complex) {
     SSDR_ARG(s16be_dev && cf32_dev, "null argument");
+    SSDR_BIND_G();
     int rc = unpack_launch(s16be_dev, cf32_dev, n_complex, 0);
     if (rc) return rc;
     SSDR_CUDA(cudaStreamSynchronize(0));
@@ -1063,6 +1157,7 @@ int ssdr_unpack_iq_s16be_dev(const void* s16be_dev, float* cf32_dev, size_t n_co
 
 int ssdr_unpack_iq_s16be(const void* s16be_host, float* cf32_host, size_t n_complex) {
     SSDR_ARG(s16be_host && cf32_host, "null argument");
+    SSDR_BIND_G();
     if (n_complex == 0) return SSDR_OK;
     unsigned char* d_in = nullptr;
     float* d_out = nullptr;

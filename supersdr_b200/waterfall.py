@@ -22,10 +22,8 @@ LOW_CUT_CW, HIGH_CUT_CW = int(CW_PITCH * 1000 - 200), int(CW_PITCH * 1000 + 200)
 HIGHLOW_CUT_AM = 6000
 
 
-def percentile_index(n, q_percent=40.0):
-    """(lo, gamma) of numpy's float32 'linear' percentile for n points -- numpy's own expression
-    ``(n - 1) * (q / float32(100))`` evaluated in float32, so that the kernel's
-    ``s[lo] + (s[lo+1] - s[lo]) * gamma`` reproduces ``np.percentile(wf_db, 40.)`` bit for bit."""
+def _percentile_index_formula(n, q_percent):
+    """numpy >= 2.0's expression: ``(n - 1) * (q / float32(100))`` evaluated in float32."""
     q = np.float32(q_percent) / np.float32(100)
     vi = np.float32(n - 1) * q
     lo = int(np.floor(vi))
@@ -33,6 +31,41 @@ def percentile_index(n, q_percent=40.0):
     if lo >= n - 1:
         lo, gamma = n - 1, np.float32(0)
     return lo, float(gamma)
+
+
+_PCT_CACHE = {}
+
+
+def percentile_index(n, q_percent=40.0):
+    """(lo, gamma) of ``np.percentile(x_float32[n], q)`` ('linear' method) AS THE INSTALLED numpy EVALUATES IT, so that
+    the kernel's ``s[lo] + (s[lo+1] - s[lo]) * gamma`` reproduces the reference's ``np.percentile(wf_db, 40.)``
+    (utils_supersdr.py:794) bit for bit whatever the numpy version: the pair is measured by probing ``np.percentile``
+    with step vectors (0 up to index j, 1 above: the result is 0, gamma or 1 according to where j lies) around the
+    analytic value of numpy >= 2.0.  A gamma that is not a float32 number (numpy 1.x interpolates in float64) cannot
+    be reproduced by the float32 kernel and is refused."""
+    key = (int(n), float(q_percent))
+    if key in _PCT_CACHE:
+        return _PCT_CACHE[key]
+    lo0, g0 = _percentile_index_formula(n, q_percent)
+    found = None
+    if n >= 2:
+        idx = np.arange(n)
+        probe = lambda j: float(np.percentile((idx > j).astype(np.float32), q_percent))
+        for j in sorted(range(max(lo0 - 2, 0), min(lo0 + 3, n - 1)), key=lambda j: abs(j - lo0)):
+            r = probe(j)
+            if 0.0 < r < 1.0:                        # j is the lower index, r the weight
+                found = (j, r)
+                break
+            if r == 0.0 and (j == 0 or probe(j - 1) == 1.0):   # weight 0: pure selection of s[j]
+                found = (j, 0.0)
+                break
+    if found is None:
+        found = (lo0, g0)
+    if float(np.float32(found[1])) != found[1]:
+        raise RuntimeError("numpy %s interpolates percentiles in float64 (weight %r): the float32 colour row of "
+                           "utils_supersdr.py:794 cannot be matched bit for bit; use numpy >= 2.0" % (np.__version__, found[1]))
+    _PCT_CACHE[key] = found
+    return found
 
 
 class WaterfallBank:

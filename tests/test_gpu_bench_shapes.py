@@ -1,0 +1,231 @@
+"""GPU parity at the BASELINE bench shapes (through the C ABI).
+
+* demodulator at configs 3 and 4 (4096 x 512*64 USB; 8192 x 512*32, modes ch % 5): the only shapes where the tcgen05
+  engine's multi-wave round scheduler, narrow tail rounds and cross-round B-operand rebuilds run (rounds > 148 CTAs).
+  Parameters honoured: utils_supersdr.py:42-50,859-873 (pass-bands), :936-945,1022-1029 (AGC set).
+* waterfall: boundary-aware float64 comparison of the GPU bytes for every FFT size and for sampled rows of the full
+  config 2, and the direct seam test  spectrum (GPU) -> the reference's spectrum_db2col arithmetic -> colour (GPU).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import tier_p, tier_u
+
+pytestmark = pytest.mark.gpu
+RMS_TOL = 1e-5
+
+
+def _rel_rms(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.sqrt(np.mean((a - b) ** 2)) / max(np.sqrt(np.mean(b ** 2)), 1e-30)
+
+
+def _oracle_params(p):
+    """ssdr_demod_params_t -> tier_u.DemodParams (same fields)."""
+    mode = {0: "am", 1: "usb", 2: "lsb", 3: "cw", 4: "nbfm"}[p.mode]
+    return tier_u.DemodParams(mode, lc=p.low_cut_hz, hc=p.high_cut_hz, f_off=p.freq_offset_hz, on=bool(p.agc_on),
+                              hang=bool(p.agc_hang), thresh=p.agc_thresh_dbm, slope=p.agc_slope_db,
+                              decay=p.agc_decay_ms, gain=p.agc_man_gain_db)
+
+
+def _run_big(ssdr, B, ns, params, seed, engines):
+    """One full-size launch per engine on IQ generated in HBM; returns {engine: (pcm_f32, pcm_i16, rssi)} and a
+    function that downloads one channel's IQ."""
+    iq = ssdr.DeviceBuffer(B * ns * 8)
+    ssdr._lib.check(ssdr.lib.ssdr_synth_iq_dev(iq.ptr, ssdr.SSDR_IQ_CF32, B, 1, ns, seed))
+    f32 = ssdr.DeviceBuffer(B * ns * 4)
+    i16 = ssdr.DeviceBuffer(B * ns * 2)
+    rssi = ssdr.DeviceBuffer(B * (ns // 512) * 4)
+    out = {}
+    for eng in engines:
+        bank = ssdr.DemodBank(B, ns, engine=eng)
+        bank.set_params(0, params)
+        bank.process_dev(iq.ptr, ssdr.SSDR_IQ_CF32, ns, f32.ptr, i16.ptr, rssi.ptr)
+        bank.sync()
+        out[eng] = (f32.download(np.float32, (B, ns)), i16.download(np.int16, (B, ns)),
+                    rssi.download(np.float32, (B, ns // 512)))
+        bank.close()
+
+    def chan_iq(ch, count=1):
+        return iq.download(np.complex64, (count, ns), offset_bytes=ch * ns * 8)
+    return out, chan_iq, (iq, f32, i16, rssi)
+
+
+def _check_against_oracle(got, chan_iq, params, channels):
+    f32, i16, rssi = got
+    for ch in channels:
+        ref, rr = tier_u.demod(chan_iq(ch)[0], _oracle_params(params[ch]), tier_u.DemodState())
+        assert _rel_rms(f32[ch], ref) < RMS_TOL, ch
+        assert np.abs(i16[ch].astype(int) - tier_u.pcm_to_i16(ref).astype(int)).max() <= 1, ch
+        assert np.abs(rssi[ch] - rr).max() < 1e-3, ch
+
+
+def _check_small_banks(ssdr, got, chan_iq, params, ns, eng, firsts):
+    """Every channel of a 4-channel bank gives bit for bit what the same channel gives inside the full batch (the
+    result must not depend on the tile, round or wave a channel lands in)."""
+    for c0 in firsts:
+        small = ssdr.DemodBank(4, ns, engine=eng)
+        small.set_params(0, params[c0:c0 + 4])
+        r = small.process(chan_iq(c0, 4))
+        assert np.array_equal(r["pcm_f32"], got[0][c0:c0 + 4]), (eng, c0)
+        assert np.array_equal(r["pcm_i16"], got[1][c0:c0 + 4]), (eng, c0)
+        assert np.array_equal(r["rssi"], got[2][c0:c0 + 4]), (eng, c0)
+        small.close()
+
+
+def pcm_checksum(f32):
+    """The checksum bench.py prints for its demodulator lines: 64-bit sum of the float32 bit patterns."""
+    return int(np.ascontiguousarray(f32).view(np.uint32).astype(np.uint64).sum())
+
+
+def test_demod_config3_shape_usb(ssdr):
+    """BASELINE config 3: 4096 channels x 32768 samples, USB 300..2700 Hz (kiwi/client.py:229-231 pass-band), AGC
+    defaults utils_supersdr.py:936-942 -- the bench's own inputs (seed 99)."""
+    B, ns = 4096, 512 * 64
+    params = [ssdr.demod_params("usb", 300, 2700)] * B
+    out, chan_iq, bufs = _run_big(ssdr, B, ns, params, 99, ("ffma", "tcgen05", "auto"))
+    sampled = [0, 1, 2, 3, 147, 148, 591, 592, 1023, 2047, 2048, 2369, 3000, 3551, 3552, 4092, 4093, 4094, 4095]
+    for eng in ("ffma", "tcgen05"):
+        _check_against_oracle(out[eng], chan_iq, params, sampled)
+        _check_small_banks(ssdr, out[eng], chan_iq, params, ns, eng, (0, 2048, 4092))
+    # the engines agree on EVERY channel (both are within 1e-5 of the float64 statement)
+    a, b = out["ffma"][0].astype(np.float64), out["tcgen05"][0].astype(np.float64)
+    rel = np.sqrt(np.mean((a - b) ** 2, axis=1)) / np.maximum(np.sqrt(np.mean(a ** 2, axis=1)), 1e-30)
+    assert rel.max() < 2 * RMS_TOL, int(rel.argmax())
+    # AUTO is one of the two engines, bit for bit (homogeneous bank: the tensor-core engine)
+    assert np.array_equal(out["auto"][0], out["tcgen05"][0])
+    import bench
+    if bench.DEMOD_CHECKSUMS.get("config3_usb", {}).get("tcgen05") is not None:
+        assert pcm_checksum(out["tcgen05"][0]) == bench.DEMOD_CHECKSUMS["config3_usb"]["tcgen05"]
+        assert pcm_checksum(out["ffma"][0]) == bench.DEMOD_CHECKSUMS["config3_usb"]["ffma"]
+    for b_ in bufs:
+        b_.free()
+
+
+def test_demod_config4_shape_mixed_modes(ssdr):
+    """BASELINE config 4 per GPU: 8192 channels x 16384 samples, modes ch % 5 -> AM/LSB/USB/CW/NBFM with the reference
+    pass-bands (utils_supersdr.py:42-50,859-873) -- the bench's own inputs (seed 99)."""
+    B, ns = 8192, 512 * 32
+    modes = [ssdr.demod_params(m) for m in ("am", "lsb", "usb", "cw", "nbfm")]
+    params = [modes[c % 5] for c in range(B)]
+    out, chan_iq, bufs = _run_big(ssdr, B, ns, params, 99, ("ffma", "tcgen05", "auto"))
+    sampled = [0, 1, 2, 3, 4, 295, 296, 1184, 2500, 4095, 4096, 4097, 4098, 4099, 6001, 7103, 7104, 8188, 8189, 8190, 8191]
+    for eng in ("ffma", "tcgen05"):
+        _check_against_oracle(out[eng], chan_iq, params, sampled)
+        _check_small_banks(ssdr, out[eng], chan_iq, params, ns, eng, (0, 4095, 8188))
+    a, b = out["ffma"][0].astype(np.float64), out["tcgen05"][0].astype(np.float64)
+    rel = np.sqrt(np.mean((a - b) ** 2, axis=1)) / np.maximum(np.sqrt(np.mean(a ** 2, axis=1)), 1e-30)
+    assert rel.max() < 2 * RMS_TOL, int(rel.argmax())
+    assert np.array_equal(out["auto"][0], out["tcgen05"][0]) or np.array_equal(out["auto"][0], out["ffma"][0])
+    import bench
+    if bench.DEMOD_CHECKSUMS.get("config4_mixed", {}).get("tcgen05") is not None:
+        assert pcm_checksum(out["tcgen05"][0]) == bench.DEMOD_CHECKSUMS["config4_mixed"]["tcgen05"]
+        assert pcm_checksum(out["ffma"][0]) == bench.DEMOD_CHECKSUMS["config4_mixed"]["ffma"]
+    for b_ in bufs:
+        b_.free()
+
+
+def test_demod_ragged_batch_many_filters(ssdr):
+    """A batch that is not a multiple of four, with eleven distinct filters (per-user pass-band deltas,
+    utils_supersdr.py:1078-1092) and per-channel AGC settings, large enough for several waves of rounds: consecutive
+    rounds change the filter id, so the B operand is rebuilt across rounds."""
+    B, ns = 4099, 512 * 16
+    modes = ("usb", "lsb", "cw", "am", "nbfm")
+    params = []
+    for c in range(B):
+        m = modes[c % 5]
+        lc, hc = ssdr.default_passband(m)
+        d = 50 * (c % 11) if m in ("usb", "cw") else 0          # widen the pass-band like change_passband does
+        params.append(ssdr.demod_params(m, lc, hc + d, f_off=25.0 * (c % 7), hang=(c % 3 == 0), slope=(c % 2) * 6,
+                                        thresh=-80 - (c % 4), decay=1000 + 500 * (c % 5)))
+    out, chan_iq, bufs = _run_big(ssdr, B, ns, params, 7, ("ffma", "tcgen05", "auto"))
+    sampled = [0, 5, 11, 54, 55, 600, 1777, 2048, 3001, 4090, 4095, 4096, 4097, 4098]
+    for eng in ("ffma", "tcgen05"):
+        _check_against_oracle(out[eng], chan_iq, params, sampled)
+    _check_small_banks(ssdr, out["ffma"], chan_iq, params, ns, "ffma", (0, 4095))
+    a, b = out["ffma"][0].astype(np.float64), out["tcgen05"][0].astype(np.float64)
+    rel = np.sqrt(np.mean((a - b) ** 2, axis=1)) / np.maximum(np.sqrt(np.mean(a ** 2, axis=1)), 1e-30)
+    assert rel.max() < 2 * RMS_TOL, int(rel.argmax())
+    assert np.array_equal(out["auto"][0], out["tcgen05"][0]) or np.array_equal(out["auto"][0], out["ffma"][0])
+    for b_ in bufs:
+        b_.free()
+
+
+# ---------------------------------------------------------------------------------------------------
+# waterfall
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
+@pytest.mark.parametrize("window", [True, False])
+def test_waterfall_bytes_vs_float64_every_size(ssdr, N, window):
+    """Independent of the builder's C oracle: the GPU byte line (n_avg = 1) against the float64 numpy statement with
+    the boundary-aware comparator -- a float32 result may differ from the float64 rounding by one step only where the
+    float64 value lies within the float32 error band of a rounding boundary (0 unexplained bins, <= N/500 flips)."""
+    B = 6
+    iq = tier_u.synth_batch(B, 1, N, seed=31 * N + window)
+    bank = ssdr.WaterfallBank(N, B, 1, window=window)
+    res = bank.process(iq)
+    for b in range(B):
+        by = res["spectrum"][b].astype(np.uint8)
+        assert np.array_equal(by.astype(np.float32), res["spectrum"][b])
+        mism, unexplained = tier_u.compare_bytes_boundary_aware(by, iq[b, 0], window=window)
+        assert unexplained == 0, (N, b, mism, unexplained)
+        assert mism <= max(N // 500, 2), (N, b, mism)
+    bank.close()
+
+
+def test_config2_sampled_rows_vs_float64(ssdr):
+    """Full BASELINE config 2 (4096 ch x 10 x 16384, generated in HBM): for sampled channels the averaged line
+    (spectrum x n_avg = sum of the ten byte lines) against the float64 statement, boundary-aware per frame."""
+    B, n, N = 4096, 10, 16384
+    iq = ssdr.DeviceBuffer(B * n * N * 8)
+    px = ssdr.DeviceBuffer(B * N)
+    sp = ssdr.DeviceBuffer(B * N * 4)
+    ssdr._lib.check(ssdr.lib.ssdr_synth_iq_dev(iq.ptr, ssdr.SSDR_IQ_CF32, B, n, N, 1234))
+    bank = ssdr.WaterfallBank(N, B, n)
+    ssdr._lib.check(ssdr.lib.ssdr_wf_process_dev(bank._h, iq.ptr, ssdr.SSDR_IQ_CF32, px.ptr, None, sp.ptr, None))
+    bank.sync()
+    for ch in (0, 1, 147, 148, 1000, 2049, 4094, 4095):
+        x = iq.download(np.complex64, (n, N), offset_bytes=ch * n * N * 8)
+        spec = sp.download(np.float32, (N,), offset_bytes=ch * N * 4)
+        sums = np.rint(spec.astype(np.float64) * n).astype(np.int64)
+        lo = np.zeros(N, np.int64)
+        hi = np.zeros(N, np.int64)
+        for f in range(n):                                   # per-frame admissible byte range
+            v, amp = tier_u.wf_frame_db(x[f])
+            err = tier_u.fft_error_bound(x[f])
+            with np.errstate(divide="ignore", invalid="ignore"):
+                band = 20.0 * np.log10(1.0 + err / np.maximum(amp, 1e-300))
+            band = np.where(np.isfinite(band), band, 1e9) + 1e-6
+            lo += np.clip(np.rint(v - band), 0, 255).astype(np.int64)
+            hi += np.clip(np.rint(v + band), 0, 255).astype(np.int64)
+        exact = sum(tier_u.wf_frame_bytes(x[f]).astype(np.int64) for f in range(n))
+        assert np.all((sums >= lo) & (sums <= hi)), ch        # 0 unexplained bins
+        assert np.count_nonzero(sums != exact) <= n * N // 500, ch
+    bank.close()
+    for o in (iq, px, sp):
+        o.free()
+
+
+@pytest.mark.parametrize("N,B,n", [(1024, 5, 10), (16384, 4, 10), (4096, 3, 3), (65536, 2, 2)])
+def test_fused_spectrum_to_colour_seam_is_the_references_arithmetic(ssdr, N, B, n):
+    """The fused kernel's own `spectrum` output (= kiwi_waterfall.spectrum, utils_supersdr.py:780-785,881-888) pushed
+    through the REFERENCE's spectrum_db2col arithmetic (oracle.tier_p.waterfall_line, pinned on fixtures from the
+    unmodified utils_supersdr.py:787-813) equals the kernel's `colour` / `pixels` / scalars outputs -- directly, not
+    through the C oracle."""
+    iq = tier_u.synth_batch(B, n, N, seed=5 * N + n)
+    bank = ssdr.WaterfallBank(N, B, n)
+    bank.set_display(zoom=4, delta_low_db=-2, delta_high_db=3)
+    res = bank.process(iq)
+    for b in range(B):
+        st = tier_p.ColourState()
+        st.zoom, st.delta_low_db, st.delta_high_db = 4, -2, 3
+        col = tier_p.spectrum_db2col(res["spectrum"][b], st)          # utils_supersdr.py:787-813
+        px = tier_p.pixel_row(col)
+        assert np.array_equal(col, res["colour"][b]), b
+        assert np.array_equal(px, res["pixels"][b]), b
+        assert np.float32(st.low_clip_db) == res["scalars"]["low_clip_db"][b]
+        assert np.float32(st.dynamic_range) == res["scalars"]["dynamic_range"][b]
+    bank.close()

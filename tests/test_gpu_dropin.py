@@ -172,3 +172,43 @@ def test_peer_ingest_across_processes(ssdr):
     got = np.frombuffer(rest[:B * N], np.uint8).reshape(B, N)
     assert np.array_equal(got, want)
     bank.close(); iq.free(); px.free()
+
+
+def test_handles_work_from_other_threads_on_any_device(ssdr):
+    """the CUDA device is a per-thread setting.  A handle created in the main thread is used from a fresh
+    thread (the reference runs kiwi_waterfall.run, kiwi_sound.run and the PortAudio callback on their own threads,
+    utils_supersdr.py:879,1106,1150) -- on device 0 and, when the box has a second GPU, on device 1, where the new
+    thread's default device (0) is the wrong one.  Stateless entry points follow the selected device as well."""
+    import threading
+    devices = [0]
+    try:
+        ssdr._lib.check(ssdr.lib.ssdr_init(1))
+        devices.append(1)
+    except ssdr.SsdrError:
+        pass
+    iq = tier_u.synth_batch(3, 2, 1024, seed=77)
+    ref = c_oracle.wf_rows(iq)["pixels"]
+    x = np.random.default_rng(1).normal(size=400)
+    try:
+        for dev in devices:
+            ssdr._lib.check(ssdr.lib.ssdr_init(dev))
+            bank = ssdr.WaterfallBank(1024, 3, 2)             # lives on `dev`
+            db = ssdr.DemodBank(2, 1024)
+            got, errs = {}, []
+
+            def worker():
+                try:                                          # this thread never called ssdr_init: runtime default = device 0
+                    got["px"] = bank.process(iq)["pixels"]
+                    got["pcm"] = db.process(np.zeros((2, 1024), np.complex64))["pcm_f32"]
+                    got["fir"] = ssdr.filtering(6000, 48000).lowpass(x)
+                except Exception as e:                        # noqa: BLE001
+                    errs.append(e)
+            t = threading.Thread(target=worker)
+            t.start(); t.join()
+            assert not errs, (dev, errs)
+            assert np.array_equal(got["px"], ref), dev
+            assert np.all(got["pcm"] == 0)
+            assert np.allclose(got["fir"], np.convolve(x, tier_p.fir_design(6000, 48000), "valid"), rtol=0, atol=1e-12)
+            bank.close(); db.close()
+    finally:
+        ssdr._lib.check(ssdr.lib.ssdr_init(0))
