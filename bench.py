@@ -329,32 +329,35 @@ def main():
     # NVLink with NCCL (torch.distributed.scatter = grouped send/recv), then every rank runs the kernel.  Channels stay
     # independent: this is the only collective anywhere, and it moves inputs, not partial results. ----------------------
     scatter = None
+    comm = None
     if dist is not None and not args.no_scatter:
         try:
-            import torch
-            local_t = torch.empty(n_samples * 2, dtype=torch.float32, device="cuda")
-            root_list = None
+            from supersdr_b200 import sharding
+            comm = sharding.Comm(rank, world)                  # ssdr_nccl_*: grouped ncclSend/ncclRecv through the C ABI
+            local_buf = S.DeviceBuffer(n_samples * 8)
+            root_buf = None
             if rank == 0:
-                root_list = [torch.empty(n_samples * 2, dtype=torch.float32, device="cuda") for _ in range(world)]
-                for r_, t_ in enumerate(root_list):
-                    S._lib.check(S.lib.ssdr_synth_iq_dev(t_.data_ptr(), S.SSDR_IQ_CF32, B, N_AVG, NFFT, 1234 + r_))
+                root_buf = S.DeviceBuffer(world * n_samples * 8)
+                for r_ in range(world):
+                    S._lib.check(S.lib.ssdr_synth_iq_dev(root_buf.ptr.value + r_ * n_samples * 8, S.SSDR_IQ_CF32, B, N_AVG, NFFT, 1234 + r_))
             sc_steps = max(2, min(args.steps, 4))
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            t_sc = 0.0
             for it in range(1 + sc_steps):
                 if it == 1:
-                    torch.cuda.synchronize(); dist.barrier(); ev[0].record()
-                dist.scatter(local_t, root_list, src=0)
-                torch.cuda.synchronize()                      # the kernel runs on the handle's own stream
-                bank.time_dev(local_t.data_ptr(), S.SSDR_IQ_CF32, px_dev.ptr, 1)
-            ev[1].record(); torch.cuda.synchronize()
-            sc_ms = max_over_ranks(ev[0].elapsed_time(ev[1]) / sc_steps)
+                    barrier()
+                    t_sc = time.perf_counter()
+                comm.scatter_from_root(root_buf.ptr.value if rank == 0 else None, world * B, N_AVG * NFFT * 8, local_buf.ptr.value)
+                bank.time_dev(local_buf.ptr, S.SSDR_IQ_CF32, px_dev.ptr, 1)      # returns when the kernel is done
+            sc_ms = max_over_ranks((time.perf_counter() - t_sc) * 1e3 / sc_steps)
             barrier()
             scatter = {"value": world * n_samples / sc_ms / 1e3, "unit": "Msamples/s", "ms_per_step": sc_ms,
                        "root_egress_gbs": (world - 1) * n_samples * 8 / sc_ms / 1e6, "steps": sc_steps,
-                       "what": "rank 0 scatters every rank's batch from its HBM over NVLink (NCCL), then all ranks run the "
-                               "kernel; scatter and kernel are not overlapped"}
-            del local_t, root_list
-            torch.cuda.empty_cache()
+                       "nccl_version": int(S.lib.ssdr_nccl_available()),
+                       "what": "rank 0 scatters every rank's batch from its HBM over NVLink (ssdr_nccl_scatter: grouped "
+                               "ncclSend/ncclRecv in the C ABI, no PyTorch), then all ranks run the kernel; not overlapped"}
+            local_buf.free()
+            if root_buf is not None:
+                root_buf.free()
         except Exception as e:                               # noqa: BLE001  (the headline arms must survive)
             scatter = {"error": repr(e)[:200]}
 
@@ -366,14 +369,14 @@ def main():
         try:
             from supersdr_b200 import sharding
             root = None
-            handle = [None]
+            handle = b""
             if rank == 0:
                 root = S.DeviceBuffer(world * n_samples * 8)
                 for r_ in range(world):
                     S._lib.check(S.lib.ssdr_synth_iq_dev(root.ptr.value + r_ * n_samples * 8, S.SSDR_IQ_CF32, B, N_AVG, NFFT, 1234 + r_))
-                handle[0] = sharding.export_device_buffer(root.ptr.value)
-            dist.broadcast_object_list(handle, src=0)
-            base = root.ptr.value if rank == 0 else sharding.open_peer_buffer(handle[0])
+                handle = sharding.export_device_buffer(root.ptr.value)
+            handle = sharding.rendezvous(handle, rank, world, port=int(os.environ.get("MASTER_PORT", "29500")) + 40)
+            base = root.ptr.value if rank == 0 else sharding.open_peer_buffer(handle)
             mine = base + rank * n_samples * 8
             pg_steps = max(2, min(args.steps, 4))
             bank.set_remote_input(rank != 0)
@@ -591,6 +594,8 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     bank.close(); iq_dev.free(); px_dev.free()
+    if comm is not None:
+        comm.close()
     if dist is not None:
         dist.destroy_process_group()
 

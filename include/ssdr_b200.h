@@ -94,6 +94,31 @@ int ssdr_ipc_export(void* dev, void* handle64);
 int ssdr_ipc_open(const void* handle64, void** dev);     /* maps the peer allocation; enables peer access */
 int ssdr_ipc_close(void* dev);
 
+/* ---------------------------------------------------------------------------------------------
+ * multi-GPU plumbing (one process per GPU): NCCL over NVLink, used only to move INPUT shards from a root rank to the
+ * ranks that own the channels, and the small pixel rows back -- channels are independent, there is no collective in the
+ * math.  The reference is a single-receiver client and has no counterpart; the shard of a rank is a
+ * contiguous block of channels, i.e. of the [batch][n_avg][nfft] input of ssdr_wf_process_dev.  libnccl is loaded with
+ * dlopen at the first call (ssdr_nccl_available() == 0 where it is missing).  All calls are asynchronous on the
+ * communicator's stream; ssdr_nccl_sync waits.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ssdr_comm* ssdr_comm_t;
+#define SSDR_NCCL_ID_BYTES 128
+int ssdr_nccl_available(void);                        /* NCCL version code (> 0) or 0 */
+int ssdr_nccl_unique_id(void* id128);                 /* rank 0: 128 opaque bytes to hand to every rank by any means */
+int ssdr_nccl_init(ssdr_comm_t* c, const void* id128, int rank, int world);      /* collective over the world */
+int ssdr_nccl_destroy(ssdr_comm_t c);
+/* The root's buffer holds rank r's shard at byte offsets[r], counts[r] bytes (arrays of `world` entries, the same on
+ * every rank); every rank receives its shard into recv_dev (the root by a device copy).  One grouped ncclSend/ncclRecv. */
+int ssdr_nccl_scatter(ssdr_comm_t c, const void* send_root_dev, const size_t* offsets, const size_t* counts,
+                      void* recv_dev, int root);
+/* The reverse: every rank's send_dev (counts[rank] bytes) lands at offsets[rank] of the root's buffer. */
+int ssdr_nccl_gather(ssdr_comm_t c, const void* send_dev, void* recv_root_dev, const size_t* offsets,
+                     const size_t* counts, int root);
+int ssdr_nccl_allreduce_max_f64(ssdr_comm_t c, double* value);   /* host scalar in/out: max over ranks (timing) */
+int ssdr_nccl_barrier(ssdr_comm_t c);
+int ssdr_nccl_sync(ssdr_comm_t c);
+
 /* Deterministic synthetic IQ written directly in HBM (bench / full-size tests): per channel three
  * tones (0.5, 0.05, 0.005 FS at hashed bins) + uniform-sum noise of sigma ~1e-3 FS, SURVEY 8d.
  * iq_dev: [batch][frames][nfft] in the given format. */

@@ -69,6 +69,15 @@ _PROTOS = {
     "ssdr_dev_memset": (_i, [_vp, _i, _sz]),
     "ssdr_device_sync": (_i, []),
     "ssdr_synth_iq_dev": (_i, [_vp, _i, _i, _i, _i, _u32]),
+    "ssdr_nccl_available": (_i, []),
+    "ssdr_nccl_unique_id": (_i, [_vp]),
+    "ssdr_nccl_init": (_i, [_pvp, _vp, _i, _i]),
+    "ssdr_nccl_destroy": (_i, [_vp]),
+    "ssdr_nccl_scatter": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
+    "ssdr_nccl_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
+    "ssdr_nccl_allreduce_max_f64": (_i, [_vp, C.POINTER(_d)]),
+    "ssdr_nccl_barrier": (_i, [_vp]),
+    "ssdr_nccl_sync": (_i, [_vp]),
     "ssdr_wf_create": (_i, [_pvp, _i, _i, _i, _i, _d, _i, _f]),
     "ssdr_wf_destroy": (_i, [_vp]),
     "ssdr_wf_set_display": (_i, [_vp, _i, _i, C.POINTER(WfDisplay)]),

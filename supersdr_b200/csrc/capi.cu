@@ -261,6 +261,15 @@ int ssdr_synth_iq_dev(void* iq_dev, int iq_format, int batch, int frames, int nf
 // =============================================================================================
 // waterfall
 // =============================================================================================
+// Master twiddle table W_N^k = (float(cos), float(-sin))(2 pi k / N), evaluated in double
+static void fill_twiddles(int N, float* tab) {
+    for (int k = 0; k < N; ++k) {
+        const double a = 2.0 * 3.14159265358979323846 * (double)k / (double)N;
+        tab[2 * k] = (float)std::cos(a);
+        tab[2 * k + 1] = (float)(-std::sin(a));
+    }
+}
+
 static size_t iq_sample_bytes(int fmt) { return fmt == SSDR_IQ_CF32 ? 8 : 4; }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
@@ -281,11 +290,7 @@ int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, d
     h->p_lo = p_lo; h->p_gamma = p_gamma;
     // spec tables: twiddles W_N^k = (cos, -sin)(2 pi k / N) and the byte thresholds
     h->h_wtab.resize(2 * (size_t)nfft);
-    for (int k = 0; k < nfft; ++k) {
-        double a = 2.0 * 3.14159265358979323846 * (double)k / (double)nfft;
-        h->h_wtab[2 * k] = (float)std::cos(a);
-        h->h_wtab[2 * k + 1] = (float)(-std::sin(a));
-    }
+    fill_twiddles(nfft, h->h_wtab.data());
     h->h_win.resize((size_t)nfft / 2);          // first half of the periodic Hann window
     for (int n = 0; n < nfft / 2; ++n)
         h->h_win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * 3.14159265358979323846 * (double)n / (double)nfft));
@@ -304,11 +309,7 @@ int ssdr_wf_create(ssdr_wf_t* out, int nfft, int batch, int n_avg, int window, d
     if ((rc = dev_alloc(&h->d_win, (size_t)nfft / 2))) return fail(rc);
     if (nfft > 16384) {
         std::vector<float> sub(2 * 16384);
-        for (int k = 0; k < 16384; ++k) {
-            double a = 2.0 * 3.14159265358979323846 * (double)k / 16384.0;
-            sub[2 * k] = (float)std::cos(a);
-            sub[2 * k + 1] = (float)(-std::sin(a));
-        }
+        fill_twiddles(16384, sub.data());
         if ((rc = dev_alloc(&h->d_wtab_sub, sub.size()))) return fail(rc);
         if ((rc = dev_alloc(&h->d_sums, (size_t)batch * nfft))) return fail(rc);
         if (cudaMemcpy(h->d_wtab_sub, sub.data(), sizeof(float) * sub.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("table upload failed"); return fail(SSDR_E_CUDA); }

@@ -212,3 +212,66 @@ def test_handles_work_from_other_threads_on_any_device(ssdr):
             bank.close(); db.close()
     finally:
         ssdr._lib.check(ssdr.lib.ssdr_init(0))
+
+
+def test_nccl_scatter_gather_two_gpus(ssdr, tmp_path):
+    """ssdr_nccl_scatter / ssdr_nccl_gather (grouped ncclSend/ncclRecv through the C ABI, no PyTorch): rank 0 scatters a
+    batch from its HBM, every rank runs the waterfall kernel on its shard, the pixel rows are gathered on rank 0 and
+    equal a single-GPU run.  Needs two GPUs (skipped on the one-GPU boxes)."""
+    import subprocess
+    import sys
+    import textwrap
+    try:
+        ssdr._lib.check(ssdr.lib.ssdr_init(1))
+    except ssdr.SsdrError:
+        pytest.skip("needs two GPUs")
+    finally:
+        ssdr._lib.check(ssdr.lib.ssdr_init(0))
+    if not ssdr.lib.ssdr_nccl_available():
+        pytest.skip("NCCL not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text("import os, sys\nsys.path.insert(0, %r)\n" % root + textwrap.dedent("""
+        import numpy as np
+        import supersdr_b200 as S
+        from supersdr_b200 import sharding
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        S.init(rank)
+        comm = sharding.Comm(rank, world)
+        total, n, N = 7, 2, 1024
+        per = n * N * 8
+        first, count = sharding.channel_shard(total, rank, world)
+        root_buf = None
+        if rank == 0:
+            root_buf = S.DeviceBuffer(total * per)
+            S._lib.check(S.lib.ssdr_synth_iq_dev(root_buf.ptr, S.SSDR_IQ_CF32, total, n, N, 5))
+        mine = S.DeviceBuffer(count * per)
+        got = comm.scatter_from_root(root_buf.ptr.value if rank == 0 else None, total, per, mine.ptr.value)
+        assert got == count * per
+        bank = S.WaterfallBank(N, count, n)
+        px = S.DeviceBuffer(count * N)
+        bank.process_dev(mine.ptr, S.SSDR_IQ_CF32, px.ptr)
+        bank.sync()
+        allpx = S.DeviceBuffer(total * N) if rank == 0 else None
+        comm.gather_rows_to_root(px.ptr.value, total, N, allpx.ptr.value if rank == 0 else None)
+        assert comm.max_over_ranks(float(rank)) == float(world - 1)
+        comm.barrier()
+        if rank == 0:
+            one = S.WaterfallBank(N, total, n)
+            ref = S.DeviceBuffer(total * N)
+            one.process_dev(root_buf.ptr, S.SSDR_IQ_CF32, ref.ptr)
+            one.sync()
+            assert np.array_equal(allpx.download(np.uint8, (total, N)), ref.download(np.uint8, (total, N)))
+            print("OK")
+        comm.close()
+    """))
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK" in outs[0]
