@@ -6,12 +6,13 @@ requires the built shared library; computing requires a B200.
 """
 from ._lib import (SsdrError, init, last_error, DeviceBuffer, PinnedArray, lib, EXPORTS, LIB_PATH,
                    SSDR_IQ_CF32, SSDR_IQ_S16BE, FS, WF_CAL_DB, KIWI_RATE, FRAME, FIR_TAPS)
-from .waterfall import WaterfallBank, WaterfallImage, kiwi_waterfall, percentile_index, create_cm, palette_u8
-from .sound import (DemodBank, InterpBank, ResampleLine, ImaAdpcmDecoder, filtering, kiwi_sound, start_audio_stream, demod_params, demod_plan,
+from .waterfall import WaterfallBank, WaterfallImage, percentile_index, create_cm, palette_u8
+from .sound import (DemodBank, InterpBank, ResampleLine, ImaAdpcmDecoder, filtering, demod_params, demod_plan,
                     design_lowpass, default_passband, unpack_iq)
+from .dropin import bind, WaterfallHotPath, SoundHotPath, parse_wf_frame, parse_snd_frame, HOT_PATH_OVERRIDES
 from .wavreader import KiwiIQWavReader, KiwiIQWavError, WavIQSource, read_kiwi_iq_wav
 
-__all__ = ["ImaAdpcmDecoder", "WaterfallImage", "create_cm", "palette_u8", "SsdrError", "init", "last_error", "DeviceBuffer", "PinnedArray", "WaterfallBank", "kiwi_waterfall",
-           "percentile_index", "DemodBank", "InterpBank", "ResampleLine", "filtering", "kiwi_sound", "start_audio_stream",
+__all__ = ["ImaAdpcmDecoder", "WaterfallImage", "create_cm", "palette_u8", "SsdrError", "init", "last_error", "DeviceBuffer", "PinnedArray", "WaterfallBank", "bind", "WaterfallHotPath", "SoundHotPath", "parse_wf_frame", "parse_snd_frame",
+           "percentile_index", "DemodBank", "InterpBank", "ResampleLine", "filtering",
            "demod_params", "demod_plan", "design_lowpass", "default_passband", "unpack_iq", "KiwiIQWavReader", "KiwiIQWavError",
            "WavIQSource", "read_kiwi_iq_wav"]

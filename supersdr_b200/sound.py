@@ -1,16 +1,14 @@
 """Audio side of the hot path.
 
 ``DemodBank`` (K4) and ``InterpBank`` (K5) are the batched engines over the C ABI
-(``ssdr_demod_*`` / ``ssdr_interp_*`` in include/ssdr_b200.h).  ``filtering`` and ``kiwi_sound`` keep
-the surface of the reference classes (utils_supersdr.py:333-348 and :901-1186): the demodulator that
-the reference leaves to the remote KiwiSDR (it only sends ``SET mod=... low_cut=... high_cut=...`` and
-``SET agc=...``, utils_supersdr.py:1022-1029) runs here on the GPU from raw IQ, followed by the
-reference's own x4 interpolation filter.
+(``ssdr_demod_*`` / ``ssdr_interp_*`` in include/ssdr_b200.h).  ``filtering`` keeps the surface of the
+reference class (utils_supersdr.py:333-348).  The demodulator that the reference leaves to the remote
+KiwiSDR (it only sends ``SET mod=... low_cut=... high_cut=...`` and ``SET agc=...``,
+utils_supersdr.py:1022-1029) runs here on the GPU from raw IQ, followed by the reference's own x4
+interpolation filter.  The drop-in for the reference class ``kiwi_sound`` is made by delegation in
+``supersdr_b200.dropin``.
 """
 import ctypes as C
-import queue
-import threading
-import time
 
 import numpy as np
 
@@ -302,210 +300,3 @@ def unpack_iq(wire_bytes):
     out = np.empty(n, np.complex64)
     check(lib.ssdr_unpack_iq_s16be(ptr(raw), ptr(out), n))
     return out
-
-
-class kiwi_sound:
-    """Drop-in for utils_supersdr.kiwi_sound (utils_supersdr.py:901-1186).
-
-    ``iq_source.read_snd_frame()`` returns ``(iq complex64[512], flags)`` (or ``None`` at end of
-    stream) in place of the SND websocket.  ``process_audio_stream`` demodulates one frame on the GPU
-    and returns ``int16[512]`` exactly where the reference returns the PCM it received;
-    ``play_buffer`` is the PortAudio callback with the reference's signature.
-    """
-    FORMAT = np.int16
-    CHANNELS = 2
-    AUDIO_RATE = 48000
-    KIWI_RATE = 12000
-    SAMPLE_RATIO = int(AUDIO_RATE / KIWI_RATE)
-    CHUNKS = 1
-    KIWI_SAMPLES_PER_FRAME = 512
-
-    def __init__(self, freq_, mode_, lc_, hc_, password_, kiwi_wf, buffer_len, volume_=100, host_=None,
-                 port_=None, subrx_=False, iq_source=None):
-        self.subrx = subrx_
-        self.kiwi_wf = kiwi_wf
-        self.host = host_ if host_ else getattr(kiwi_wf, "host", None)
-        self.port = port_ if port_ else getattr(kiwi_wf, "port", None)
-        self.FULL_BUFF_LEN = max(1, buffer_len)
-        self.audio_buffer = queue.Queue(maxsize=self.FULL_BUFF_LEN)
-        self.terminate = False
-        self.volume = volume_
-        self.max_rssi_before_mute = -20
-        self.mute_counter = 0
-        self.muting_delay = 15
-        self.adc_overflow_flag = False
-        self.status = None
-        self.run_index = 0
-        self.delta_t = 0.0
-        self.rssi = -127
-        self.freq = freq_
-        self.radio_mode = mode_
-        self.lc, self.hc = lc_, hc_
-        # AGC parameters, utils_supersdr.py:936-945
-        self.on, self.hang, self.thresh, self.slope = True, False, -80, 0
-        self.decay_other, self.decay_cw, self.gain = 4000, 1000, 50
-        self.min_agc_delay, self.max_agc_delay = 400, 8000
-        self.decay = self.decay_other
-        self.audio_balance = 0.0
-        self.freq_offset = 0
-        self.KIWI_RATE_TRUE = float(self.KIWI_RATE)
-        self.iq_source = iq_source
-        if iq_source is None:
-            raise Exception("no IQ source")
-        self.stream = iq_source
-        self._demod = DemodBank(1, self.KIWI_SAMPLES_PER_FRAME)
-        self._interp = InterpBank(1, int(self.SAMPLE_RATIO), max_samples=self.KIWI_SAMPLES_PER_FRAME * self.CHUNKS)
-        self.kiwi_filter = filtering(self.KIWI_RATE / 2, self.AUDIO_RATE)
-        self.n_tap = self.kiwi_filter.n_tap
-        gcd = np.gcd(self.KIWI_RATE, self.AUDIO_RATE)
-        self.n_low, self.n_high = int(self.KIWI_RATE / gcd), int(self.AUDIO_RATE / gcd)
-        self.late_flag = False
-        self.audio_rec = type("audio_rec_stub", (), {"recording_flag": False, "audio_buffer": []})()
-        self._push_params()
-
-    # ---- control surface: the SET messages become kernel parameters --------------------------------
-    def _push_params(self):
-        self._demod.set_params(0, [demod_params(self.radio_mode, self.lc, self.hc, 0.0, self.on, self.hang,
-                                                self.thresh, self.slope, self.decay, self.gain)])
-
-    def change_agc_delay(self, delta):
-        """utils_supersdr.py:1009-1019."""
-        if delta < 0:
-            if self.decay > self.min_agc_delay:
-                self.decay += delta
-        else:
-            if self.decay < self.max_agc_delay:
-                self.decay += delta
-        if self.radio_mode == "CW":
-            self.decay_cw = self.decay
-        else:
-            self.decay_other = self.decay
-
-    def set_agc_params(self):
-        """utils_supersdr.py:1022-1024 ('SET agc=...')."""
-        self._push_params()
-
-    def set_mode_freq_pb(self):
-        """utils_supersdr.py:1026-1029 ('SET mod=... low_cut=... high_cut=... freq=...')."""
-        self.decay = self.decay_other if self.radio_mode != "CW" else self.decay_cw
-        if hasattr(self.iq_source, "set_freq"):
-            self.iq_source.set_freq(self.freq)
-        self._push_params()
-
-    def change_passband(self, delta_low_, delta_high_):
-        """utils_supersdr.py:1078-1092."""
-        if self.radio_mode == "USB":
-            lc_, hc_ = LOW_CUT_SSB + delta_low_, HIGH_CUT_SSB + delta_high_
-        elif self.radio_mode == "LSB":
-            lc_, hc_ = -HIGH_CUT_SSB - delta_high_, -LOW_CUT_SSB - delta_low_
-        elif self.radio_mode == "AM":
-            lc_, hc_ = -HIGHLOW_CUT_AM - delta_low_, HIGHLOW_CUT_AM + delta_high_
-        elif self.radio_mode == "CW":
-            lc_, hc_ = LOW_CUT_CW + delta_low_, HIGH_CUT_CW + delta_high_
-        self.lc, self.hc = lc_, hc_
-        return lc_, hc_
-
-    def keepalive(self):
-        if hasattr(self.iq_source, "keepalive"):
-            self.iq_source.keepalive()
-
-    def close_connection(self):
-        if hasattr(self.iq_source, "close"):
-            self.iq_source.close()
-
-    # ---- hot path -------------------------------------------------------------------------------------
-    def process_audio_stream(self):
-        """utils_supersdr.py:1044-1076: returns int16[512] or None; sets rssi / adc_overflow_flag."""
-        item = self.iq_source.read_snd_frame()
-        if item is None:
-            self.terminate = True
-            if self.kiwi_wf is not None:
-                self.kiwi_wf.terminate = True
-            raise EOFError("IQ stream ended")
-        iq, flags = item
-        self.adc_overflow_flag = True if (flags & 2) else False
-        res = self._demod.process(np.asarray(iq, np.complex64).reshape(1, -1), want_f32=False)
-        self.rssi = float(res["rssi"][0, -1])
-        return res["pcm_i16"][0]
-
-    def get_audio_chunk(self):
-        try:
-            snd_buf = self.process_audio_stream()
-        except Exception:
-            self.terminate = True
-            return None
-        if snd_buf is not None:
-            self.keepalive()
-        return snd_buf
-
-    def play_buffer(self, outdata, frame_count, time_info, status):
-        """utils_supersdr.py:1106-1148, the sound-card callback."""
-        self.status = status
-        if self.late_flag:
-            try:
-                outdata[:] = 0
-            except Exception:
-                pass
-            return
-        popped = [self.audio_buffer.get() for _ in range(self.CHUNKS)]
-        popped = np.array(popped).flatten().astype(np.int16)
-        if self.SAMPLE_RATIO % 1:                           # high bandwidth kiwis (3ch 20kHz), utils_supersdr.py:1125-1126
-            if getattr(self, "_resampler", None) is None or (self._resampler.up, self._resampler.down) != (self.n_high, self.n_low):
-                self._resampler = ResampleLine(self.n_high, self.n_low)
-            out = self._resampler.process(popped.reshape(1, -1), self.volume, self.audio_balance)[0]
-        else:
-            out = self._interp.process(popped.reshape(1, -1), self.volume, self.audio_balance)[0]
-        outdata[:, 0] = out[:, 0]
-        outdata[:, 1] = out[:, 1]
-        if self.rssi > self.max_rssi_before_mute:          # mute on TX, utils_supersdr.py:1141-1147
-            self.mute_counter = self.muting_delay
-        elif self.mute_counter > 0:
-            self.mute_counter -= 1
-        if self.mute_counter > 0:
-            outdata *= 0
-        self.old_outdata = outdata[:]
-
-    def run(self):
-        """utils_supersdr.py:1150-1186 (frame pacing / late-drop bookkeeping)."""
-        self.total_delay_ms = 0.0
-        delta_time_ms = 0.0
-        self.ms_per_frame = (self.KIWI_SAMPLES_PER_FRAME / self.KIWI_RATE_TRUE) * 1000
-        self.late_flag = False
-        while not self.terminate:
-            time_prev = time.time_ns() / 1000000
-            snd_buf = self.get_audio_chunk()
-            if snd_buf is not None and not self.late_flag:
-                self.audio_buffer.put(snd_buf)
-                self.run_index += 1
-                self.total_delay_ms -= delta_time_ms
-            else:
-                self.total_delay_ms -= self.ms_per_frame
-            delta_time_ms = time.time_ns() / 1000000 - time_prev
-            self.total_delay_ms += delta_time_ms
-            if not self.late_flag and self.total_delay_ms > (self.FULL_BUFF_LEN + 2) * self.ms_per_frame:
-                self.late_flag = True
-            if self.late_flag and self.total_delay_ms < self.ms_per_frame:
-                while self.audio_buffer.qsize() < self.FULL_BUFF_LEN and not self.terminate:
-                    snd_buf = self.get_audio_chunk()
-                    if snd_buf is not None:
-                        self.audio_buffer.put(snd_buf)
-                self.late_flag = False
-                self.total_delay_ms = 0.0
-                delta_time_ms = 0.0
-
-
-def start_audio_stream(kiwi_snd, output_stream_factory=None):
-    """utils_supersdr.py:1188-1216.  ``output_stream_factory(blocksize, callback)`` stands in for
-    ``sounddevice.OutputStream`` (not available headless)."""
-    rx_t = threading.Thread(target=kiwi_snd.run, daemon=True)
-    rx_t.start()
-    while kiwi_snd.audio_buffer.qsize() < kiwi_snd.FULL_BUFF_LEN and not kiwi_snd.terminate:
-        time.sleep(0.001)
-    if kiwi_snd.terminate:
-        return (None, None)
-    stream = None
-    if output_stream_factory is not None:
-        stream = output_stream_factory(int(kiwi_snd.KIWI_SAMPLES_PER_FRAME * kiwi_snd.CHUNKS * kiwi_snd.SAMPLE_RATIO),
-                                       kiwi_snd.play_buffer)
-        stream.start()
-    return True, stream

@@ -1,14 +1,13 @@
 """Waterfall side of the hot path.
 
 ``WaterfallBank`` is the batched engine (B independent channels per GPU) over the C ABI
-(``ssdr_wf_*`` in include/ssdr_b200.h).  ``kiwi_waterfall`` keeps the attribute / method surface of
-the reference class (utils_supersdr.py:592-898) so ``supersdr.py`` can use it unchanged; it owns a
-one-channel bank and computes locally, from raw IQ frames, what the reference receives finished
-from the KiwiSDR server (uint8 W/F lines, utils_supersdr.py:780-785) and then post-processes
-(averaging :881-886, ``spectrum_db2col`` :787-813).
+(``ssdr_wf_*`` in include/ssdr_b200.h): from raw IQ frames it computes what the reference receives
+finished from the KiwiSDR server (uint8 W/F lines, utils_supersdr.py:780-785) and then post-processes
+(averaging :881-886, ``spectrum_db2col`` :787-813); ``colorrow`` is the entry for finished lines.
+``WaterfallImage`` is the scrolling image / palette / trace on the GPU.  The drop-in for the reference
+class ``kiwi_waterfall`` is made by delegation in ``supersdr_b200.dropin``.
 """
 import ctypes as C
-from collections import deque
 
 import numpy as np
 
@@ -260,214 +259,3 @@ class WaterfallImage:
             self.close()
         except Exception:
             pass
-
-
-class kiwi_waterfall:
-    """Drop-in for utils_supersdr.kiwi_waterfall (utils_supersdr.py:592-898).
-
-    Same constructor signature and public attributes; ``iq_source`` replaces the W/F websocket: any
-    object whose ``read_wf_frame()`` returns one frame of ``WF_BINS`` complex64 IQ samples (or
-    ``None`` when the stream ended).  Everything ``supersdr.py`` reads (``wf_data``, ``wf_color``,
-    ``spectrum``, ``wf_min_db`` ...) is produced by the CUDA path.
-    """
-    MAX_FREQ = 30000
-    CENTER_FREQ = int(MAX_FREQ / 2)
-    MAX_ZOOM = 14
-    WF_BINS = 1024
-    MAX_FPS = 23
-    MIN_DYN_RANGE = 40.
-    CLIP_LOWP, CLIP_HIGHP = 40., 100
-    delta_low_db, delta_high_db = 0, 0
-    low_clip_db, high_clip_db = -120, -60
-    wf_min_db, wf_max_db = low_clip_db, low_clip_db + MIN_DYN_RANGE
-    kiwi_wf_timestamp = None
-    wf_buffer_len = 3
-
-    def __init__(self, host_, port_, pass_, zoom_, freq_, eibi, disp, iq_source=None, wf_bins=None):
-        self.eibi = eibi
-        self.host, self.port, self.password = host_, port_, pass_
-        self.zoom = zoom_
-        self.freq = freq_ if freq_ else 14200
-        self.averaging_n = 1
-        self.wf_auto_scaling = True
-        if wf_bins:
-            self.WF_BINS = int(wf_bins)
-        self.BINS2PIXEL_RATIO = disp.DISPLAY_WIDTH / self.WF_BINS
-        self.old_averaging_n = self.averaging_n
-        self.dynamic_range = self.MIN_DYN_RANGE
-        self.wf_white_flag = False
-        self.terminate = False
-        self.run_index = 0
-        self.tune = self.freq
-        self.radio_mode = "USB"
-        self.span_khz = self.zoom_to_span()
-        self.start_f_khz = self.start_freq()
-        self.end_f_khz = self.end_freq()
-        self.div_list, self.subdiv_list = [], []
-        self.min_bin_spacing = 100
-        self.space_khz = 10
-        self.counter, self.actual_freq = self.start_frequency_to_counter(self.start_f_khz)
-        self.wf_color = None
-        self.freq_offset = 0
-        self.iq_source = iq_source
-        if iq_source is None:
-            raise Exception("no IQ source")          # reference raises on a failed connect, utils:667
-        self.bins_per_khz = self.WF_BINS / self.span_khz
-        self.wf_data = np.zeros((disp.WF_HEIGHT, self.WF_BINS))
-        self.wf_data_tmp = deque([], self.wf_buffer_len)
-        self.avg_spectrum_deque = deque([], self.averaging_n)
-        self._bank = None
-        self._bank_n = None
-
-    # ---- frequency / zoom arithmetic: utils_supersdr.py:747-777 --------------------------------
-    def zoom_to_span(self):
-        assert self.zoom >= 0 and self.zoom <= self.MAX_ZOOM
-        self.span_khz = self.MAX_FREQ / 2 ** self.zoom
-        return self.span_khz
-
-    def start_frequency_to_counter(self, start_frequency_):
-        assert start_frequency_ >= 0 and start_frequency_ <= self.MAX_FREQ
-        self.counter = round(start_frequency_ / self.MAX_FREQ * 2 ** self.MAX_ZOOM * self.WF_BINS)
-        start_frequency_ = self.counter * self.MAX_FREQ / self.WF_BINS / 2 ** self.MAX_ZOOM
-        return self.counter, start_frequency_
-
-    def start_freq(self):
-        self.start_f_khz = self.freq - self.span_khz / 2
-        return self.start_f_khz
-
-    def end_freq(self):
-        self.end_f_khz = self.freq + self.span_khz / 2
-        return self.end_f_khz
-
-    def offset_to_bin(self, offset_khz_):
-        return self.WF_BINS / self.span_khz * offset_khz_
-
-    def bins_to_khz(self, bins_):
-        return (1. / (self.WF_BINS / self.span_khz)) * bins_ + self.start_f_khz
-
-    def deltabins_to_khz(self, bins_):
-        return (1. / (self.WF_BINS / self.span_khz)) * bins_
-
-    def gen_div(self):
-        """Frequency-axis ticks as waterfall bin indices (behaviour of utils_supersdr.py:696-717):
-        major ticks every ``space_khz`` (x10 until at least ``min_bin_spacing`` bins apart), minor ticks
-        at a tenth of that; the spacing is escalated until one of the lists is non-empty."""
-        self.space_khz = 10
-        self.div_list, self.subdiv_list = [], []
-        lo, hi = int(self.start_f_khz), int(self.end_f_khz)
-        to_bin = lambda f: int(self.offset_to_bin(f - self.start_f_khz))
-        while not self.div_list and not self.subdiv_list:
-            minor = self.space_khz / 10
-            if self.bins_per_khz * self.space_khz > self.min_bin_spacing:
-                self.div_list = [to_bin(f) for f in range(lo, hi + 1) if not f % self.space_khz]
-            if self.bins_per_khz * minor > self.min_bin_spacing / 10:
-                self.subdiv_list = [to_bin(f) for f in range(lo, hi + 1) if not f % minor]
-            self.space_khz *= 10
-
-    def set_freq_zoom(self, freq_, zoom_):
-        """utils_supersdr.py:815-845 (the SET zoom/start message becomes a source retune)."""
-        self.freq, self.zoom = freq_, zoom_
-        self.zoom_to_span(); self.start_freq(); self.end_freq()
-        if zoom_ == 0:
-            self.freq = self.CENTER_FREQ
-            self.start_freq(); self.end_freq()
-            self.span_khz = self.MAX_FREQ
-        else:
-            if self.start_f_khz < 0:
-                self.freq = self.zoom_to_span() / 2
-                self.start_freq(); self.end_freq(); self.zoom_to_span()
-            elif self.end_f_khz > self.MAX_FREQ:
-                self.freq = self.MAX_FREQ - self.zoom_to_span() / 2
-                self.start_freq(); self.end_freq(); self.zoom_to_span()
-        self.counter, actual_freq = self.start_frequency_to_counter(self.start_f_khz)
-        if hasattr(self.iq_source, "set_zoom_start"):
-            self.iq_source.set_zoom_start(self.zoom, self.counter)
-        if self.eibi is not None and hasattr(self.eibi, "get_stations"):
-            self.eibi.get_stations(self.start_f_khz, self.end_f_khz)
-        self.bins_per_khz = self.WF_BINS / self.span_khz
-        self.gen_div()
-        return self.freq
-
-    def change_passband(self, delta_low_, delta_high_):
-        """utils_supersdr.py:859-873."""
-        if self.radio_mode == "USB":
-            lc_, hc_ = LOW_CUT_SSB + delta_low_, HIGH_CUT_SSB + delta_high_
-        elif self.radio_mode == "LSB":
-            lc_, hc_ = -HIGH_CUT_SSB - delta_high_, -LOW_CUT_SSB - delta_low_
-        elif self.radio_mode == "AM":
-            lc_, hc_ = -HIGHLOW_CUT_AM - delta_low_, HIGHLOW_CUT_AM + delta_high_
-        elif self.radio_mode == "CW":
-            lc_, hc_ = LOW_CUT_CW + delta_low_, HIGH_CUT_CW + delta_high_
-        self.lc, self.hc = lc_, hc_
-        return lc_, hc_
-
-    def keepalive(self):
-        if hasattr(self.iq_source, "keepalive"):
-            self.iq_source.keepalive()
-
-    def close_connection(self):
-        if hasattr(self.iq_source, "close"):
-            self.iq_source.close()
-
-    def set_white_flag(self):
-        self.wf_color = np.ones_like(self.wf_color) * 255
-        self.wf_data[0, :] = self.wf_color
-
-    # ---- the hot path ----------------------------------------------------------------------------
-    def _get_bank(self, n):
-        if self._bank is None or self._bank_n != n:
-            if self._bank is not None:
-                self._bank.close()
-            self._bank = WaterfallBank(self.WF_BINS, 1, n)
-            self._bank_n = n
-        return self._bank
-
-    def receive_spectrum(self):
-        """utils_supersdr.py:780-785: one line.  Here: one IQ frame -> FFT -> Kiwi byte line (float32)."""
-        frame = self.iq_source.read_wf_frame()
-        if frame is None:
-            self.terminate = True
-            return None
-        self._frames.append(np.asarray(frame, dtype=np.complex64).reshape(self.WF_BINS))
-        self.keepalive()
-        return frame
-
-    def spectrum_db2col(self):
-        """utils_supersdr.py:787-813 on the GPU: consumes the frames gathered by receive_spectrum."""
-        n = len(self._frames)
-        bank = self._get_bank(n)
-        bank.set_display(0, 1, zoom=self.zoom, auto_scale=self.wf_auto_scaling, delta_low_db=self.delta_low_db,
-                         delta_high_db=self.delta_high_db, low_clip_db=float(self.low_clip_db),
-                         dynamic_range=float(self.dynamic_range))
-        res = bank.process(np.stack(self._frames)[None, :, :])
-        sc = res["scalars"][0]
-        self.spectrum = res["spectrum"][0]
-        self.wf_color = res["colour"][0]
-        self.wf_pixels = res["pixels"][0]
-        if self.wf_auto_scaling:
-            self.low_clip_db = sc["low_clip_db"]
-            self.high_clip_db = sc["high_clip_db"]
-            self.dynamic_range = sc["dynamic_range"]
-        self.wf_min_db = sc["wf_min_db"]
-        self.wf_max_db = sc["wf_max_db"]
-
-    def run_once(self):
-        """One iteration of ``run`` (utils_supersdr.py:880-897)."""
-        self._frames = []
-        n = self.averaging_n if self.averaging_n > 1 else 1
-        for _ in range(n):
-            if self.receive_spectrum() is None:
-                return False
-        self.run_index += 1
-        self.spectrum_db2col()
-        self.wf_data_tmp.appendleft(self.wf_color)
-        if len(self.wf_data_tmp) > 0 and self.run_index > self.wf_buffer_len:
-            self.wf_data[1:, :] = self.wf_data[0:-1, :]
-            self.wf_data[0, :] = self.wf_data_tmp.pop()
-        return True
-
-    def run(self):
-        while not self.terminate:
-            if not self.run_once():
-                break
-        return

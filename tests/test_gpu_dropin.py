@@ -11,29 +11,68 @@ from oracle import c_oracle, tier_p, tier_u
 pytestmark = pytest.mark.gpu
 
 
-class FakeKiwi:
-    """Headless IQ source standing in for the W/F and SND websockets."""
+import fake_kiwi
+import fake_ref
 
-    def __init__(self, wf_frames, snd_frames):
-        self.wf, self.snd = list(wf_frames), list(snd_frames)
-        self.keepalives = 0
+
+class IQSource:
+    """Headless IQ source for the FFT path of the waterfall mixin (``iq_source.read_wf_frame``)."""
+
+    def __init__(self, wf_frames):
+        self.wf = list(wf_frames)
 
     def read_wf_frame(self):
         return self.wf.pop(0) if self.wf else None
 
-    def read_snd_frame(self):
-        return (self.snd.pop(0), 0) if self.snd else None
 
-    def keepalive(self):
-        self.keepalives += 1
+def test_waterfall_dropin_wire_frames(ssdr):
+    """The bound kiwi_waterfall fed W/F WIRE FRAMES (utils_supersdr.py:782-784) by a fake Kiwi: the product's own header
+    parse, the GPU mean + spectrum_db2col, the ring image -- against the reference's arithmetic on the same lines."""
+    K = ssdr.bind(fake_ref)
+    disp = types.SimpleNamespace(DISPLAY_WIDTH=1024, WF_HEIGHT=40)
+    rng = np.random.default_rng(3)
+    lines = np.clip(rng.normal(110, 9, (24, 1024)), 0, 255).astype(np.uint8)
+    msgs = [fake_kiwi.wf_frame(lines[i], x_bin=7, zoom=3, seq=i) for i in range(24)]
+    msgs.insert(5, b"MSG some=thing else=1")                  # a non-W/F message in between is skipped (utils_supersdr.py:782)
+    stream = fake_kiwi.FakeKiwiStream(msgs)
+    wf = K.kiwi_waterfall(stream, 3, disp)
+    assert isinstance(wf, fake_ref.kiwi_waterfall) and wf.wf_data.shape == (40, 1024) and not wf.wf_data.any()
+    st = tier_p.ColourState()
+    st.zoom = 3
+    rows = []
+    wf.averaging_n = 1
+    for it in range(8):                                       # single lines (the 6th receive is the MSG: row recoloured)
+        assert wf.run_once()
+        if it == 5:
+            continue
+        k = it if it < 5 else it - 1
+        spec, col, px = tier_p.waterfall_line(lines[k], st)
+        assert np.array_equal(wf.spectrum, spec) and np.array_equal(wf.wf_color, col) and np.array_equal(wf.wf_pixels, px)
+        assert np.float32(wf.wf_min_db) == st.wf_min_db and np.float32(wf.wf_max_db) == st.wf_max_db
+        assert wf.kiwi_wf_seq == k
+    wf.averaging_n = 4                                        # time-binning mean, utils_supersdr.py:881-888
+    for it in range(4):
+        assert wf.run_once()
+        blk = lines[7 + 4 * it: 11 + 4 * it]
+        spec, col, px = tier_p.waterfall_line(blk, st)
+        assert np.array_equal(wf.spectrum, spec) and np.array_equal(wf.wf_color, col)
+        rows.append(col)
+    # ring image == the reference's scroll (utils_supersdr.py:893-897): newest on top, three lines of delay
+    img = wf.wf_data
+    assert img.shape == (40, 1024) and img.dtype == np.float64
+    assert np.array_equal(img[0], rows[0].astype(np.float64))          # 12 lines pushed: the 9th shows on top
+    wf.set_white_flag()
+    assert np.all(wf.wf_data[0] == 255)
+    assert stream.sent.count("SET keepalive") == 23
 
 
-def test_kiwi_waterfall_dropin(ssdr):
+def test_waterfall_dropin_iq_source(ssdr):
+    """The FFT path of the same mixin: raw IQ frames instead of finished lines."""
+    K = ssdr.bind(fake_ref)
     disp = types.SimpleNamespace(DISPLAY_WIDTH=1024, WF_HEIGHT=40)
     frames = tier_u.synth_iq(1024, seed=9, frames=24)
-    src = FakeKiwi(frames, [])
-    wf = ssdr.kiwi_waterfall("fake", 8073, "", 3, 7100, None, disp, iq_source=src)
-    assert wf.WF_BINS == 1024 and wf.wf_data.shape == (40, 1024) and wf.span_khz == 30000 / 8
+    wf = K.kiwi_waterfall(fake_kiwi.FakeKiwiStream([]), 3, disp)
+    wf.iq_source = IQSource(frames)
     wf.averaging_n = 4
     st = tier_p.ColourState()
     st.zoom = 3
@@ -43,48 +82,58 @@ def test_kiwi_waterfall_dropin(ssdr):
         lines = np.stack([c_oracle.wf_frame_bytes(frames[it * 4 + k]) for k in range(4)])
         spec, col, px = tier_p.waterfall_line(lines, st)       # what the reference would compute from those lines
         assert np.array_equal(wf.spectrum, spec) and np.array_equal(wf.wf_color, col)
-        assert np.float32(wf.wf_min_db) == st.wf_min_db and np.float32(wf.wf_max_db) == st.wf_max_db
         rows.append(col)
-    # scroll buffer semantics utils:893-897: a 3-deep delay deque (maxlen 3: the very first row falls off
-    # its far end on the 4th line), scrolling starts with the 4th line, newest on top
+    # a 3-deep delay deque (maxlen 3), scrolling starts with the 4th line, newest on top (utils_supersdr.py:893-897)
     assert np.array_equal(wf.wf_data[0], rows[3].astype(np.float64)) and np.array_equal(wf.wf_data[1], rows[2])
     assert np.array_equal(wf.wf_data[2], rows[1]) and not wf.wf_data[3].any()
-    assert src.keepalives == 24
     assert not wf.run_once() and wf.terminate            # stream ended
-    assert wf.change_passband(10, -20) == (40, 2980)     # USB defaults utils:859-862
-    assert wf.set_freq_zoom(14200, 5) == 14200 and wf.span_khz == 30000 / 32
-    assert abs(wf.bins_to_khz(512) - 14200) < 1e-9
 
 
-def test_kiwi_sound_dropin(ssdr):
-    n_frames = 10
-    iq = tier_u.synth_demod_iq("usb", 512 * n_frames, seed=2)
-    src = FakeKiwi([], [iq[i * 512:(i + 1) * 512] for i in range(n_frames)])
-    wf = types.SimpleNamespace(host="fake", port=8073, terminate=False, kiwi_wf_timestamp=0)
-    snd = ssdr.kiwi_sound(7100, "USB", 30, 3000, "", wf, 4, iq_source=src)
-    assert snd.SAMPLE_RATIO == 4 and snd.n_tap == 33 and snd.KIWI_SAMPLES_PER_FRAME == 512
-    ref, rssi = tier_u.demod(iq, tier_u.DemodParams("usb", 30, 3000), tier_u.DemodState())
+def test_sound_dropin_wire_frames(ssdr):
+    """The bound kiwi_sound fed SND WIRE FRAMES: (a) int16 PCM frames as a stock Kiwi sends them (utils_supersdr.py:
+    1065-1072) -> header fields + GPU interpolator; (b) IQ frames (SET mod=iq, kiwi/client.py:443-454) -> unpack +
+    demodulator + interpolator on the GPU."""
+    K = ssdr.bind(fake_ref)
+    wfobj = types.SimpleNamespace(terminate=False)
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-20000, 20000, (6, 512)).astype(np.int16)
+    msgs = [fake_kiwi.snd_frame(pcm[i], rssi_dbm=-73.5 - i, flags=2 * (i == 2), seq=i) for i in range(6)]
+    snd = K.kiwi_sound(fake_kiwi.FakeKiwiStream(msgs), "USB", 30, 3000, wfobj, 4)
     st = tier_p.InterpState()
     snd.volume, snd.audio_balance = 80, 0.25
-    for k in range(n_frames):
-        pcm = snd.process_audio_stream()
-        assert pcm.dtype == np.int16 and pcm.shape == (512,)
-        assert np.abs(pcm.astype(int) - tier_u.pcm_to_i16(ref[k * 512:(k + 1) * 512]).astype(int)).max() <= 1
-        assert abs(snd.rssi - rssi[k]) < 1e-3
-        snd.audio_buffer.put(pcm)
+    snd.audio_rec.recording_flag = True
+    for i in range(6):
+        got = snd.process_audio_stream()
+        assert got.dtype == np.int16 and np.array_equal(got, pcm[i])
+        assert abs(snd.rssi - (-73.5 - i)) < 1e-9 and snd.adc_overflow_flag == (i == 2)
+        snd.audio_buffer.put(got)
         out = np.zeros((2048, 2), np.int16)
         snd.play_buffer(out, 2048, None, None)
-        _, o2 = tier_p.play_buffer(pcm, st, 80, 0.25)
+        mono, o2 = tier_p.play_buffer(pcm[i], st, 80, 0.25)
         assert np.abs(out.astype(int) - o2.astype(int)).max() <= 1
+        assert np.abs(snd.audio_rec.audio_buffer[-1].astype(int) - mono.astype(np.int16).astype(int)).max() <= 1
     with pytest.raises(EOFError):
         snd.process_audio_stream()
-    assert snd.terminate and wf.terminate
-    snd.radio_mode = "CW"
-    assert snd.change_passband(0, 0) == (400, 800)
+    assert snd.terminate and wfobj.terminate
+    # (b) IQ frames
+    n_frames = 8
+    iq = tier_u.synth_demod_iq("usb", 512 * n_frames, seed=2)
+    iq = (np.rint(iq.real) + 1j * np.rint(iq.imag)).astype(np.complex64)          # the wire carries int16 counts
+    msgs = [fake_kiwi.iq_frame(iq[i * 512:(i + 1) * 512], seq=i, gpssec=i) for i in range(n_frames)]
+    wfobj = types.SimpleNamespace(terminate=False)
+    snd = K.kiwi_sound(fake_kiwi.FakeKiwiStream(msgs), "USB", 30, 3000, wfobj, 4)
+    snd.iq_mode = True
+    ref, rssi = tier_u.demod(iq, tier_u.DemodParams("usb", 30, 3000), tier_u.DemodState())
+    for k in range(n_frames):
+        got = snd.process_audio_stream()
+        assert got.dtype == np.int16 and got.shape == (512,)
+        assert np.abs(got.astype(int) - tier_u.pcm_to_i16(ref[k * 512:(k + 1) * 512]).astype(int)).max() <= 1
+        assert abs(snd.rssi - rssi[k]) < 1e-3
+    # the reference's SET senders still run (control plane inherited) and the kernel parameters follow them
+    snd.radio_mode, snd.lc, snd.hc, snd.decay = "CW", 400, 800, 1000
     snd.set_mode_freq_pb()
-    assert snd.decay == 1000                                   # decay_cw, utils_supersdr.py:1027
-    snd.change_agc_delay(100)
-    assert snd.decay == 1100 and snd.decay_cw == 1100
+    snd.set_agc_params()
+    assert snd.stream.sent[-2].startswith("SET mod=cw low_cut=400 high_cut=800") and snd.stream.sent[-1].startswith("SET agc=1")
     # TX mute, utils_supersdr.py:1141-1147
     snd.rssi = -10
     snd.audio_buffer.put(np.full(512, 1000, np.int16))
