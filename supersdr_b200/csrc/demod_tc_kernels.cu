@@ -66,7 +66,11 @@ constexpr unsigned CHB = 4 * GRPB;        // per channel: re octets 0, 1 then im
 constexpr unsigned A_BYTES = WARPS * CHB; // 24576: the hi (TF32) part of the rows, 128-byte swizzle
 // the lo part of the rows as bfloat16, no swizzle: 16-byte K chunks (8 samples) in four planes, row r of a plane at r * 16
 constexpr unsigned A16_ROWS = 4 * WARPS * GROWS;          // 192 rows per tile
-constexpr unsigned A16_LBO = A16_ROWS * 16 + 16;          // plane pitch (3088: +16 spreads the planes over the banks)
+// plane pitch 3136 = 64 bytes mod 128: a warp's 8-byte stores cover 4 planes x 4 rows, 16 bytes each; with the planes half a
+// bank window apart, (4 plane + row) mod 8 is uniform over the eight 16-byte bank groups and the store takes its two
+// wavefronts (a pitch of +16 bytes made plane and row collide: up to 4 wavefronts, a third of the kernel's shared-memory
+// wavefronts were conflict replays -- profiles/r1zzz_demod_tc_ncu_summary.txt)
+constexpr unsigned A16_LBO = A16_ROWS * 16 + 64;
 constexpr unsigned A16_BYTES = 13 * 1024;                 // 4 planes, rounded so that the next tile's hi part stays 1024-aligned
 constexpr unsigned TILE_BYTES = A_BYTES + A16_BYTES;
 constexpr unsigned B16_LBO = 4 * 128;                     // B_hi as bfloat16, no swizzle: K chunk of 8 -> 32 rows x 16 bytes

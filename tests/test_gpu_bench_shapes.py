@@ -232,7 +232,10 @@ def test_waterfall_bytes_vs_float64_every_size(ssdr, N, window):
 
 def test_config2_sampled_rows_vs_float64(ssdr):
     """Full BASELINE config 2 (4096 ch x 10 x 16384, generated in HBM): for sampled channels the averaged line
-    (spectrum x n_avg = sum of the ten byte lines) against the float64 statement, boundary-aware per frame."""
+    (spectrum x n_avg = sum of the ten byte lines) against the float64 statement, boundary-aware per frame.  Error
+    budget per bin: 4 eps log2(N) ||x w||_2 -- twice the constant of the single-frame comparator, because 1.3 million
+    bins are checked here (on 3.9 million bins the CPU statement of the same arithmetic uses up to 0.85 of the single
+    budget) and the chain-twiddle pass multiplies up to four rounded twiddles."""
     B, n, N = 4096, 10, 16384
     iq = ssdr.DeviceBuffer(B * n * N * 8)
     px = ssdr.DeviceBuffer(B * N)
@@ -249,7 +252,7 @@ def test_config2_sampled_rows_vs_float64(ssdr):
         hi = np.zeros(N, np.int64)
         for f in range(n):                                   # per-frame admissible byte range
             v, amp = tier_u.wf_frame_db(x[f])
-            err = tier_u.fft_error_bound(x[f])
+            err = 2.0 * tier_u.fft_error_bound(x[f])
             with np.errstate(divide="ignore", invalid="ignore"):
                 band = 20.0 * np.log10(1.0 + err / np.maximum(amp, 1e-300))
             band = np.where(np.isfinite(band), band, 1e9) + 1e-6

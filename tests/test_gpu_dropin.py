@@ -60,7 +60,8 @@ def test_waterfall_dropin_wire_frames(ssdr):
     # ring image == the reference's scroll (utils_supersdr.py:893-897): newest on top, three lines of delay
     img = wf.wf_data
     assert img.shape == (40, 1024) and img.dtype == np.float64
-    assert np.array_equal(img[0], rows[0].astype(np.float64))          # 12 lines pushed: the 9th shows on top
+    # 12 lines pushed: deque(maxlen=3).appendleft + pop shows line k - 2 on top at line k (the first line is dropped)
+    assert np.array_equal(img[0], rows[1].astype(np.float64)) and np.array_equal(img[1], rows[0].astype(np.float64))
     wf.set_white_flag()
     assert np.all(wf.wf_data[0] == 255)
     assert stream.sent.count("SET keepalive") == 23
