@@ -41,9 +41,10 @@ def main():
                               "msamples_per_s": round(B * a.n_avg * N / ms / 1e3, 1), "gbs": round(alg / ms / 1e6, 1),
                               "frac_of_measured_hbm": round(alg / ms / 1e6 / peak, 4),
                               "l2_resident": in_bytes < 126e6,
-                              # N > 16384: front pass + scratch round trip: 3x the single-pass input bytes move
-                              "hbm_passes": 3 if N > 16384 else 1,
-                              "moved_gbs": round((alg + (2 * in_bytes if N > 16384 else 0)) / ms / 1e6, 1)}), flush=True)
+                              # N > 16384: three-kernel path (default): front pass + scratch round trip through HBM, 3x the input bytes
+                              # move; fused kernel (SSDR_WF_BIG=fused): the scratch stays in L2, but slower
+                              "big_path": ("fused" if os.environ.get("SSDR_WF_BIG") == "fused" else "3k") if N > 16384 else None,
+                              "hbm_passes": (1 if os.environ.get("SSDR_WF_BIG") == "fused" else 3) if N > 16384 else 1}), flush=True)
             bank.close(); iq.free(); px.free()
 
 

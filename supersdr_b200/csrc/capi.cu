@@ -90,7 +90,7 @@ struct ssdr_wf {
     // large-N path (nfft > 16384)
     float* d_wtab_sub = nullptr;      // 16384-point twiddle table of the sub-transforms
     void* d_scratch = nullptr;        // front-pass output, sized for scratch_ch channels
-    int scratch_ch = 0;
+    size_t scratch_bytes = 0;
     uint16_t* d_sums = nullptr;       // [batch][nfft]
     float* d_thr = nullptr;
     ssdr_wf_display_t* d_disp = nullptr;
@@ -391,14 +391,16 @@ static WfLaunch wf_base(ssdr_wf_t h) {
     return a;
 }
 
-// large-N path: the front-pass scratch holds `channels` channels (complex64, same size as their input)
+// large-N path: scratch of the front pass -- per SM for the fused kernel (L2-resident), per channel for the three-kernel path
 static int wf_ensure_scratch(ssdr_wf_t h, int channels) {
-    if (h->nfft <= 16384 || h->scratch_ch >= channels) return SSDR_OK;
+    if (h->nfft <= 16384) return SSDR_OK;
+    const size_t need = wf_big_scratch_bytes(h->nfft, h->n_avg, channels);
+    if (h->scratch_bytes >= need) return SSDR_OK;
     SSDR_CUDA(cudaStreamSynchronize(h->compute));
-    cudaFree(h->d_scratch); h->d_scratch = nullptr; h->scratch_ch = 0;
-    int rc = dev_alloc(reinterpret_cast<unsigned char**>(&h->d_scratch), (size_t)channels * h->n_avg * h->nfft * 8);
+    cudaFree(h->d_scratch); h->d_scratch = nullptr; h->scratch_bytes = 0;
+    int rc = dev_alloc(reinterpret_cast<unsigned char**>(&h->d_scratch), need);
     if (rc) return rc;
-    h->scratch_ch = channels;
+    h->scratch_bytes = need;
     return SSDR_OK;
 }
 

@@ -66,11 +66,12 @@ constexpr unsigned CHB = 4 * GRPB;        // per channel: re octets 0, 1 then im
 constexpr unsigned A_BYTES = WARPS * CHB; // 24576: the hi (TF32) part of the rows, 128-byte swizzle
 // the lo part of the rows as bfloat16, no swizzle: 16-byte K chunks (8 samples) in four planes, row r of a plane at r * 16
 constexpr unsigned A16_ROWS = 4 * WARPS * GROWS;          // 192 rows per tile
-// plane pitch 3136 = 64 bytes mod 128: a warp's 8-byte stores cover 4 planes x 4 rows, 16 bytes each; with the planes half a
-// bank window apart, (4 plane + row) mod 8 is uniform over the eight 16-byte bank groups and the store takes its two
-// wavefronts (a pitch of +16 bytes made plane and row collide: up to 4 wavefronts, a third of the kernel's shared-memory
-// wavefronts were conflict replays -- profiles/r1zzz_demod_tc_ncu_summary.txt)
-constexpr unsigned A16_LBO = A16_ROWS * 16 + 64;
+// plane pitch 3104 = 32 bytes (8 banks) mod 128: every shared-memory access to the planes is then conflict-free --
+//   * the mixer's 8-byte stores (half-warp = 2 rows x 4 planes x 2 halves): word offsets 8 plane + 4 row + 2 half, 16 distinct;
+//   * the 16-byte history copies (quarter-warp = 4 planes x 2 rows): 8 plane + 4 row, 8 distinct 4-word groups.
+// (The r1 pitch of 3088 made plane and row collide, 3136 made planes p and p + 2 collide: ncu counted 2 x the ideal
+// wavefronts on these instructions, a quarter of the kernel's shared-memory wavefronts -- profiles/r2e_demod_tc_ncu_summary.txt.)
+constexpr unsigned A16_LBO = A16_ROWS * 16 + 32;
 constexpr unsigned A16_BYTES = 13 * 1024;                 // 4 planes, rounded so that the next tile's hi part stays 1024-aligned
 constexpr unsigned TILE_BYTES = A_BYTES + A16_BYTES;
 constexpr unsigned B16_LBO = 4 * 128;                     // B_hi as bfloat16, no swizzle: K chunk of 8 -> 32 rows x 16 bytes
@@ -366,11 +367,13 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 for (int i = 0; i < SPL; ++i) park[32 * i] = y[i];
             }
 #endif
+            // suspend-time hint: the warp sleeps in hardware until the commit arrives (or 2 us pass) instead of spinning
+            // through try_wait / yield / branch -- a fifth of the kernel's issued instructions were this loop
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
                 "WAIT_%=:\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                "@!p bra WAIT_%=;\n\t}" ::"r"(barp), "r"(phase) : "memory");
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+                "@!p bra WAIT_%=;\n\t}" ::"r"(barp), "r"(phase), "r"(2000u) : "memory");
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (active) {

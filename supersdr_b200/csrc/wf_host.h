@@ -33,6 +33,8 @@ struct WfLaunch {
 };
 
 int wf_plan(int nfft, int* radices);
+bool wf_big_fused();                                                   // large-N path: fused kernel (default) or three kernels
+size_t wf_big_scratch_bytes(int nfft, int n_avg, int channels);        // scratch the large-N path needs for `channels` channels
 int wf_launch(const WfLaunch& a, cudaStream_t st);
 
 struct DemodLaunch;

@@ -20,12 +20,14 @@
 
 #include <cstdint>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <vector>
 
 #include "common.cuh"
 #include "fft_radix.cuh"
+#include "tmem_scratch.cuh"
 #include "wf_host.h"
 
 // Developer timing experiments (scripts/exp_variants.sh): SSDR_EXP is a bit mask that removes one phase of the
@@ -867,6 +869,161 @@ __global__ void __launch_bounds__(256) wf_front_kernel(const void* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Large frames, fused (opt-in, SSDR_WF_BIG=fused; measured slower than the three-kernel path, see wf_big_fused()): ONE persistent kernel does the front pass and the rf 16384-point sub-transforms of
+// a frame back to back on the same SM, so the rf sub-frames travel through a per-CTA scratch (rf x 128 KB) that never
+// leaves L2 -- HBM sees the samples once (8 B/sample) instead of three times (read, scratch write, scratch read).
+// The byte sums of the rf sub-transforms (rf x 16 packed words per thread) live in TENSOR MEMORY (tmem_scratch.cuh):
+// the SM's registers and shared memory are full (the 16384-point plan), its tensor memory is idle.  Arithmetic:
+// exactly the three-kernel path's (same device functions, same order), so the results are bit-identical.
+// ---------------------------------------------------------------------------------------------
+SSDR_DEV void tmem_st4(unsigned addr, const uint4& v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+SSDR_DEV uint4 tmem_ld4(unsigned addr) {
+    uint4 v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// last radix-32 pass + power + byte + accumulate into the thread's tensor-memory words (16 per sub-transform)
+template <class C>
+SSDR_DEV void pass_last_tmem(const float2* d, int t, unsigned tm_acc, bool first_frame, const WfKernelParams& kp, unsigned long long* bar) {
+    const float4* p = reinterpret_cast<const float4*>(d + 34 * t);
+    float2 x[32];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const float4 v = p[m];
+        x[2 * m] = make_float2(v.x, v.y);
+        x[2 * m + 1] = make_float2(v.z, v.w);
+    }
+    if constexpr (C::SPLIT) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+    }
+    dft<32>(x);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 a = make_uint4(0u, 0u, 0u, 0u);
+        if (!first_frame) { a = tmem_ld4(tm_acc + 4 * c); tmem_wait_ld(); }
+        const uint4 k8 = quantise8(x + 8 * c, kp);
+        a.x += k8.x; a.y += k8.y; a.z += k8.z; a.w += k8.w;
+        tmem_st4(tm_acc + 4 * c, a);
+    }
+    tmem_wait_st();
+}
+
+struct WfBigParams {
+    WfKernelParams kp;              // kp.wtab = 16384-point table, kp.sums = [batch][rf * 16384], kp.rf, kp.batch = channels
+    const float2* wtab_big;         // N-point master table (front-pass chain twiddles W_N^j)
+    const float* win_big;           // first half of the N-point Hann window (global memory)
+    float2* scratch;                // [gridDim.x][rf][16384] complex64, L2-resident
+};
+
+template <int RF, int FMT, bool WINDOW>
+__global__ void __launch_bounds__(512, 1)
+wf_big_fused_kernel(const WfBigParams bp) {
+    using C = Cfg<14>;
+    constexpr int M = 16384, G = C::G;
+    const WfKernelParams& kp = bp.kp;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2* d = reinterpret_cast<float2*>(smem + C::SM_DATA);
+    float2* tw1 = reinterpret_cast<float2*>(smem + C::SM_TW1);
+    float2* w1s = reinterpret_cast<float2*>(smem + C::SM_W1);
+    unsigned* tm_slot = reinterpret_cast<unsigned*>(smem + C::SM_RED);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + C::SM_MBAR);
+    const int t = threadIdx.x, warp = t >> 5;
+
+    for (int e = t; e < C::TW1; e += blockDim.x) { const int q = e / 32 + 1, j = e & 31; tw1[e] = kp.wtab[j * q * (M / 1024)]; }
+#pragma unroll
+    for (int i = 0; i < C::NB0; ++i) w1s[t + i * C::THREADS] = __ldg(kp.wtab + t + i * G);
+    constexpr int TM_COLS = 64 * RF;                             // 4 warps per lane quarter x RF sub-transforms x 16 words
+    if (warp == 0) tmem_alloc_cols(tm_slot, TM_COLS);
+    tmem_fence_before();
+    if (t == 0) mbar_init(bar, G / 32);
+    __syncthreads();
+    tmem_fence_after();
+    // this thread's tensor-memory words: lane quarter (warp & 3), RF x 16 columns per warp of the quarter
+    const unsigned tm_base = *tm_slot + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 16 * RF);
+    unsigned frames_done = 0;
+    float2* scr = bp.scratch + (size_t)blockIdx.x * RF * M;
+    constexpr unsigned sample_bytes = (FMT == SSDR_IQ_CF32) ? 8u : 4u;
+
+    for (int ch = blockIdx.x; ch < kp.batch; ch += (int)gridDim.x) {
+#pragma unroll 1
+        for (int f = 0; f < kp.n_avg; ++f) {
+            const size_t fr = (size_t)ch * kp.n_avg + f;
+            // the next frame -> L2 while this one is transformed (one bulk request)
+            if (kp.prefetch && t == 0 && (f + 1 < kp.n_avg || ch + (int)gridDim.x < kp.batch)) {
+                const size_t nxt = (f + 1 < kp.n_avg) ? fr + 1 : (size_t)(ch + gridDim.x) * kp.n_avg;
+                prefetch_l2(static_cast<const unsigned char*>(kp.iq) + nxt * (size_t)RF * M * sample_bytes, (unsigned)(RF * M) * sample_bytes);
+            }
+            // ---- front pass (radix RF over stride 16384): window, butterfly, chain twiddles W_N^(j q) -> scratch --------
+#pragma unroll 4
+            for (int i = 0; i < M / 512; ++i) {
+                const int j = t + 512 * i;
+                float2 x[RF];
+#pragma unroll
+                for (int b = 0; b < RF; ++b) x[b] = load_iq<FMT>(kp.iq, fr * (size_t)(RF * M) + (size_t)(j + b * M));
+                if constexpr (WINDOW) {
+                    float wv[RF / 2];
+#pragma unroll
+                    for (int m = 0; m < RF / 2; ++m) wv[m] = __ldg(bp.win_big + j + m * M);
+                    l1_window<RF>(x, wv);
+                } else {
+                    l1<RF>(x);
+                }
+                dft_rest<RF>(x);
+                tw_two_level<RF>(x, __ldg(bp.wtab_big + j));
+#pragma unroll
+                for (int q = 0; q < RF; ++q) __stcg(scr + (size_t)q * M + j, x[q]);
+            }
+            __syncthreads();                                      // the sub-frames are in L2, visible to the whole CTA
+            // ---- the RF 16384-point sub-transforms (no window), byte sums of sub-transform q in tensor memory ---------------
+#pragma unroll 1
+            for (int q = 0; q < RF; ++q) {
+                const float2* src = scr + (size_t)q * M;
+                float2 xa[C::R0], xb[C::R0];
+#pragma unroll
+                for (int m = 0; m < C::R0; ++m) xa[m] = __ldcg(src + t + m * C::M0);
+#pragma unroll
+                for (int m = 0; m < C::R0; ++m) xb[m] = __ldcg(src + t + G + m * C::M0);
+                first_math<C, false>(xa, 0, nullptr, nullptr, t, w1s[t]);
+                if (frames_done) mbar_wait(bar, (frames_done - 1) & 1u);
+                first_store<C>(xa, 0, d, t);
+                first_math<C, false>(xb, 1, nullptr, nullptr, t, w1s[t + C::THREADS]);
+                first_store<C>(xb, 1, d, t);
+                __syncthreads();
+                {
+                    const int lvl = (t >> 7) & 3;
+                    if (lvl) { const long long c0 = clock64(); while (clock64() - c0 < lvl * C::STAGGER) { } }
+                }
+                pass_mid<C>(d, tw1, t);
+                __syncwarp();
+                pass_last_tmem<C>(d, t, tm_base + 16 * q, f == 0, kp, bar);
+                ++frames_done;
+            }
+            // every sub-transform's first-pass loads were followed by a CTA barrier: the next front pass may overwrite the scratch
+        }
+        // ---- byte sums of the RF sub-transforms -> global sums in output order (rf apart), as the three-kernel path --------
+#pragma unroll 1
+        for (int q = 0; q < RF; ++q) {
+            unsigned acc[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 a = tmem_ld4(tm_base + 16 * q + 4 * c);
+                acc[4 * c] = a.x; acc[4 * c + 1] = a.y; acc[4 * c + 2] = a.z; acc[4 * c + 3] = a.w;
+            }
+            tmem_wait_ld();
+            sums_stage<C>(reinterpret_cast<unsigned*>(d), 0, t, ch * RF + q, acc, kp, (t >> 5) + C::R0 * (t & 31));
+            __syncthreads();                                      // the stage is the frame buffer
+        }
+    }
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free_cols(*tm_slot, TM_COLS);
+}
+
 // One CTA per channel: sums uint16[N] (output order) -> scalars, colour row, pixels, spectrum.
 // Same arithmetic as colour_stage (utils_supersdr.py:787-813); the keys are re-read from
 // global memory (L2) instead of living in registers.
@@ -1014,10 +1171,59 @@ int wf_plan(int nfft, int* radices) {
     return n;
 }
 
+// Large-N path selection: the three-kernel path through an HBM scratch (default) or the fused kernel (SSDR_WF_BIG=fused).
+// Measured (profiles/r2f_sweep_big_*.jsonl, 32768 points x 10 frames): three kernels 182 Gsamples/s, fused 162 -- the fused
+// kernel moves a third of the bytes over HBM but serialises the latency-bound front pass with the sub-transforms on
+// each SM (no registers / shared memory left for a producer warp or a staging buffer); interleaving the next frame's
+// front pass with the sub-transforms was slower still (131).  The three-kernel path stays the default.
+bool wf_big_fused() {
+    static const bool fused = [] { const char* e = std::getenv("SSDR_WF_BIG"); return e && !std::strcmp(e, "fused"); }();
+    return fused;
+}
+size_t wf_big_scratch_bytes(int nfft, int n_avg, int channels) {
+    if (nfft <= 16384) return 0;
+    return wf_big_fused() ? (size_t)sm_count() * nfft * 8 : (size_t)channels * n_avg * nfft * 8;
+}
+
+// fused: front pass + sub-transforms in one persistent kernel (scratch stays in L2) -> colour kernel (two launches)
+static int launch_big_fused(const WfLaunch& a, WfKernelParams kp, cudaStream_t st) {
+    const int rf = a.nfft / 16384;
+    using C = Cfg<14>;
+    WfBigParams bp;
+    bp.kp = kp;
+    bp.kp.iq = a.iq; bp.kp.wtab = reinterpret_cast<const float2*>(a.wtab_sub); bp.kp.batch = a.batch; bp.kp.sums = a.sums; bp.kp.rf = rf;
+    bp.kp.pixels = nullptr; bp.kp.colour = nullptr; bp.kp.spectrum = nullptr; bp.kp.scalars = nullptr;
+    bp.wtab_big = reinterpret_cast<const float2*>(a.wtab); bp.win_big = a.win; bp.scratch = reinterpret_cast<float2*>(a.scratch);
+    const int grid = std::min(a.batch, sm_count());
+    auto launch = [&](auto kern) -> int {
+        SSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SM_BYTES));
+        kern<<<grid, 512, C::SM_BYTES, st>>>(bp);
+        count_launch();
+        SSDR_CUDA(cudaGetLastError());
+        return SSDR_OK;
+    };
+    int rc;
+#define SSDR_BIGF(RF, FMT) (a.window ? launch(wf_big_fused_kernel<RF, FMT, true>) : launch(wf_big_fused_kernel<RF, FMT, false>))
+    if (rf == 2) rc = (a.iq_format == SSDR_IQ_CF32) ? SSDR_BIGF(2, SSDR_IQ_CF32) : SSDR_BIGF(2, SSDR_IQ_S16BE);
+    else rc = (a.iq_format == SSDR_IQ_CF32) ? SSDR_BIGF(4, SSDR_IQ_CF32) : SSDR_BIGF(4, SSDR_IQ_S16BE);
+#undef SSDR_BIGF
+    if (rc) return rc;
+    WfKernelParams k3 = kp;
+    k3.sums = a.sums;
+    const size_t smem = ((size_t)255 * a.n_avg + 1 + 32 + 8) * sizeof(unsigned);
+    SSDR_CUDA(cudaFuncSetAttribute(wf_colour_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int g3 = std::min(a.batch, sm_count() * 2);
+    wf_colour_big_kernel<<<g3, 1024, smem, st>>>(k3, a.nfft);
+    count_launch();
+    SSDR_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
 // N = 32768 / 65536: front pass -> 16384-point kernel in sums mode -> colour kernel (three launches)
 static int launch_big(const WfLaunch& a, WfKernelParams kp, cudaStream_t st) {
     const int rf = a.nfft / 16384;
     if (!a.scratch || !a.sums || !a.wtab_sub) { set_error("large-N launch without scratch buffers"); return SSDR_E_STATE; }
+    if (wf_big_fused()) return launch_big_fused(a, kp, st);
     const size_t pts = (size_t)a.batch * a.n_avg * 16384;
     int grid = (int)std::min<size_t>((pts + 255) / 256, (size_t)sm_count() * 32);
     float2* scr = reinterpret_cast<float2*>(a.scratch);

@@ -266,3 +266,28 @@ def test_full_size_config2_properties(ssdr):
         o.close()
     for o in (iq, px, px2):
         o.free()
+
+
+def test_large_frames_fused_kernel_equals_three_kernel_path(ssdr, tmp_path):
+    """The opt-in fused large-frame kernel (SSDR_WF_BIG=fused: front pass + sub-transforms on one SM, sub-frames through an
+    L2-resident scratch, byte sums in tensor memory) gives the rows of the default three-kernel path bit for bit.  The
+    switch is read once per process, so the fused run is a subprocess."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "fused.npz"
+    code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
+            "import supersdr_b200 as S\nfrom oracle import tier_u\nres = {}\n"
+            "for N, B, n in ((32768, 151, 2), (65536, 5, 3)):\n"
+            "    bank = S.WaterfallBank(N, B, n); bank.set_display(zoom=1)\n"
+            "    r = bank.process(tier_u.synth_batch(B, n, N, seed=N + B))\n"
+            "    res['px%%d' %% N], res['sp%%d' %% N] = r['pixels'], r['spectrum']\n"
+            "np.savez(%r, **res)\n") % (root, str(out))
+    subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, SSDR_WF_BIG="fused"), timeout=600)
+    got = np.load(out)
+    for N, B, n in ((32768, 151, 2), (65536, 5, 3)):
+        bank = ssdr.WaterfallBank(N, B, n)
+        bank.set_display(zoom=1)
+        r = bank.process(tier_u.synth_batch(B, n, N, seed=N + B))
+        assert np.array_equal(got["px%d" % N], r["pixels"]) and np.array_equal(got["sp%d" % N], r["spectrum"])
+        bank.close()
