@@ -245,7 +245,10 @@ static void fft_dif(cpx* d, int N, const int* radices, int np, const float* tab,
     int L = N;
     for (int p = 0; p < np; ++p) {
         int r = radices[p], M = L / r, step = N / L;
-        int use_table = (M * (r - 1) <= SO_TABLE_PASS_MAX);
+        /* table twiddles for the small passes and (round 2) for the radix-16 pass of the 16384-point plan, whose 30
+         * per-thread twiddles the kernel keeps in tensor memory; the remaining chain passes: 4096 / 8192 first pass,
+         * large-N front pass */
+        int use_table = (M * (r - 1) <= SO_TABLE_PASS_MAX) || (L == 16384 && r == 16);
         for (int base = 0; base < N; base += L) {
             for (int j = 0; j < M; ++j) {
                 cpx x[32], w[32];

@@ -15,8 +15,25 @@ def main():
     ap.add_argument("--fmt", default="cf32", choices=["cf32", "s16be"])
     ap.add_argument("--max-bytes", type=float, default=8e9)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--gpus", type=int, default=1, help="N > 1: one child process per GPU runs the same sweep on its own shard of "
+                    "`batch` channels per GPU (channels are independent: no collective); prints the per-point aggregate")
     a = ap.parse_args()
-    S.init(0)
+    if a.gpus > 1:
+        import subprocess
+        cmd = [sys.executable, os.path.abspath(__file__), "--sizes", a.sizes, "--batches", a.batches, "--n-avg", str(a.n_avg),
+               "--fmt", a.fmt, "--max-bytes", str(a.max_bytes), "--iters", str(a.iters)]
+        procs = [subprocess.Popen(cmd + ["--device", str(d)], stdout=subprocess.PIPE, text=True) for d in range(a.gpus)]
+        outs = [[json.loads(l) for l in p.communicate()[0].splitlines() if l.startswith("{")] for p in procs]
+        for rows in zip(*outs):
+            r0 = dict(rows[0])
+            r0.update({"n_gpus": a.gpus, "batch_per_gpu": r0["batch"], "ms": max(r["ms"] for r in rows),
+                       "msamples_per_s": round(sum(r["msamples_per_s"] for r in rows), 1), "gbs": round(sum(r["gbs"] for r in rows), 1),
+                       "frac_of_measured_hbm": round(min(r["frac_of_measured_hbm"] for r in rows), 4),
+                       "frac_per_gpu": [r["frac_of_measured_hbm"] for r in rows]})
+            print(json.dumps(r0), flush=True)
+        return
+    S.init(a.device)
     try:
         peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:

@@ -92,13 +92,19 @@ struct Cfg {
     // W_N^j of the first-pass butterflies (chain passes only): LG 14 parks this thread's two values in a thread-private
     // shared-memory column, LG 13 keeps its four in registers (the column would cost the second CTA per SM), smaller
     // sizes share one table of M0 = 1024 entries
-    static constexpr int W1_MODE = (NP == 2) ? 0 : (LG == 14) ? 1 : (LG == 13) ? 2 : 3;
+    // LG 14 (round 2): no chain -- the 2 x 15 first-pass twiddles W_N^(j q) of a thread are loop invariant and live in
+    // TENSOR MEMORY (tmem_scratch.cuh), read back with tcgen05.ld: 30 complex multiplies per thread and frame instead of
+    // 58, no shared-memory column, and the loads read no registers
+    static constexpr bool TW_DIRECT = (LG == 14);
+    static constexpr int TM_WORDS = 64;                                       // per thread: NB0 x 32 words (15 float2 + pad)
+    static constexpr int TM_COLS = (THREADS / 128) * TM_WORDS;                // 4 warps share a lane quarter: 256 columns
+    static constexpr int W1_MODE = (NP == 2) ? 0 : (LG == 14) ? 0 : (LG == 13) ? 2 : 3;
     static constexpr size_t W1_BYTES = (W1_MODE == 1) ? (size_t)THREADS * NB0 * sizeof(float2) : (W1_MODE == 3) ? (size_t)M0 * sizeof(float2) : 0;
     static constexpr size_t SM_W1 = SM_ACC + (size_t)THREADS * 16 * sizeof(unsigned);
     static constexpr size_t SM_WIN = SM_W1 + W1_BYTES;                                   // first half of the Hann window, N/2 floats
     static constexpr size_t SM_RED = SM_WIN + (size_t)(N / 2) * sizeof(float);
     static constexpr size_t SM_MBAR = SM_RED + (size_t)FPC * 8 * sizeof(int);
-    static constexpr size_t SM_BYTES = SM_MBAR + 8;
+    static constexpr size_t SM_BYTES = SM_MBAR + 16;       // mbarrier + the tensor-memory base address slot
 };
 
 struct WfKernelParams {
@@ -121,6 +127,7 @@ struct WfKernelParams {
     float p_gamma;
     float est_c1, est_c0;           // byte value ~= log2(P) * c1 + c0   (rounded to nearest = the byte)
     int key_bits;                   // bits needed for 255 * n_avg (selection iterations)
+    int stagger;                    // cycles between the warp groups' starts of the warp-local passes (0: the size's default)
 };
 
 // ---- sample load (K6 fused): complex64 or Kiwi big-endian int16 pairs (kiwi/client.py:449-453) --
@@ -231,7 +238,7 @@ SSDR_DEV void first_load(float2 (&x)[C::R0], int i, int t, const void* src, size
 
 // First pass, part 2: window, radix-R0 butterfly and twiddles of butterfly i, in registers.
 template <class C, bool WINDOW>
-SSDR_DEV void first_math(float2 (&x)[C::R0], int i, const float2* tw0, const float* win, int t, float2 w1) {
+SSDR_DEV void first_math(float2 (&x)[C::R0], int i, const float2* tw0, const float* win, int t, float2 w1, unsigned tm_tw = 0u) {
     constexpr int R = C::R0, M = C::M0, G = C::G;
     constexpr bool TABLE = (M == 32);
     const int j = t + i * G;
@@ -252,6 +259,17 @@ SSDR_DEV void first_math(float2 (&x)[C::R0], int i, const float2* tw0, const flo
     if constexpr (TABLE) {
 #pragma unroll
         for (int q = 1; q < R; ++q) x[q] = cmul(x[q], tw0[(q - 1) * 32 + j]);
+    } else if constexpr (C::TW_DIRECT) {
+        // table twiddles W_N^(j q), q = 1..15, from this thread's tensor-memory words (two loads of eight twiddles)
+        unsigned w[16];
+        tmem_ld16(tm_tw + 32u * (unsigned)i, w);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 1; q <= 8; ++q) x[q] = cmul(x[q], make_float2(__uint_as_float(w[2 * q - 2]), __uint_as_float(w[2 * q - 1])));
+        tmem_ld16(tm_tw + 32u * (unsigned)i + 16u, w);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 9; q < R; ++q) x[q] = cmul(x[q], make_float2(__uint_as_float(w[2 * q - 18]), __uint_as_float(w[2 * q - 17])));
     } else {
         tw_two_level<R>(x, w1);
     }
@@ -714,6 +732,32 @@ wf_fft_kernel(const WfKernelParams kp) {
         if (threadIdx.x == 0) mbar_init(bar, G / 32);
         __syncthreads();
     }
+    unsigned tm_tw = 0u;                      // this thread's tensor-memory words (TW_DIRECT)
+    unsigned* tm_slot = reinterpret_cast<unsigned*>(smem + C::SM_MBAR) + 2;
+    if constexpr (C::TW_DIRECT) {
+        const int warp = threadIdx.x >> 5;
+        if (warp == 0) tmem_alloc_cols(tm_slot, C::TM_COLS);
+        tmem_fence_before();
+        __syncthreads();
+        tmem_fence_after();
+        tm_tw = *tm_slot + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * C::TM_WORDS);
+#pragma unroll
+        for (int i = 0; i < C::NB0; ++i) {
+            const int j = t + i * G;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                unsigned v[16];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int q = 8 * half + k + 1;                       // q = 1..16 (16: padding)
+                    const float2 w = (q < C::R0) ? __ldg(kp.wtab + ((j * q) & (N - 1))) : make_float2(0.f, 0.f);
+                    v[2 * k] = __float_as_uint(w.x); v[2 * k + 1] = __float_as_uint(w.y);
+                }
+                tmem_st16(tm_tw + 32u * (unsigned)i + 16u * (unsigned)half, v);
+            }
+        }
+        tmem_wait_st();
+    }
 
     constexpr unsigned sample_bytes = (FMT == SSDR_IQ_CF32) ? 8u : 4u;
     const int ch_stride = (int)gridDim.x * FPC;
@@ -741,7 +785,7 @@ wf_fft_kernel(const WfKernelParams kp) {
 #endif
             };
             if constexpr (C::NB0 == 1) {
-                first_math<C, WINDOW>(x0, 0, tw0, win, t, w1_of(0));
+                first_math<C, WINDOW>(x0, 0, tw0, win, t, w1_of(0), tm_tw);
                 buffer_free();
                 first_store<C>(x0, 0, d, t);
             } else {
@@ -752,11 +796,11 @@ wf_fft_kernel(const WfKernelParams kp) {
 #pragma unroll
                 for (int i = 0; i < C::NB0; i += 2) {
                     first_load<C, FMT>(xb, i + 1, t, kp.iq, off);
-                    first_math<C, WINDOW>(xa, i, tw0, win, t, w1_of(i));
+                    first_math<C, WINDOW>(xa, i, tw0, win, t, w1_of(i), tm_tw);
                     if (i == 0) buffer_free();
                     first_store<C>(xa, i, d, t);
                     if (i + 2 < C::NB0) first_load<C, FMT>(xa, i + 2, t, kp.iq, off);
-                    first_math<C, WINDOW>(xb, i + 1, tw0, win, t, w1_of(i + 1));
+                    first_math<C, WINDOW>(xb, i + 1, tw0, win, t, w1_of(i + 1), tm_tw);
                     first_store<C>(xb, i + 1, d, t);
                 }
             }
@@ -766,7 +810,8 @@ wf_fft_kernel(const WfKernelParams kp) {
             // from here each warp owns a contiguous 1024-point (NP == 3) / 32-point sub-transform: warp-local
             if constexpr (C::STAGGER > 0) {
                 const int lvl = (LG == 14) ? ((threadIdx.x >> 7) & 3) : (LG == 13) ? ((threadIdx.x >> 6) & 3) : ((threadIdx.x >> 5) & 3);     // four levels
-                if (lvl) { const long long c0 = clock64(); while (clock64() - c0 < lvl * C::STAGGER) { } }   // (__nanosleep is too coarse: 2.08 ms)
+                const int stg = kp.stagger > 0 ? kp.stagger : C::STAGGER;
+                if (lvl) { const long long c0 = clock64(); while (clock64() - c0 < lvl * stg) { } }   // (__nanosleep is too coarse: 2.08 ms)
             }
 #if !(SSDR_EXP & 16)
             if constexpr (C::NP == 3) {
@@ -794,6 +839,11 @@ wf_fft_kernel(const WfKernelParams kp) {
                                (C::NP == 3) ? ((t >> 5) + C::R0 * (t & 31)) : t, (C::NP == 3) ? 32 : 1, 2 * C::PADN);
 #endif
         if constexpr (C::SPLIT) group_sync<C>(slot);     // the row stage has been read before the next channel's first store
+    }
+    if constexpr (C::TW_DIRECT) {
+        tmem_fence_before();
+        __syncthreads();
+        if ((threadIdx.x >> 5) == 0) tmem_free_cols(*tm_slot, C::TM_COLS);
     }
 }
 
@@ -929,22 +979,40 @@ wf_big_fused_kernel(const WfBigParams bp) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* d = reinterpret_cast<float2*>(smem + C::SM_DATA);
     float2* tw1 = reinterpret_cast<float2*>(smem + C::SM_TW1);
-    float2* w1s = reinterpret_cast<float2*>(smem + C::SM_W1);
     unsigned* tm_slot = reinterpret_cast<unsigned*>(smem + C::SM_RED);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + C::SM_MBAR);
     const int t = threadIdx.x, warp = t >> 5;
 
     for (int e = t; e < C::TW1; e += blockDim.x) { const int q = e / 32 + 1, j = e & 31; tw1[e] = kp.wtab[j * q * (M / 1024)]; }
-#pragma unroll
-    for (int i = 0; i < C::NB0; ++i) w1s[t + i * C::THREADS] = __ldg(kp.wtab + t + i * G);
-    constexpr int TM_COLS = 64 * RF;                             // 4 warps per lane quarter x RF sub-transforms x 16 words
+    // tensor memory per thread: 64 words of first-pass twiddles (as wf_fft_kernel<14>) + RF x 16 words of byte sums;
+    // four warps share a lane quarter: 4 x (64 + 16 RF) = 384 / 512 columns -> the whole tensor memory
+    constexpr int TM_PER_THREAD = C::TM_WORDS + 16 * RF;
+    constexpr int TM_COLS = 512;
+    static_assert(4 * TM_PER_THREAD <= 512, "tensor memory budget");
     if (warp == 0) tmem_alloc_cols(tm_slot, TM_COLS);
     tmem_fence_before();
     if (t == 0) mbar_init(bar, G / 32);
     __syncthreads();
     tmem_fence_after();
-    // this thread's tensor-memory words: lane quarter (warp & 3), RF x 16 columns per warp of the quarter
-    const unsigned tm_base = *tm_slot + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 16 * RF);
+    // this thread's tensor-memory words: lane quarter (warp & 3), TM_PER_THREAD columns per warp of the quarter
+    const unsigned tm_tw = *tm_slot + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * TM_PER_THREAD);
+    const unsigned tm_base = tm_tw + (unsigned)C::TM_WORDS;
+#pragma unroll
+    for (int i = 0; i < C::NB0; ++i) {
+        const int j = t + i * G;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            unsigned v[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int q = 8 * half + k + 1;
+                const float2 w = (q < C::R0) ? __ldg(kp.wtab + ((j * q) & (M - 1))) : make_float2(0.f, 0.f);
+                v[2 * k] = __float_as_uint(w.x); v[2 * k + 1] = __float_as_uint(w.y);
+            }
+            tmem_st16(tm_tw + 32u * (unsigned)i + 16u * (unsigned)half, v);
+        }
+    }
+    tmem_wait_st();
     unsigned frames_done = 0;
     float2* scr = bp.scratch + (size_t)blockIdx.x * RF * M;
     constexpr unsigned sample_bytes = (FMT == SSDR_IQ_CF32) ? 8u : 4u;
@@ -988,10 +1056,10 @@ wf_big_fused_kernel(const WfBigParams bp) {
                 for (int m = 0; m < C::R0; ++m) xa[m] = __ldcg(src + t + m * C::M0);
 #pragma unroll
                 for (int m = 0; m < C::R0; ++m) xb[m] = __ldcg(src + t + G + m * C::M0);
-                first_math<C, false>(xa, 0, nullptr, nullptr, t, w1s[t]);
+                first_math<C, false>(xa, 0, nullptr, nullptr, t, make_float2(1.f, 0.f), tm_tw);
                 if (frames_done) mbar_wait(bar, (frames_done - 1) & 1u);
                 first_store<C>(xa, 0, d, t);
-                first_math<C, false>(xb, 1, nullptr, nullptr, t, w1s[t + C::THREADS]);
+                first_math<C, false>(xb, 1, nullptr, nullptr, t, make_float2(1.f, 0.f), tm_tw);
                 first_store<C>(xb, 1, d, t);
                 __syncthreads();
                 {
@@ -1265,6 +1333,7 @@ int wf_launch(const WfLaunch& a, cudaStream_t st) {
     kp.lines = a.lines; kp.batch = a.batch; kp.n_avg = a.n_avg; kp.p_lo = a.p_lo; kp.p_gamma = a.p_gamma;
     kp.est_c1 = a.est_c1; kp.est_c0 = a.est_c0; kp.prefetch = a.remote_input ? 0 : 1;
     kp.key_bits = 1;
+    if (const char* e = std::getenv("SSDR_WF_STAGGER")) kp.stagger = std::atoi(e);      // developer knob (scripts/exp_stagger.sh)
     while ((1 << kp.key_bits) <= 255 * a.n_avg) ++kp.key_bits;
     const int lg = ilog2(a.nfft);
     if (!a.lines && lg > 14) return launch_big(a, kp, st);
