@@ -96,8 +96,9 @@ struct Cfg {
     // TENSOR MEMORY (tmem_scratch.cuh), read back with tcgen05.ld: 30 complex multiplies per thread and frame instead of
     // 58, no shared-memory column, and the loads read no registers
     static constexpr bool TW_DIRECT = (LG == 14);
-    static constexpr int TM_WORDS = 64;                                       // per thread: NB0 x 32 words (15 float2 + pad)
-    static constexpr int TM_COLS = (THREADS / 128) * TM_WORDS;                // 4 warps share a lane quarter: 256 columns
+    static constexpr bool TM_MID = TW_DIRECT;                                 // middle-pass twiddles in tensor memory as well
+    static constexpr int TM_WORDS = TM_MID ? 128 : 64;                        // per thread: NB0 x 32 words (15 float2 + pad) [+ 64: 31 float2 + pad]
+    static constexpr int TM_COLS = (THREADS / 128) * TM_WORDS;                // 4 warps share a lane quarter: 256 / 512 columns
     static constexpr int W1_MODE = (NP == 2) ? 0 : (LG == 14) ? 0 : (LG == 13) ? 2 : 3;
     static constexpr size_t W1_BYTES = (W1_MODE == 1) ? (size_t)THREADS * NB0 * sizeof(float2) : (W1_MODE == 3) ? (size_t)M0 * sizeof(float2) : 0;
     static constexpr size_t SM_W1 = SM_ACC + (size_t)THREADS * 16 * sizeof(unsigned);
@@ -306,18 +307,43 @@ SSDR_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
 }
 
 // radix-32 pass over sub-transforms of length 1024 (NP == 3 only): table twiddles W_1024^(j q)
-template <class C>
-SSDR_DEV void pass_mid(float2* d, const float2* tw1, int t) {
+// TM_MID (LG 14, round 2): the 31 twiddles of this lane come from the thread's tensor-memory words (tm_mid .. + 64) in
+// four chunks of eight, the next chunk in flight while the current one multiplies, instead of 31 shared-memory loads.
+template <class C, bool TM_MID = false>
+SSDR_DEV void pass_mid(float2* d, const float2* tw1, int t, unsigned tm_mid = 0u) {
     const int j = t & 31;
     float2* p = d + (t >> 5) * (1024 + 64) + j;
     float2 x[32];
 #pragma unroll
     for (int m = 0; m < 32; ++m) x[m] = p[34 * m];
+    if constexpr (TM_MID) {
+        unsigned wa[16], wb[16];
+        tmem_ld16(tm_mid, wa);                       // twiddles q = 1..8 arrive during the butterfly
 #if !(SSDR_EXP & 8)
-    dft<32>(x);
+        dft<32>(x);
+#endif
+        tmem_wait_ld();
+        tmem_ld16(tm_mid + 16u, wb);                 // q = 9..16
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[1 + k] = cmul(x[1 + k], make_float2(__uint_as_float(wa[2 * k]), __uint_as_float(wa[2 * k + 1])));
+        tmem_wait_ld();
+        tmem_ld16(tm_mid + 32u, wa);                 // q = 17..24
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[9 + k] = cmul(x[9 + k], make_float2(__uint_as_float(wb[2 * k]), __uint_as_float(wb[2 * k + 1])));
+        tmem_wait_ld();
+        tmem_ld16(tm_mid + 48u, wb);                 // q = 25..31 (+ padding)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[17 + k] = cmul(x[17 + k], make_float2(__uint_as_float(wa[2 * k]), __uint_as_float(wa[2 * k + 1])));
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 7; ++k) x[25 + k] = cmul(x[25 + k], make_float2(__uint_as_float(wb[2 * k]), __uint_as_float(wb[2 * k + 1])));
+    } else {
+#if !(SSDR_EXP & 8)
+        dft<32>(x);
 #endif
 #pragma unroll
-    for (int q = 1; q < 32; ++q) x[q] = cmul(x[q], tw1[(q - 1) * 32 + j]);
+        for (int q = 1; q < 32; ++q) x[q] = cmul(x[q], tw1[(q - 1) * 32 + j]);
+    }
 #pragma unroll
     for (int q = 0; q < 32; ++q) p[34 * q] = x[q];
 }
@@ -756,6 +782,19 @@ wf_fft_kernel(const WfKernelParams kp) {
                 tmem_st16(tm_tw + 32u * (unsigned)i + 16u * (unsigned)half, v);
             }
         }
+        if constexpr (C::TM_MID) {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                unsigned v[16];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int q = 8 * c4 + k + 1;                         // q = 1..32 (32: padding)
+                    const float2 w = (q < 32) ? __ldg(kp.wtab + (t & 31) * q * (N / 1024)) : make_float2(0.f, 0.f);
+                    v[2 * k] = __float_as_uint(w.x); v[2 * k + 1] = __float_as_uint(w.y);
+                }
+                tmem_st16(tm_tw + 64u + 16u * (unsigned)c4, v);
+            }
+        }
         tmem_wait_st();
     }
 
@@ -815,7 +854,7 @@ wf_fft_kernel(const WfKernelParams kp) {
             }
 #if !(SSDR_EXP & 16)
             if constexpr (C::NP == 3) {
-                pass_mid<C>(d, tw1, t);
+                pass_mid<C, C::TM_MID>(d, tw1, t, tm_tw + 64u);
                 __syncwarp();
             }
 #endif
@@ -986,7 +1025,8 @@ wf_big_fused_kernel(const WfBigParams bp) {
     for (int e = t; e < C::TW1; e += blockDim.x) { const int q = e / 32 + 1, j = e & 31; tw1[e] = kp.wtab[j * q * (M / 1024)]; }
     // tensor memory per thread: 64 words of first-pass twiddles (as wf_fft_kernel<14>) + RF x 16 words of byte sums;
     // four warps share a lane quarter: 4 x (64 + 16 RF) = 384 / 512 columns -> the whole tensor memory
-    constexpr int TM_PER_THREAD = C::TM_WORDS + 16 * RF;
+    constexpr int TW_WORDS = 64;                                 // first-pass twiddles only (the middle pass keeps its shared-memory table here)
+    constexpr int TM_PER_THREAD = TW_WORDS + 16 * RF;
     constexpr int TM_COLS = 512;
     static_assert(4 * TM_PER_THREAD <= 512, "tensor memory budget");
     if (warp == 0) tmem_alloc_cols(tm_slot, TM_COLS);
@@ -996,7 +1036,7 @@ wf_big_fused_kernel(const WfBigParams bp) {
     tmem_fence_after();
     // this thread's tensor-memory words: lane quarter (warp & 3), TM_PER_THREAD columns per warp of the quarter
     const unsigned tm_tw = *tm_slot + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * TM_PER_THREAD);
-    const unsigned tm_base = tm_tw + (unsigned)C::TM_WORDS;
+    const unsigned tm_base = tm_tw + (unsigned)TW_WORDS;
 #pragma unroll
     for (int i = 0; i < C::NB0; ++i) {
         const int j = t + i * G;
