@@ -43,6 +43,13 @@
 #ifndef SSDR_TC_TILES
 #define SSDR_TC_TILES 4           // tiles (groups of four warps) per CTA: 16 warps at 128 registers
 #endif
+#ifndef SSDR_TC_L1_PREFETCH
+#define SSDR_TC_L1_PREFETCH 1     // 1: the next frame's IQ lines are pulled into L1 just before the back end of the previous frame, so the
+                                  //    mixer's loads after the MMA wait hit L1 instead of paying the L2 latency on the tile's critical path
+#endif
+#ifndef SSDR_TC_L2_AHEAD
+#define SSDR_TC_L2_AHEAD (SSDR_TC_L1_PREFETCH ? 2 : 1)      // frames ahead of the L2 prefetch
+#endif
 #ifndef SSDR_TC_EARLYMIX
 #define SSDR_TC_EARLYMIX 0        // 1: mixer arithmetic of frame b + 1 before the wait for the MMAs of frame b (parked in
                                   //    shared memory across the wait); 0: after it.  Measured: 1 is 13 % slower.
@@ -248,8 +255,8 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             float2 xin[SPL];
 #pragma unroll
             for (int q = 0; q < 4; ++q) demod_ld_iq4<FMT>(kp.iq, s0 + 128 * q + 4 * lane, &xin[4 * q]);
-            if (b + 1 < nblk) {                             // next frame -> L2 (one 128-byte line per lane)
-                const char* nx = static_cast<const char*>(kp.iq) + (s0 + FR) * (FMT == SSDR_IQ_CF32 ? 8 : 4) + lane * 128;
+            if (b + SSDR_TC_L2_AHEAD < nblk) {              // a later frame -> L2 (one 128-byte line per lane)
+                const char* nx = static_cast<const char*>(kp.iq) + (s0 + SSDR_TC_L2_AHEAD * FR) * (FMT == SSDR_IQ_CF32 ? 8 : 4) + lane * 128;
                 if (FMT == SSDR_IQ_CF32 || lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
             }
 #pragma unroll
@@ -359,6 +366,12 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 }
             }
             __syncwarp();
+#if SSDR_TC_L1_PREFETCH
+            if (active && b + 1 < nblk) {                   // frame b + 1 -> L1 while the back end and the MMAs run
+                const char* nx = static_cast<const char*>(kp.iq) + ((size_t)ch * kp.pitch + (size_t)(b + 1) * FR) * (FMT == SSDR_IQ_CF32 ? 8 : 4) + lane * 128;
+                if (FMT == SSDR_IQ_CF32 || lane < 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+            }
+#endif
             if (b > 0) back_end(b - 1);                     // overlaps the MMAs of frame b
 #if SSDR_TC_EARLYMIX
             if (active && b + 1 < nblk) {                   // ... and so does the mixer of frame b + 1; its output waits in shared

@@ -267,3 +267,28 @@ def test_adpcm_reference_golden(ssdr):
     d = np.tile(data[0, :512 + 5], (300, 1))
     ref = ssdr.ImaAdpcmDecoder().decode(bytes(data[0, :512 + 5]))
     assert np.array_equal(big.decode(d), np.tile(ref, (300, 1)))
+
+
+def test_argument_validation_of_the_advice_items(ssdr):
+    """an AGC decay that would overflow the float32 envelope scan is refused (instead of poisoning the
+    channel's state with NaN); the *_dev entry points refuse device pointers that are not 16-byte aligned (instead of
+    faulting); batches beyond the grid's y dimension are refused with a message."""
+    import ctypes
+    bank = ssdr.DemodBank(2, 1024)
+    with pytest.raises(ssdr.SsdrError):
+        bank.set_params(0, [ssdr.demod_params("usb", decay=0.5)] * 2)
+    bank.set_params(0, [ssdr.demod_params("usb", decay=1.0)] * 2)            # the shortest accepted decay stays finite
+    x = np.stack([tier_u.synth_demod_iq("usb", 1024, seed=s) for s in (1, 2)])
+    r = bank.process(x)
+    assert np.all(np.isfinite(r["pcm_f32"])) and np.all(np.isfinite(bank.process(x)["pcm_f32"]))
+    iq = ssdr.DeviceBuffer(2 * 1024 * 8 + 64)
+    out = ssdr.DeviceBuffer(2 * 1024 * 4 + 64)
+    with pytest.raises(ssdr.SsdrError):
+        bank.process_dev(ctypes.c_void_p(iq.ptr.value + 8), ssdr.SSDR_IQ_CF32, 1024, out.ptr)
+    with pytest.raises(ssdr.SsdrError):
+        bank.process_dev(iq.ptr, ssdr.SSDR_IQ_CF32, 1024, ctypes.c_void_p(out.ptr.value + 4))
+    bank.process_dev(iq.ptr, ssdr.SSDR_IQ_CF32, 1024, out.ptr)
+    bank.sync()
+    bank.close(); iq.free(); out.free()
+    with pytest.raises(ssdr.SsdrError):
+        ssdr.InterpBank(70000, 4)
