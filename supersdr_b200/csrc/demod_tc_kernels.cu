@@ -44,8 +44,8 @@
 #define SSDR_TC_TILES 4           // tiles (groups of four warps) per CTA: 16 warps at 128 registers
 #endif
 #ifndef SSDR_TC_L1_PREFETCH
-#define SSDR_TC_L1_PREFETCH 1     // 1: the next frame's IQ lines are pulled into L1 just before the back end of the previous frame, so the
-                                  //    mixer's loads after the MMA wait hit L1 instead of paying the L2 latency on the tile's critical path
+#define SSDR_TC_L1_PREFETCH 0     // 1: the next frame's IQ lines are pulled into L1 just before the back end of the previous frame, so the
+                                  //    mixer's loads after the MMA wait would hit L1.  Measured (round 2): 181 instead of 186 Gsamples/s -- 0.
 #endif
 #ifndef SSDR_TC_L2_AHEAD
 #define SSDR_TC_L2_AHEAD (SSDR_TC_L1_PREFETCH ? 2 : 1)      // frames ahead of the L2 prefetch
