@@ -9,6 +9,6 @@ for m in "$@"; do
 done
 wait
 for m in "$@"; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build/exp/libssdr_exp$m.so ../../build/csrc/capi.o ../../build/exp/wf_$m.o ../../build/csrc/demod_kernels.o ../../build/csrc/misc_kernels.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build/exp/libssdr_exp$m.so ../../build/csrc/capi.o ../../build/exp/wf_$m.o ../../build/csrc/demod_kernels.o ../../build/csrc/demod_tc_kernels.o ../../build/csrc/misc_kernels.o ../../build/csrc/nccl_comm.o -ldl
 done
 ls -la ../../build/exp/*.so

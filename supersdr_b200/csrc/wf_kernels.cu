@@ -16,6 +16,7 @@
 // free).  The per-bin byte sums over the n_avg frames never leave registers (16 packed uint16 pairs
 // per thread); the colour stage selects the order statistics from those registers and transposes the
 // finished row through the (then idle) frame buffer so that HBM sees only coalesced row stores.
+#include <cuda.h>                // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -34,6 +35,28 @@
 // kernel at a time to measure its marginal cost.  Results are WRONG when any bit is set; the product build has 0.
 #ifndef SSDR_EXP
 #define SSDR_EXP 0
+#endif
+
+// Developer timeline (scripts/wf_trace.py): -DSSDR_TRACE records clock64() at the phase boundaries of every warp of CTA 0
+// for the first frames of a launch.  Not in the product build.
+#ifdef SSDR_TRACE
+#define TRACE_FRAMES 40
+#define TRACE_PTS 16
+__device__ long long g_wf_trace[TRACE_FRAMES * 16 * TRACE_PTS];
+__device__ int g_wf_trace_frames;
+extern "C" int ssdr_debug_wf_trace(long long* out, int* frames) {
+    cudaMemcpyFromSymbol(out, g_wf_trace, sizeof(long long) * TRACE_FRAMES * 16 * TRACE_PTS);
+    cudaMemcpyFromSymbol(frames, g_wf_trace_frames, sizeof(int));
+    return 0;
+}
+// time stamps go to shared memory (a global store in the middle of the frame would sit in front of the proxy fence of the
+// staging hook and distort what it measures); the warp's row is flushed to global memory at the end of the frame
+__device__ __forceinline__ long long* trace_slots() { __shared__ long long s[16 * TRACE_PTS]; return s; }
+#define TRACE(pt) do { if ((threadIdx.x & 31) == 0) trace_slots()[(threadIdx.x >> 5) * TRACE_PTS + (pt)] = clock64(); } while (0)
+#define TRACE_FLUSH() do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_frame < TRACE_FRAMES) { for (int k_ = 0; k_ < TRACE_PTS; ++k_) \
+    g_wf_trace[(tr_frame * 16 + (threadIdx.x >> 5)) * TRACE_PTS + k_] = trace_slots()[(threadIdx.x >> 5) * TRACE_PTS + k_]; } } while (0)
+#else
+#define TRACE(pt) do { } while (0)
 #endif
 
 namespace ssdr {
@@ -105,7 +128,12 @@ struct Cfg {
     static constexpr size_t SM_WIN = SM_W1 + W1_BYTES;                                   // first half of the Hann window, N/2 floats
     static constexpr size_t SM_RED = SM_WIN + (size_t)(N / 2) * sizeof(float);
     static constexpr size_t SM_MBAR = SM_RED + (size_t)FPC * 8 * sizeof(int);
-    static constexpr size_t SM_BYTES = SM_MBAR + 16;       // mbarrier + the tensor-memory base address slot
+    static constexpr size_t SM_TBAR = SM_MBAR + 16;        // mbarrier + the tensor-memory base address slot
+    static constexpr size_t SM_BYTES = SM_TBAR + 16 * 8;   // STAGED: one transaction barrier per warp
+    // STAGED (LG 14, local input): the raw samples of a frame are bulk-copied by the TMA engine into the frame buffer
+    // itself -- each warp's own 1024-point region, free from the moment the warp has loaded its last-pass inputs -- one
+    // frame ahead; no global load in the frame loop.  Column mapping: warp w owns first-pass columns 64 w .. 64 w + 63.
+    static constexpr bool CAN_STAGE = (LG == 14);
 };
 
 struct WfKernelParams {
@@ -239,10 +267,10 @@ SSDR_DEV void first_load(float2 (&x)[C::R0], int i, int t, const void* src, size
 
 // First pass, part 2: window, radix-R0 butterfly and twiddles of butterfly i, in registers.
 template <class C, bool WINDOW>
-SSDR_DEV void first_math(float2 (&x)[C::R0], int i, const float2* tw0, const float* win, int t, float2 w1, unsigned tm_tw = 0u) {
+SSDR_DEV void first_math(float2 (&x)[C::R0], int i, const float2* tw0, const float* win, int t, float2 w1, unsigned tm_tw = 0u, int jcol = -1) {
     constexpr int R = C::R0, M = C::M0, G = C::G;
     constexpr bool TABLE = (M == 32);
-    const int j = t + i * G;
+    const int j = (jcol >= 0) ? jcol : t + i * G;
 #if SSDR_EXP & 256
     return;
 #endif
@@ -278,9 +306,9 @@ SSDR_DEV void first_math(float2 (&x)[C::R0], int i, const float2* tw0, const flo
 
 // First pass, part 3: scatter the outputs of butterfly i into the frame buffer.
 template <class C>
-SSDR_DEV void first_store(const float2 (&x)[C::R0], int i, float2* d, int t) {
+SSDR_DEV void first_store(const float2 (&x)[C::R0], int i, float2* d, int t, int jcol = -1) {
     constexpr int R = C::R0, M = C::M0;
-    const int j = t + i * C::G;
+    const int j = (jcol >= 0) ? jcol : t + i * C::G;
     float2* o = (M == 32) ? d + j : d + j + 2 * (j >> 5);
 #pragma unroll
     for (int q = 0; q < R; ++q) o[q * (M + M / 16)] = x[q];
@@ -304,6 +332,36 @@ SSDR_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
         "WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra WAIT_%=;\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// ---- TMA staging of the raw frame (STAGED kernels) ----------------------------------------------
+// expect `bytes` of bulk-copy traffic on the barrier and arrive once
+SSDR_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.release.cta.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// one bulk copy global -> shared memory by the TMA engine; completion is counted in bytes on the mbarrier
+SSDR_DEV void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+SSDR_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one 2-D tile global -> shared memory (UTMALDG): box of the tensor map at element coordinates (x, y)
+SSDR_DEV void tma_tile_2d(void* dst_smem, const CUtensorMap* tmap, int x, int y, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(tmap), "r"(x), "r"(y), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// sample m (row) of first-pass butterfly i of this lane from the warp's staged tile [16 rows][64 samples]
+template <int FMT>
+SSDR_DEV float2 staged_sample(const unsigned char* region, int m, int i, int lane) {
+    if constexpr (FMT == SSDR_IQ_CF32) {
+        return reinterpret_cast<const float2*>(region)[m * 64 + i * 32 + lane];
+    } else {
+        const unsigned v = reinterpret_cast<const unsigned*>(region)[m * 64 + i * 32 + lane];
+        const unsigned sw = __byte_perm(v, 0u, 0x2301);
+        const int re = (int)(short)(sw & 0xffffu), im = (int)sw >> 16;
+        return make_float2((float)re, (float)im);
+    }
 }
 
 // radix-32 pass over sub-transforms of length 1024 (NP == 3 only): table twiddles W_1024^(j q)
@@ -355,9 +413,12 @@ SSDR_DEV void pass_mid(float2* d, const float2* tw1, int t, unsigned tm_mid = 0u
 // frames live in a thread-private uint4[4] column of shared memory (two uint16 lanes per word, no carry:
 // <= 25500), touched with 128-bit accesses only.  STRIDE = threads per CTA (column stride in uint4).
 template <int STRIDE>
-SSDR_DEV void last_epilogue(float2 (&x)[32], uint4* accs, bool first_frame, const WfKernelParams& kp) {
+SSDR_DEV void last_epilogue(float2 (&x)[32], uint4* accs, bool first_frame, const WfKernelParams& kp, int tr_frame = 1 << 30) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
+        if (c == 1) TRACE(12);
+        if (c == 2) TRACE(13);
+        if (c == 3) TRACE(14);
         uint4 a = make_uint4(0u, 0u, 0u, 0u);
         if (!first_frame) a = accs[c * STRIDE];
 #if SSDR_EXP & 1
@@ -374,8 +435,9 @@ SSDR_DEV void last_epilogue(float2 (&x)[32], uint4* accs, bool first_frame, cons
 }
 
 // last radix-32 pass (sub-transform length 32, no twiddles) + power + byte + accumulate
-template <class C>
-SSDR_DEV void pass_last(const float2* d, int t, uint4* accs, bool first_frame, const WfKernelParams& kp, unsigned long long* bar) {
+struct NoHook { SSDR_DEV void operator()() const {} };
+template <class C, class Hook = NoHook>
+SSDR_DEV void pass_last(const float2* d, int t, uint4* accs, bool first_frame, const WfKernelParams& kp, unsigned long long* bar, Hook after_loads = Hook(), int tr_frame = 1 << 30) {
     const float4* p = reinterpret_cast<const float4*>(d + 34 * t);       // 272-byte thread stride: 16-byte aligned, conflict-free
     float2 x[32];
 #pragma unroll
@@ -384,14 +446,26 @@ SSDR_DEV void pass_last(const float2* d, int t, uint4* accs, bool first_frame, c
         x[2 * m] = make_float2(v.x, v.y);
         x[2 * m + 1] = make_float2(v.z, v.w);
     }
-    if constexpr (C::SPLIT) {                 // this warp no longer needs the frame buffer
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
-    }
+    if constexpr (!std::is_same<Hook, NoHook>::value) {
+        // STAGED: the first butterfly level consumes every loaded value, so when the warp meets behind it all its reads of
+        // the region have COMPLETED (register dependences, no proxy fence needed) -> the hook bulk-copies the next frame's
+        // samples into the region
+        l1<32>(x);
+        after_loads();
+        TRACE(10);
+        dft_rest<32>(x);
+    } else {
+        if constexpr (C::SPLIT) {             // this warp no longer needs the frame buffer
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+        }
+        TRACE(10);
 #if !(SSDR_EXP & 4)
-    dft<32>(x);
+        dft<32>(x);
 #endif
-    last_epilogue<C::THREADS>(x, accs, first_frame, kp);
+    }
+    TRACE(11);
+    last_epilogue<C::THREADS>(x, accs, first_frame, kp, tr_frame);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -706,11 +780,12 @@ SSDR_DEV void sums_stage(unsigned* stage, int slot, int t, int vc, unsigned (&ac
 // ---------------------------------------------------------------------------------------------
 // the fused waterfall kernel
 // ---------------------------------------------------------------------------------------------
-template <int LG, int FMT, bool WINDOW>
+template <int LG, int FMT, bool WINDOW, bool STAGED = false>
 __global__ void __launch_bounds__(Cfg<LG>::THREADS, Cfg<LG>::MIN_CTAS)
-wf_fft_kernel(const WfKernelParams kp) {
+wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap) {
     using C = Cfg<LG>;
     constexpr int N = C::N, G = C::G, FPC = C::FPC;
+    static_assert(!STAGED || (C::CAN_STAGE && C::SPLIT && C::NB0 == 2 && C::TW_DIRECT), "staged input: one 16384-point frame per CTA");
     extern __shared__ __align__(16) unsigned char smem[];
     float2* data = reinterpret_cast<float2*>(smem + C::SM_DATA);
     float2* tw0 = reinterpret_cast<float2*>(smem + C::SM_TW0);
@@ -753,11 +828,18 @@ wf_fft_kernel(const WfKernelParams kp) {
     };
 
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + C::SM_MBAR);
+    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(smem + C::SM_TBAR) + (threadIdx.x >> 5);   // STAGED: this warp's
     unsigned frames_done = 0;                 // frames this group has finished (mbarrier phase counter)
     if constexpr (C::SPLIT) {
         if (threadIdx.x == 0) mbar_init(bar, G / 32);
+        if constexpr (STAGED) { if ((threadIdx.x & 31) == 0) mbar_init(tbar, 1); }
         __syncthreads();
     }
+    // first-pass column of butterfly i of this thread
+    auto col_of = [&](int i) -> int {
+        if constexpr (STAGED) return (t >> 5) * 64 + i * 32 + (t & 31);
+        else return t + i * G;
+    };
     unsigned tm_tw = 0u;                      // this thread's tensor-memory words (TW_DIRECT)
     unsigned* tm_slot = reinterpret_cast<unsigned*>(smem + C::SM_MBAR) + 2;
     if constexpr (C::TW_DIRECT) {
@@ -769,7 +851,7 @@ wf_fft_kernel(const WfKernelParams kp) {
         tm_tw = *tm_slot + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * C::TM_WORDS);
 #pragma unroll
         for (int i = 0; i < C::NB0; ++i) {
-            const int j = t + i * G;
+            const int j = col_of(i);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 unsigned v[16];
@@ -800,12 +882,113 @@ wf_fft_kernel(const WfKernelParams kp) {
 
     constexpr unsigned sample_bytes = (FMT == SSDR_IQ_CF32) ? 8u : 4u;
     const int ch_stride = (int)gridDim.x * FPC;
+#ifdef SSDR_TRACE
+    int tr_frame = 0;
+#endif
+    if constexpr (STAGED) {
+        // ---- TMA-staged frame loop (16384 points, local input) ---------------------------------------------------
+        // Per frame and warp: wait for the warp's tile (bulk-copied into its own region of the frame buffer while the
+        // previous frame's last pass and quantiser ran), pull the 2 x 16 samples of each lane into registers, tell the
+        // CTA the region is consumed (mbarrier `bar`, 16 arrivals), first butterfly, wait until EVERY region is consumed
+        // (only then may first-pass outputs overwrite them), stores, second butterfly, stores, CTA barrier, warp-local
+        // passes.  Right after the last-pass loads the region is free again and lanes 0..15 issue the 16 row copies
+        // (512 bytes each) of the next frame.
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        unsigned char* region = reinterpret_cast<unsigned char*>(d + (size_t)warp * (1024 + 64));
+        const unsigned char* iq8 = static_cast<const unsigned char*>(kp.iq);
+        // one tile [16 rows][64 samples] of frame `fr` (global frame number): rows 16 fr .. 16 fr + 15 of the input seen as
+        // [frames x 16][1024 samples], columns 64 w .. 64 w + 63; one UTMALDG by one lane
+        constexpr int inner_per_sample = (FMT == SSDR_IQ_CF32) ? 2 : 1;      // tensor-map elements are 32-bit words
+        auto stage_issue = [&](int fr) {
+            if (lane == 0) {
+                mbar_expect_tx(tbar, 16u * 64u * sample_bytes);
+                tma_tile_2d(region, &tmap, warp * 64 * inner_per_sample, fr * 16, tbar);
+            }
+        };
+        const int j0 = col_of(0), j1 = col_of(1);
+        for (int ch = blockIdx.x; ch < kp.batch; ch += ch_stride) {
+            size_t off = (size_t)ch * kp.n_avg * N;
+            int fr = ch * kp.n_avg;                     // global frame number
+            if (lane == 0) fence_proxy_async();         // the row stage wrote the buffer through the generic proxy
+            stage_issue(fr);                            // frame 0: the buffer is free (kernel start / barrier after the row stage)
+#pragma unroll 1
+            for (int f = 0; f < kp.n_avg; ++f) {
+                TRACE(0);
+                if (kp.prefetch && t == 0) {            // the frame after next (or the next channel's first frame) -> L2
+                    const bool last = (f + 1 == kp.n_avg);
+                    const size_t nxt = last ? (size_t)(ch + ch_stride) * kp.n_avg * N : off + N;
+                    if (!last || ch + ch_stride < kp.batch) prefetch_l2(iq8 + nxt * sample_bytes, (unsigned)N * sample_bytes);
+                }
+                float2 xa[C::R0], xb[C::R0];
+                mbar_wait(tbar, frames_done & 1u);
+#pragma unroll
+                for (int m = 0; m < C::R0; ++m) xa[m] = staged_sample<FMT>(region, m, 0, lane);
+#pragma unroll
+                for (int m = 0; m < C::R0; ++m) xb[m] = staged_sample<FMT>(region, m, 1, lane);
+                TRACE(1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar);        // this warp's region is consumed (release: the loads above are ordered before)
+                // both butterflies BEFORE the wait: a warp that finished the previous frame early does all its first-pass
+                // arithmetic while the late warps still run their last pass; after the wait only the stores are left
+                first_math<C, WINDOW>(xa, 0, tw0, win, t, make_float2(1.f, 0.f), tm_tw, j0);
+#if SSDR_EXP & 512        // timing model of the uneven first-pass split (3, 2, 2, 1 butterflies by stagger level); WRONG results
+                if (((threadIdx.x >> 7) & 3) != 3) first_math<C, WINDOW>(xb, 1, tw0, win, t, make_float2(1.f, 0.f), tm_tw, j1);
+                if (((threadIdx.x >> 7) & 3) == 0) first_math<C, WINDOW>(xa, 0, tw0, win, t, make_float2(1.f, 0.f), tm_tw, j0);
+#else
+                first_math<C, WINDOW>(xb, 1, tw0, win, t, make_float2(1.f, 0.f), tm_tw, j1);
+#endif
+                TRACE(2);
+                mbar_wait(bar, frames_done & 1u);       // ... and so is everybody's
+                TRACE(3);
+                first_store<C>(xa, 0, d, t, j0);
+                TRACE(4);
+                first_store<C>(xb, 1, d, t, j1);
+                TRACE(5);
+                __syncthreads();
+                TRACE(6);
+                {
+                    const int lvl = (threadIdx.x >> 7) & 3;
+                    const int stg = kp.stagger > 0 ? kp.stagger : C::STAGGER;
+                    if (lvl && stg > 1) { const long long c0 = clock64(); while (clock64() - c0 < lvl * stg) { } }
+                }
+                TRACE(7);
+                pass_mid<C, C::TM_MID>(d, tw1, t, tm_tw + 64u);
+                __syncwarp();
+                TRACE(8);
+                const bool more = (f + 1 < kp.n_avg);
+                ++fr;
+#ifdef SSDR_TRACE
+                pass_last<C>(d, t, accs, f == 0, kp, bar, [&]() { __syncwarp(); if (more) stage_issue(fr); }, tr_frame);
+#else
+                pass_last<C>(d, t, accs, f == 0, kp, bar, [&]() { __syncwarp(); if (more) stage_issue(fr); });
+#endif
+                TRACE(9);
+#ifdef SSDR_TRACE
+                TRACE_FLUSH();
+                ++tr_frame;
+                if (threadIdx.x == 0 && blockIdx.x == 0) g_wf_trace_frames = tr_frame;
+#endif
+                ++frames_done;
+                off += N;
+            }
+            unsigned acc[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 a = accs[c * C::THREADS];
+                acc[4 * c] = a.x; acc[4 * c + 1] = a.y; acc[4 * c + 2] = a.z; acc[4 * c + 3] = a.w;
+            }
+            if (kp.sums) sums_stage<C>(reinterpret_cast<unsigned*>(d), slot, t, ch, acc, kp, (t >> 5) + C::R0 * (t & 31));
+            else colour_stage<C, false>(reinterpret_cast<float*>(d), red, slot, t, ch, acc, kp, (t >> 5) + C::R0 * (t & 31), 32, 2 * C::PADN);
+            __syncthreads();                            // the row stage has been read before the next channel's tile lands
+        }
+    } else {
     for (int ch = blockIdx.x * FPC + slot; ch < kp.batch; ch += ch_stride) {
         float2 x0[C::R0];
         size_t off = (size_t)ch * kp.n_avg * N;
         first_load<C, FMT>(x0, 0, t, kp.iq, off);
 #pragma unroll 1
         for (int f = 0; f < kp.n_avg; ++f) {
+            TRACE(0);
             // the frame after next (or the first frame of this group's next channel) -> L2
             if (kp.prefetch && t == 0) {
                 const bool last = (f + 1 == kp.n_avg);
@@ -836,29 +1019,43 @@ wf_fft_kernel(const WfKernelParams kp) {
                 for (int i = 0; i < C::NB0; i += 2) {
                     first_load<C, FMT>(xb, i + 1, t, kp.iq, off);
                     first_math<C, WINDOW>(xa, i, tw0, win, t, w1_of(i), tm_tw);
+                    TRACE(1);
                     if (i == 0) buffer_free();
+                    TRACE(2);
                     first_store<C>(xa, i, d, t);
                     if (i + 2 < C::NB0) first_load<C, FMT>(xa, i + 2, t, kp.iq, off);
+                    TRACE(3);
                     first_math<C, WINDOW>(xb, i + 1, tw0, win, t, w1_of(i + 1), tm_tw);
+                    TRACE(4);
                     first_store<C>(xb, i + 1, d, t);
                 }
             }
+            TRACE(5);
 #if !(SSDR_EXP & 128)
             group_sync<C>(slot);
 #endif
+            TRACE(6);
             // from here each warp owns a contiguous 1024-point (NP == 3) / 32-point sub-transform: warp-local
             if constexpr (C::STAGGER > 0) {
                 const int lvl = (LG == 14) ? ((threadIdx.x >> 7) & 3) : (LG == 13) ? ((threadIdx.x >> 6) & 3) : ((threadIdx.x >> 5) & 3);     // four levels
                 const int stg = kp.stagger > 0 ? kp.stagger : C::STAGGER;
                 if (lvl) { const long long c0 = clock64(); while (clock64() - c0 < lvl * stg) { } }   // (__nanosleep is too coarse: 2.08 ms)
             }
+            TRACE(7);
 #if !(SSDR_EXP & 16)
             if constexpr (C::NP == 3) {
                 pass_mid<C, C::TM_MID>(d, tw1, t, tm_tw + 64u);
                 __syncwarp();
             }
 #endif
+            TRACE(8);
             pass_last<C>(d, t, accs, f == 0, kp, bar);
+            TRACE(9);
+#ifdef SSDR_TRACE
+            TRACE_FLUSH();
+            ++tr_frame;
+            if (threadIdx.x == 0 && blockIdx.x == 0) g_wf_trace_frames = tr_frame;
+#endif
             ++frames_done;
             off += N;
             if (f + 1 < kp.n_avg) first_load<C, FMT>(x0, 0, t, kp.iq, off);
@@ -878,6 +1075,7 @@ wf_fft_kernel(const WfKernelParams kp) {
                                (C::NP == 3) ? ((t >> 5) + C::R0 * (t & 31)) : t, (C::NP == 3) ? 32 : 1, 2 * C::PADN);
 #endif
         if constexpr (C::SPLIT) group_sync<C>(slot);     // the row stage has been read before the next channel's first store
+    }
     }
     if constexpr (C::TW_DIRECT) {
         tmem_fence_before();
@@ -1235,9 +1433,35 @@ __global__ void __launch_bounds__(1024) wf_colour_big_kernel(const WfKernelParam
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// Tensor map of the input seen as [frames x 16 rows][1024 samples] (32-bit words), box = 16 rows x 64 samples: the tile one
+// warp of the staged 16384-point kernel pulls per frame.  The driver's encoder is reached through the runtime
+// (cudaGetDriverEntryPoint), so the library does not link libcuda.
+static int make_stage_tmap(CUtensorMap* tm, const void* iq, int fmt, size_t frames) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (encode_fn)f;
+    }();
+    if (!encode) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SSDR_E_CUDA; }
+    const cuuint32_t words = (fmt == SSDR_IQ_CF32) ? 2u : 1u;             // 32-bit words per sample
+    const cuuint64_t gdim[2] = {1024ull * words, (cuuint64_t)frames * 16ull};
+    const cuuint64_t gstride[1] = {1024ull * words * 4ull};
+    const cuuint32_t box[2] = {64u * words, 16u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(iq), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SSDR_E_CUDA; }
+    return SSDR_OK;
+}
+
 template <int LG>
 static int launch_fft(const WfKernelParams& kp, int fmt, int window, cudaStream_t st) {
     using C = Cfg<LG>;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
     auto launch = [&](auto kern) -> int {
         SSDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SM_BYTES));
         int occ = 0;
@@ -1246,11 +1470,23 @@ static int launch_fft(const WfKernelParams& kp, int fmt, int window, cudaStream_
         const int n_groups = (kp.batch + C::FPC - 1) / C::FPC;
         int grid = sm_count() * occ;
         if (grid > n_groups) grid = n_groups;
-        kern<<<grid, C::THREADS, C::SM_BYTES, st>>>(kp);
+        kern<<<grid, C::THREADS, C::SM_BYTES, st>>>(kp, tmap);
         count_launch();
         SSDR_CUDA(cudaGetLastError());
         return SSDR_OK;
     };
+    if constexpr (C::CAN_STAGE) {
+        // local input: the TMA-staged kernel.  Peer (NVLink) input keeps the direct-load kernel -- bulk
+        // requests on peer addresses are pathologically slow (section 7).  SSDR_WF_STAGED=0 selects the direct-load kernel
+        // (the comparison arm of profiles/).
+        static const bool staged_on = [] { const char* e = getenv("SSDR_WF_STAGED"); return !(e && e[0] == '0'); }();
+        if (staged_on && kp.prefetch && ((uintptr_t)kp.iq & 15u) == 0) {
+            const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg);
+            if (rc) return rc;
+            if (fmt == SSDR_IQ_CF32) return window ? launch(wf_fft_kernel<LG, SSDR_IQ_CF32, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_CF32, false, true>);
+            return window ? launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, false, true>);
+        }
+    }
     if (fmt == SSDR_IQ_CF32) return window ? launch(wf_fft_kernel<LG, SSDR_IQ_CF32, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_CF32, false>);
     return window ? launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, false>);
 }
