@@ -55,6 +55,24 @@
                                   //    shared memory across the wait); 0: after it.  Measured: 1 is 13 % slower.
 #endif
 
+// Developer timeline (scripts/demod_trace.py): -DSSDR_TRACE records clock64() at the phase boundaries of every warp of CTA 0.
+#ifdef SSDR_TRACE
+#define DTRACE_FRAMES 96
+#define DTRACE_PTS 8
+__device__ long long g_demod_trace[DTRACE_FRAMES * 16 * DTRACE_PTS];
+extern "C" int ssdr_debug_demod_trace(long long* out) {
+    cudaMemcpyFromSymbol(out, g_demod_trace, sizeof(long long) * DTRACE_FRAMES * 16 * DTRACE_PTS);
+    return 0;
+}
+__device__ __forceinline__ long long* dtrace_slots() { __shared__ long long s[16 * DTRACE_PTS]; return s; }
+#define DTRACE(pt) do { if ((threadIdx.x & 31) == 0) dtrace_slots()[(threadIdx.x >> 5) * DTRACE_PTS + (pt)] = clock64(); } while (0)
+#define DTRACE_FLUSH() do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < DTRACE_FRAMES) { for (int k_ = 0; k_ < DTRACE_PTS; ++k_) \
+    g_demod_trace[(tr_n * 16 + (threadIdx.x >> 5)) * DTRACE_PTS + k_] = dtrace_slots()[(threadIdx.x >> 5) * DTRACE_PTS + k_]; } ++tr_n; } while (0)
+#else
+#define DTRACE(pt) do { } while (0)
+#define DTRACE_FLUSH() do { } while (0)
+#endif
+
 namespace ssdr {
 
 namespace {
@@ -183,6 +201,9 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tm = sh.tmem_base + (unsigned)tile * 128u;
     unsigned phase = 0;
+#ifdef SSDR_TRACE
+    int tr_n = 0;
+#endif
 
     const int nblk = kp.n_samples / FR;
     const unsigned wch = (unsigned)warp * CHB;              // this warp's channel slot in the array of 128-byte rows
@@ -330,6 +351,7 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
 #endif
         }
         for (int b = 0; tile_active && b < nblk; ++b) {
+            DTRACE(0);
             // This warp's rows of frame b are in place: publish them to the tensor core (async proxy), order this warp's
             // earlier TMEM reads before the MMAs, and count the warp in.  No warp waits for another one here: the LAST
             // of the tile's four warps to arrive issues the tile's MMAs.
@@ -372,7 +394,9 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 if (FMT == SSDR_IQ_CF32 || lane < 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
             }
 #endif
+            DTRACE(1);
             if (b > 0) back_end(b - 1);                     // overlaps the MMAs of frame b
+            DTRACE(2);
 #if SSDR_TC_EARLYMIX
             if (active && b + 1 < nblk) {                   // ... and so does the mixer of frame b + 1; its output waits in shared
                 mix_compute(b + 1, y);                      // memory (thread-private slots), not in registers
@@ -389,6 +413,7 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 "@!p bra WAIT_%=;\n\t}" ::"r"(barp), "r"(phase), "r"(2000u) : "memory");
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            DTRACE(3);
             if (active) {
                 // the frame's last four blocks become the history of the next frame (the MMAs of frame b have completed)
                 {
@@ -407,6 +432,7 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                         *reinterpret_cast<const uint4*>(sA16 + plane * A16_LBO + ((g0 + 1u) * GROWS + 8u + row) * 16u);
                 }
                 __syncwarp();
+                DTRACE(4);
                 if (b + 1 < nblk) {
 #if SSDR_TC_EARLYMIX
 #pragma unroll
@@ -414,9 +440,12 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
 #else
                     mix_compute(b + 1, y);
 #endif
+                    DTRACE(5);
                     mix_store(y);
                 }
             }
+            DTRACE(6);
+            DTRACE_FLUSH();
         }
         if (tile_active) back_end(nblk - 1);
         if (active) {

@@ -946,9 +946,9 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
                 TRACE(5);
                 __syncthreads();
                 TRACE(6);
-                {
+                {   // stagger of the warp-local passes (section 5.1); the staged kernel is flat between 200 and 400 cycles per level
                     const int lvl = (threadIdx.x >> 7) & 3;
-                    const int stg = kp.stagger > 0 ? kp.stagger : C::STAGGER;
+                    const int stg = kp.stagger > 0 ? kp.stagger : 300;
                     if (lvl && stg > 1) { const long long c0 = clock64(); while (clock64() - c0 < lvl * stg) { } }
                 }
                 TRACE(7);
