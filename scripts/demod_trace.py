@@ -26,3 +26,9 @@ d = np.diff(t[fs, :, :7], axis=2)
 print("frame period per warp (cycles):", np.diff(t[fs, :, 0], axis=0).mean())
 for k, nm in enumerate(names):
     print("%-32s %7.0f   per tile %s" % (nm, d[:, :, k].mean(), "  ".join("%6.0f" % d[:, 4 * i:4 * i + 4, k].mean() for i in range(4))))
+if os.environ.get("TRACE_RAW"):
+    for f in (20, 21, 22):
+        b0 = t[f, :, 0].min()
+        print("frame %d (rel. cycles): per warp T0 (rows ready), T1 (arrived / issued), T2 (back end done), T3 (MMAs done), T6 (rows of next frame stored)" % f)
+        for k in (0, 1, 2, 3, 6):
+            print("  T%d %s" % (k, " ".join("%6.0f" % (v - b0) for v in t[f, :, k])))

@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "demod_host.h"
@@ -49,6 +50,9 @@
 #endif
 #ifndef SSDR_TC_L2_AHEAD
 #define SSDR_TC_L2_AHEAD (SSDR_TC_L1_PREFETCH ? 2 : 1)      // frames ahead of the L2 prefetch
+#endif
+#ifndef SSDR_TC_STAGGER
+#define SSDR_TC_STAGGER 0         // developer knob: cycles between the starts of a CTA's tiles within a round (measured: no effect, the tiles are not in lock step)
 #endif
 #ifndef SSDR_TC_EARLYMIX
 #define SSDR_TC_EARLYMIX 0        // 1: mixer arithmetic of frame b + 1 before the wait for the MMAs of frame b (parked in
@@ -134,17 +138,21 @@ __device__ __forceinline__ constexpr unsigned idesc_tf32(int m, int n) {
 __device__ __forceinline__ constexpr unsigned idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
-__device__ __forceinline__ void mma_f16(unsigned tmem, uint64_t da, uint64_t db, unsigned idesc, unsigned accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+// MMAs for a warp-UNIFORM issue section (every lane holds the same operands, one elected lane issues): descriptors
+// as (lo, hi) words so that stepping through the operand is one 32-bit add on the low word (start-address field).
+__device__ __forceinline__ void mma_tf32_elect(unsigned tmem, unsigned da_lo, unsigned da_hi, unsigned db_lo, unsigned db_hi, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\telect.sync _|p, 0xffffffff;\n\tsetp.ne.b32 q, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, q;\n\t}"
+                 ::"r"(tmem), "r"(da_lo), "r"(da_hi), "r"(db_lo), "r"(db_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_f16_elect(unsigned tmem, unsigned da_lo, unsigned da_hi, unsigned db_lo, unsigned db_hi, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\telect.sync _|p, 0xffffffff;\n\tsetp.ne.b32 q, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t}"
+                 ::"r"(tmem), "r"(da_lo), "r"(da_hi), "r"(db_lo), "r"(db_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ unsigned pack_bf16(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const unsigned*>(&v);
-}
-__device__ __forceinline__ void mma_tf32(unsigned tmem, uint64_t da, uint64_t db, unsigned idesc, unsigned accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
     unsigned r[32];
@@ -170,7 +178,7 @@ struct alignas(8) TcShared {
 template <int FMT>
 __global__ void __launch_bounds__(TILES * WARPS * 32, 1)
 demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, const int* __restrict__ quad_fid, int n_rounds,
-                int* __restrict__ round_ctr) {
+                int* __restrict__ round_ctr, int tile_stagger) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ TcShared sh;
     const unsigned raw = (unsigned)__cvta_generic_to_shared(smem_raw);
@@ -350,6 +358,12 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             for (int i = 12; i < SPL; ++i) park[32 * i] = y[i];       // the slots always hold the newest frame's tail (history)
 #endif
         }
+        // Tile stagger (round 2, found with the phase timeline scripts/demod_trace.py): the four tiles of a CTA leave the round
+        // barrier together and stay in lock step, so their MMA batches reach the tensor pipe at the same time; the pipe
+        // time-slices them, every batch takes four times as long (issue -> commit 6.7 k cycles instead of 1.4 k) and each warp
+        // waits 2.7 k cycles per frame behind its back end.  Starting tile k of a round k x tile_stagger cycles late spreads
+        // the batches over the frame period: each tile then has the tensor pipe to itself.  Paid once per round.
+        if (tile && tile_stagger > 0) { const long long c0 = clock64(); while (clock64() - c0 < (long long)tile * tile_stagger) { } }
         for (int b = 0; tile_active && b < nblk; ++b) {
             DTRACE(0);
             // This warp's rows of frame b are in place: publish them to the tensor core (async proxy), order this warp's
@@ -359,32 +373,42 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #if SSDR_TC_LASTARRIVER
             __syncwarp();
-            if (lane == 0) {
-                unsigned old;
+            unsigned old = 0u;
+            if (lane == 0)
                 asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(&sh.arrived[tile])) : "memory");
-                if ((old & 3u) == 3u) {
+            // The issue section is warp-uniform (round 2): the whole warp of the last arriver enters it, every lane computes the
+            // same descriptor words with plain 32-bit adds and ONE elected lane issues each MMA.  The per-thread form (inside
+            // `if (lane == 0)`) cost ~21 instructions per MMA -- ptxas wraps every tcgen05.mma of a divergent region in an
+            // ELECT / 5 x R2UR.BROADCAST / branch loop -- 3.2 k cycles per frame on the critical path of the tile's slowest warp
+            // (phase timeline, scripts/demod_trace.py).
+            if (__shfl_sync(0xffffffffu, (int)((old & 3u) == 3u), 0)) {
+                {
 #else
             asm volatile("bar.sync %0, 128;" ::"r"(tile + 1) : "memory");        // the tile's four warps
             {
-                if (issuer) {
+                if (warp == 0) {
 #endif
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     constexpr unsigned i64 = idesc_tf32(128, 64), i16 = idesc_bf16(128, 32);
                     const unsigned td = tm + (unsigned)(b & 1) * 64u;
-#pragma unroll 1
+                    const uint64_t dA = desc_sw128(aAh, GRPB), dB = desc_sw128(aB, 1024u);
+                    const uint64_t dA16 = desc_none(aA16, A16_LBO, GROWS * 16u), dB16 = desc_none(aB16, B16_LBO, 128u);
+                    const unsigned a_lo = (unsigned)dA, a_hi = (unsigned)(dA >> 32), b_lo = (unsigned)dB, b_hi = (unsigned)(dB >> 32);
+                    const unsigned a16_lo = (unsigned)dA16, a16_hi = (unsigned)(dA16 >> 32), b16_lo = (unsigned)dB16, b16_hi = (unsigned)(dB16 >> 32);
+#pragma unroll
                     for (int c = 0; c < KCH; ++c) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {       // TF32 K step of 8 samples = 32 bytes inside the swizzled row
-                            const unsigned oa = (unsigned)c * ROWB + (unsigned)j * 32u, ob = aB + (unsigned)c * B_ATOM + (unsigned)j * 32u;
-                            mma_tf32(td, desc_sw128(aAh + oa, GRPB), desc_sw128(ob, 1024u), i64, (c | j) != 0);     // A_hi [B_hi | B_lo] -> columns 0..63
+                            const unsigned oa = (unsigned)c * ROWB + (unsigned)j * 32u, ob = (unsigned)c * B_ATOM + (unsigned)j * 32u;
+                            mma_tf32_elect(td, a_lo + (oa >> 4), a_hi, b_lo + (ob >> 4), b_hi, i64, (c | j) != 0);     // A_hi [B_hi | B_lo] -> columns 0..63
                         }
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {       // bfloat16 K step of 16 samples = two planes; rows shifted by c like the hi part
-                            mma_f16(td, desc_none(aA16 + (unsigned)(2 * j) * A16_LBO + (unsigned)c * 16u, A16_LBO, GROWS * 16u),
-                                    desc_none(aB16 + (unsigned)(4 * c + 2 * j) * B16_LBO, B16_LBO, 128u), i16, 1u);               // A_lo B_hi -> columns 0..31
+                            mma_f16_elect(td, a16_lo + (((unsigned)(2 * j) * A16_LBO + (unsigned)c * 16u) >> 4), a16_hi,
+                                          b16_lo + (((unsigned)(4 * c + 2 * j) * B16_LBO) >> 4), b16_hi, i16, 1u);               // A_lo B_hi -> columns 0..31
                         }
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(barp) : "memory");
+                    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(barp) : "memory");
                 }
             }
             __syncwarp();
@@ -485,7 +509,8 @@ int demod_tc_launch(const DemodLaunch& a, const int4* quad_ch, const int* quad_f
     if (grid > n_rounds) grid = n_rounds;
     if (grid < 1) return SSDR_OK;
     SSDR_CUDA(cudaMemsetAsync(round_ctr, 0, sizeof(int), st));
-    kern<<<grid, TILES * WARPS * 32, SMEM_BYTES, st>>>(kp, quad_ch, quad_fid, n_rounds, round_ctr);
+    static const int tile_stagger = [] { const char* e = getenv("SSDR_TC_STAGGER"); return e ? atoi(e) : SSDR_TC_STAGGER; }();   // developer knob
+    kern<<<grid, TILES * WARPS * 32, SMEM_BYTES, st>>>(kp, quad_ch, quad_fid, n_rounds, round_ctr, tile_stagger);
     count_launch();
     SSDR_CUDA(cudaGetLastError());
     return SSDR_OK;

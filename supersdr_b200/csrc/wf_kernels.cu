@@ -1100,19 +1100,37 @@ wf_colorrow_kernel(const WfKernelParams kp) {
         unsigned acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0u;
-        // thread t owns bins 32 t .. 32 t + 31: two 16-byte loads per line
-        for (int f = 0; f < kp.n_avg; ++f) {
-            const uint4* src = reinterpret_cast<const uint4*>(kp.lines + ((size_t)ch * kp.n_avg + f) * N + 32 * t);
+        // thread t owns bins 32 t .. 32 t + 31: two 16-byte loads per line, four lines (eight loads) in flight per thread
+        const uint4* src0 = reinterpret_cast<const uint4*>(kp.lines + (size_t)ch * kp.n_avg * N + 32 * t);
+        for (int f0 = 0; f0 < kp.n_avg; f0 += 4) {
+            uint4 v[4][2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint4 v = __ldg(src + h);
-                const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    acc[h * 8 + 2 * k] += __byte_perm(w[k], 0u, 0x4140);       // bytes 0, 1 -> two uint16 lanes
-                    acc[h * 8 + 2 * k + 1] += __byte_perm(w[k], 0u, 0x4342);   // bytes 2, 3
+            for (int j = 0; j < 4; ++j) {
+                if (f0 + j < kp.n_avg) {
+                    v[j][0] = __ldcs(src0 + (size_t)(f0 + j) * (N / 16));
+                    v[j][1] = __ldcs(src0 + (size_t)(f0 + j) * (N / 16) + 1);
+                } else {
+                    v[j][0] = v[j][1] = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned w[4] = {v[j][h].x, v[j][h].y, v[j][h].z, v[j][h].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        acc[h * 8 + 2 * k] += __byte_perm(w[k], 0u, 0x4140);       // bytes 0, 1 -> two uint16 lanes
+                        acc[h * 8 + 2 * k + 1] += __byte_perm(w[k], 0u, 0x4342);   // bytes 2, 3
+                    }
+                }
+            }
+        }
+        // the lines of this group's next channel -> L2 while the colour stage runs (one bulk request)
+        if (t == 0) {
+            const int nx = ch + (int)gridDim.x * FPC;
+            const size_t bytes = (size_t)kp.n_avg * N;
+            if (nx < kp.batch && bytes <= (1u << 20) && (bytes & 15u) == 0) prefetch_l2(kp.lines + (size_t)nx * bytes, (unsigned)bytes);
         }
         group_sync<C>(slot);          // the previous row's transposed reads are done
         colour_stage<C, true>(stage, red, slot, t, ch, acc, kp, 0, 0, C::PADN);
