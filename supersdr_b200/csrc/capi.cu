@@ -409,6 +409,7 @@ int ssdr_wf_process_dev(ssdr_wf_t h, const void* iq_dev, int iq_format, uint8_t*
     SSDR_ARG(h && iq_dev, "null argument");
     SSDR_BIND_H(h);
     SSDR_ARG(iq_format == SSDR_IQ_CF32 || iq_format == SSDR_IQ_S16BE, "bad iq_format %d", iq_format);
+    SSDR_ARG(((uintptr_t)iq_dev & 15u) == 0, "iq_dev must be 16-byte aligned (bulk prefetch / TMA tile copies)");
     int rcs = wf_ensure_scratch(h, h->batch);
     if (rcs) return rcs;
     WfLaunch a = wf_base(h);

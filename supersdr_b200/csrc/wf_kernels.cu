@@ -210,19 +210,22 @@ __device__ __noinline__ unsigned quantise_pair_exact(float P0, float P1, float v
 // parallelism across the MUFU latency) and ONE test covers all of them: some |v - rint(v)| within kQEps of a
 // rounding boundary, or some v + magic outside [magic, magic + 255] (estimate out of range, infinite or NaN:
 // no clamps on the fast path).  Only then the thresholds are consulted (exact, rare).
-SSDR_DEV uint4 quantise8(const float2* x, const WfKernelParams& kp) {
-    float P[8];
+// NP pairs of bins (NP = 4: eight bins, NP = 8: sixteen) -> NP words byte0 | byte1 << 16; one boundary / range test and one
+// branch for all of them.
+template <int NP>
+SSDR_DEV void quantise_pairs(const float2* x, unsigned (&r)[NP], const WfKernelParams& kp) {
+    float P[2 * NP];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 2 * NP; ++i) {
         const float t = x[i].y * x[i].y;
         P[i] = __fmaf_rn(x[i].x, x[i].x, t);
     }
-    float2 v[4], m[4];
+    float2 v[NP], m[NP];
     float worst = 0.0f;
     unsigned range = 0u;
     const float2 c1 = make_float2(kp.est_c1, kp.est_c1), c0 = make_float2(kp.est_c0, kp.est_c0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NP; ++i) {
         v[i] = __ffma2_rn(make_float2(lg2_ftz(P[2 * i]), lg2_ftz(P[2 * i + 1])), c1, c0);
         m[i] = __fadd2_rn(v[i], make_float2(kQMagic, kQMagic));
         const float2 nf = __fadd2_rn(m[i], make_float2(-kQMagic, -kQMagic));
@@ -230,23 +233,23 @@ SSDR_DEV uint4 quantise8(const float2* x, const WfKernelParams& kp) {
         worst = fmaxf(worst, fmaxf(fabsf(dd.x), fabsf(dd.y)));
         range |= (__float_as_uint(m[i].x) ^ kQMagicBits) | (__float_as_uint(m[i].y) ^ kQMagicBits);   // < 256 iff both in range
     }
-    uint4 r;                                              // low 16 bits of m = nearest integer
-    r.x = __byte_perm(__float_as_uint(m[0].x), __float_as_uint(m[0].y), 0x5410);
-    r.y = __byte_perm(__float_as_uint(m[1].x), __float_as_uint(m[1].y), 0x5410);
-    r.z = __byte_perm(__float_as_uint(m[2].x), __float_as_uint(m[2].y), 0x5410);
-    r.w = __byte_perm(__float_as_uint(m[3].x), __float_as_uint(m[3].y), 0x5410);
-    if (worst > 0.5f - kQEps || range >= 256u) {
-        unsigned* rw = &r.x;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NP; ++i) r[i] = __byte_perm(__float_as_uint(m[i].x), __float_as_uint(m[i].y), 0x5410);   // low 16 bits of m = nearest integer
+    if (worst > 0.5f - kQEps || range >= 256u) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
             const float2 nf = __fadd2_rn(m[i], make_float2(-kQMagic, -kQMagic));
             const float2 dd = __fadd2_rn(v[i], make_float2(-nf.x, -nf.y));
             const unsigned rg = (__float_as_uint(m[i].x) ^ kQMagicBits) | (__float_as_uint(m[i].y) ^ kQMagicBits);
             if (!(fmaxf(fabsf(dd.x), fabsf(dd.y)) <= 0.5f - kQEps) || rg >= 256u)
-                rw[i] = quantise_pair_exact(P[2 * i], P[2 * i + 1], v[i].x, v[i].y, kp.thr);
+                r[i] = quantise_pair_exact(P[2 * i], P[2 * i + 1], v[i].x, v[i].y, kp.thr);
         }
     }
-    return r;
+}
+SSDR_DEV uint4 quantise8(const float2* x, const WfKernelParams& kp) {
+    unsigned r[4];
+    quantise_pairs<4>(x, r, kp);
+    return make_uint4(r[0], r[1], r[2], r[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -412,26 +415,41 @@ SSDR_DEV void pass_mid(float2* d, const float2* tw1, int t, unsigned tm_mid = 0u
 // |X|^2 -> byte -> accumulate for the 32 outputs of a last-pass butterfly.  The byte sums over the n_avg
 // frames live in a thread-private uint4[4] column of shared memory (two uint16 lanes per word, no carry:
 // <= 25500), touched with 128-bit accesses only.  STRIDE = threads per CTA (column stride in uint4).
+#ifndef SSDR_QGROUP
+#define SSDR_QGROUP 8           // bins per quantiser group (one boundary test + branch each).  Measured (B200, config 2): 8: 1.582 ms, 16: 1.600, 32: 1.890
+#endif
 template <int STRIDE>
 SSDR_DEV void last_epilogue(float2 (&x)[32], uint4* accs, bool first_frame, const WfKernelParams& kp, int tr_frame = 1 << 30) {
+#if SSDR_EXP & 1
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        if (c == 1) TRACE(12);
-        if (c == 2) TRACE(13);
-        if (c == 3) TRACE(14);
         uint4 a = make_uint4(0u, 0u, 0u, 0u);
         if (!first_frame) a = accs[c * STRIDE];
-#if SSDR_EXP & 1
         a.x += (__float_as_uint(x[8 * c].x) ^ __float_as_uint(x[8 * c + 1].y)) & 0xffu;
         a.y += (__float_as_uint(x[8 * c + 2].x) ^ __float_as_uint(x[8 * c + 3].y)) & 0xffu;
         a.z += (__float_as_uint(x[8 * c + 4].x) ^ __float_as_uint(x[8 * c + 5].y)) & 0xffu;
         a.w += (__float_as_uint(x[8 * c + 6].x) ^ __float_as_uint(x[8 * c + 7].y)) & 0xffu;
-#else
-        const uint4 k8 = quantise8(x + 8 * c, kp);
-        a.x += k8.x; a.y += k8.y; a.z += k8.z; a.w += k8.w;
-#endif
         accs[c * STRIDE] = a;
     }
+#else
+    constexpr int NP = SSDR_QGROUP / 2, NG = 32 / SSDR_QGROUP, WPG = NP / 4;      // pairs per group, groups, uint4 words per group
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if (g == 1) TRACE(12);
+        if (g == 2) TRACE(13);
+        if (g == 3) TRACE(14);
+        uint4 a[WPG];
+#pragma unroll
+        for (int w = 0; w < WPG; ++w) a[w] = first_frame ? make_uint4(0u, 0u, 0u, 0u) : accs[(g * WPG + w) * STRIDE];
+        unsigned r[NP];
+        quantise_pairs<NP>(x + SSDR_QGROUP * g, r, kp);
+#pragma unroll
+        for (int w = 0; w < WPG; ++w) {
+            a[w].x += r[4 * w]; a[w].y += r[4 * w + 1]; a[w].z += r[4 * w + 2]; a[w].w += r[4 * w + 3];
+            accs[(g * WPG + w) * STRIDE] = a[w];
+        }
+    }
+#endif
 }
 
 // last radix-32 pass (sub-transform length 32, no twiddles) + power + byte + accumulate

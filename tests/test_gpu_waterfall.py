@@ -297,9 +297,9 @@ def test_large_frames_fused_kernel_equals_three_kernel_path(ssdr, tmp_path):
 @pytest.mark.parametrize("fmt", ["cf32", "s16be"])
 def test_staged_kernel_equals_direct_load_kernel(ssdr, fmt):
     """16384-point frames take the TMA-staged kernel (one tensor-map tile per warp and frame) when the
-    input is local and 16-byte aligned, the direct-load kernel otherwise (peer input, unaligned pointer).  Same arithmetic
-    routines, so every output must be bit-identical -- on more channels than CTAs, so that a CTA walks several channels
-    (tile of the next channel issued behind the row stage), and through an input pointer that is only 8-byte aligned."""
+    input is local, the direct-load kernel when it is flagged as peer (NVLink) input.  Same arithmetic routines, so every
+    output must be bit-identical -- on more channels than CTAs, so that a CTA walks several channels (the tile of the next
+    channel is issued behind the row stage).  An input pointer that is not 16-byte aligned is refused (header contract)."""
     import ctypes
     B, n, N = 300, 3, 16384
     code = ssdr.SSDR_IQ_CF32 if fmt == "cf32" else ssdr.SSDR_IQ_S16BE
@@ -307,27 +307,25 @@ def test_staged_kernel_equals_direct_load_kernel(ssdr, fmt):
     iq = ssdr.DeviceBuffer(B * n * N * sb + 64)
     ssdr._lib.check(ssdr.lib.ssdr_synth_iq_dev(iq.ptr, code, B, n, N, 4321))
     outs = []
-    for remote, shift in ((False, 0), (True, 0), (False, 8)):
-        src = iq.ptr
-        if shift:                                   # the same samples 8 bytes further on: not 16-byte aligned
-            host = np.zeros(B * n * N * sb + shift, np.uint8)
-            host[shift:] = iq.download(np.uint8, (B * n * N * sb,))
-            moved = ssdr.DeviceBuffer(host.nbytes).upload(host)
-            src = ctypes.c_void_p(moved.ptr.value + shift)
+    for remote in (False, True):
         bank = ssdr.WaterfallBank(N, B, n)
         bank.set_remote_input(remote)
         px, col, spec = ssdr.DeviceBuffer(B * N), ssdr.DeviceBuffer(B * N * 4), ssdr.DeviceBuffer(B * N * 4)
-        bank.process_dev(src, code, px.ptr, col.ptr, spec.ptr)
+        bank.process_dev(iq.ptr, code, px.ptr, col.ptr, spec.ptr)
         bank.sync()
         outs.append((px.download(np.uint8, (B, N)), col.download(np.float32, (B, N)), spec.download(np.float32, (B, N))))
+        if not remote:
+            with pytest.raises(ssdr.SsdrError):
+                bank.process_dev(ctypes.c_void_p(iq.ptr.value + 8), code, px.ptr)
         bank.close()
         for o in (px, col, spec):
             o.free()
-        if shift:
-            moved.free()
-    for other in outs[1:]:
-        for a, b in zip(outs[0], other):
-            assert np.array_equal(a, b)
-    x = iq.download(np.complex64 if fmt == "cf32" else np.uint8, (2, n, N) if fmt == "cf32" else (2, n, N, 4), offset_bytes=150 * n * N * sb)
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    if fmt == "cf32":
+        x = iq.download(np.complex64, (2, n, N), offset_bytes=150 * n * N * sb)
+    else:
+        raw = iq.download(np.uint8, (2 * n * N * 4,), offset_bytes=150 * n * N * sb).view(">i2").astype(np.float32)
+        x = (raw[0::2] + 1j * raw[1::2]).astype(np.complex64).reshape(2, n, N)
     assert np.array_equal(c_oracle.wf_rows(x)["pixels"], outs[0][0][150:152])
     iq.free()
