@@ -14,7 +14,7 @@ bank = S.WaterfallBank(N, B, n)
 for _ in range(2):
     ms = bank.time_dev(iq.ptr, S.SSDR_IQ_CF32, px.ptr, 1)
 print("ms", ms)
-F, W, P = 40, 16, 16
+F, W, P = 40, 16, 24
 buf = (C.c_longlong * (F * W * P))(); fr = C.c_int()
 S.lib.ssdr_debug_wf_trace(buf, C.byref(fr))
 full = np.frombuffer(buf, dtype=np.int64).reshape(F, W, P).astype(np.float64)
@@ -54,3 +54,16 @@ print("inside pass_last, by level:")
 for a, b, nm in zip(seq[:-1], seq[1:], lab):
     dd = q[:, :, b] - q[:, :, a]
     print("  %-20s %s" % (nm, "  ".join("%6.0f" % dd[:, l * 4:(l + 1) * 4].mean() for l in range(4))))
+
+# row stage (once per channel): its time stamps sit in slots 10..15 of the channel's NEXT frame record (f % 10 == 0)
+rows = [f for f in range(10, 38) if f % 10 == 0]
+if rows:
+    c = np.array([full[f, :, 16:22] for f in rows])            # [channels][warps][6]
+    prev9 = np.array([full[f - 1, :, 9] for f in rows])
+    nxt0 = np.array([full[f, :, 0] for f in rows])
+    lab = ["entry (accumulator reload)", "max", "histogram (32 shared atomics per thread)", "rank scan, min, lerp", "key -> colour table, row staged", "row stores (32 per thread)"]
+    print("row stage, cycles (mean over warps):")
+    print("  %-44s %7.0f" % ("last quantiser -> entry", (c[:, :, 0] - prev9).mean()))
+    for k in range(5):
+        print("  %-44s %7.0f" % (lab[k + 1], (c[:, :, k + 1] - c[:, :, k]).mean()))
+    print("  %-44s %7.0f" % ("end -> first wait of the next channel (T0)", (nxt0 - c[:, :, 5]).mean()))

@@ -41,7 +41,7 @@
 // for the first frames of a launch.  Not in the product build.
 #ifdef SSDR_TRACE
 #define TRACE_FRAMES 40
-#define TRACE_PTS 16
+#define TRACE_PTS 24
 __device__ long long g_wf_trace[TRACE_FRAMES * 16 * TRACE_PTS];
 __device__ int g_wf_trace_frames;
 extern "C" int ssdr_debug_wf_trace(long long* out, int* frames) {
@@ -547,6 +547,7 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
     const bool leader = (lane == 0);                    // used only when G > 32 (whole warps)
 
     const ssdr_wf_display_t dp = kp.disp[ch];
+    TRACE(16);
 
     // wf_db[0] = wf_db[1] (utils_supersdr.py:791).  Output index o of (t, q):
     //   FFT order:  o = kbase(t) + G (q ^ 16), kbase = (t >> 5) + R0 (t & 31)  (NP == 3)  or  t  (NP == 2)
@@ -591,6 +592,7 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
         kmax = red[3];
     }
     const int vmax = kmax;
+    TRACE(17);
 
     if (dp.auto_scale) {          // group-uniform
         const int want = kp.p_lo + 1;
@@ -614,6 +616,7 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
 #pragma unroll
                 for (int q = 0; q < 32; ++q) atomicAdd(&hist[key_at(q)], 1u);
                 group_sync<C>(slot);
+                TRACE(18);
                 const int cpt = ((nbins + G - 1) / G) | 1;      // odd chunk length: conflict-free chunk walks
                 const int b0 = t * cpt, b1 = min(b0 + cpt, nbins);
                 int sum = 0;
@@ -692,6 +695,7 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
         const float dd = high_clip - low_clip;
         dyn = dd > 40.0f ? dd : 40.0f;
     }
+    TRACE(19);
     const float low = low_clip + (float)dp.delta_low_db;
     const float nf = dyn + (float)dp.delta_high_db;
     const float den = nf - (float)dp.delta_low_db;
@@ -747,13 +751,37 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
         if (dden.ok) emit_row(std::true_type{}); else emit_row(std::false_type{});     // group-uniform
     }
     group_sync<C>(slot);
+    TRACE(20);
+    // four consecutive outputs per thread and step: one 16-byte read of the (swizzled) stage, one 4-byte pixel store /
+    // 16-byte colour store (a warp writes 128 / 512 contiguous bytes) instead of thirty-two 1-byte stores per thread
+    auto stage4 = [&](int o4) -> float4 {
+        if constexpr (LINEAR || C::SWZ == 0 || C::SWZ == 1) {          // padded layout / swizzle that varies inside the group
+            return make_float4(stage[sidx(o4)], stage[sidx(o4 + 1)], stage[sidx(o4 + 2)], stage[sidx(o4 + 3)]);
+        } else if constexpr (C::SWZ >= 2) {
+            const int sw = (o4 >> C::SWZ) & 31;                         // constant over the aligned group of four
+            float4 v = *reinterpret_cast<const float4*>(stage + (o4 ^ (sw & ~3)));
+            if (sw & 1) { float u = v.x; v.x = v.y; v.y = u; u = v.z; v.z = v.w; v.w = u; }
+            if (sw & 2) { float u = v.x; v.x = v.z; v.z = u; u = v.y; v.y = v.w; v.w = u; }
+            return v;
+        } else {
+            return *reinterpret_cast<const float4*>(stage + o4);
+        }
+    };
 #pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
-        const int o = t + i * G;
-        const float c = stage[sidx(o)];
-        if (kp.colour) kp.colour[row + o] = c;
-        if (kp.pixels) kp.pixels[row + o] = (uint8_t)__float2int_rn(c);
+    for (int i = 0; i < 8; ++i) {
+        const int o4 = 4 * (t + i * G);
+        const float4 c = stage4(o4);
+        if (kp.colour) *reinterpret_cast<float4*>(kp.colour + row + o4) = c;
+        if (kp.pixels) {
+            // rint(c), 0 <= c <= 255, as the low byte of c + 1.5 * 2^23 (round to nearest even, exactly cvt.rni): the
+            // conversion unit runs at a quarter of the fp32 rate and 16384 conversions per row were a tenth of the row stage
+            const unsigned b0 = __float_as_uint(__fadd_rn(c.x, kQMagic)), b1 = __float_as_uint(__fadd_rn(c.y, kQMagic));
+            const unsigned b2 = __float_as_uint(__fadd_rn(c.z, kQMagic)), b3 = __float_as_uint(__fadd_rn(c.w, kQMagic));
+            const unsigned px = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+            *reinterpret_cast<unsigned*>(kp.pixels + row + o4) = px;
+        }
     }
+    TRACE(21);
     if (kp.spectrum) {                                                    // kiwi_waterfall.spectrum (optional output)
         group_sync<C>(slot);
 #pragma unroll
@@ -763,9 +791,9 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
         }
         group_sync<C>(slot);
 #pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-            const int o = t + i * G;
-            kp.spectrum[row + o] = stage[sidx(o)];
+        for (int i = 0; i < 8; ++i) {
+            const int o4 = 4 * (t + i * G);
+            *reinterpret_cast<float4*>(kp.spectrum + row + o4) = stage4(o4);
         }
     }
     // the caller's next barrier (before the frame buffer is written again) orders these reads
