@@ -133,7 +133,7 @@ struct Cfg {
     // STAGED (LG 14, local input): the raw samples of a frame are bulk-copied by the TMA engine into the frame buffer
     // itself -- each warp's own 1024-point region, free from the moment the warp has loaded its last-pass inputs -- one
     // frame ahead; no global load in the frame loop.  Column mapping: warp w owns first-pass columns 64 w .. 64 w + 63.
-    static constexpr bool CAN_STAGE = (LG == 14);
+    static constexpr bool CAN_STAGE = (LG == 14 || LG == 13);      // one frame per CTA, 8 KB tile per warp = its region
 };
 
 struct WfKernelParams {
@@ -355,12 +355,12 @@ SSDR_DEV void tma_tile_2d(void* dst_smem, const CUtensorMap* tmap, int x, int y,
 }
 
 // sample m (row) of first-pass butterfly i of this lane from the warp's staged tile [16 rows][64 samples]
-template <int FMT>
+template <int FMT, int ROW>      // ROW = samples per tile row (32 per first-pass butterfly of a lane)
 SSDR_DEV float2 staged_sample(const unsigned char* region, int m, int i, int lane) {
     if constexpr (FMT == SSDR_IQ_CF32) {
-        return reinterpret_cast<const float2*>(region)[m * 64 + i * 32 + lane];
+        return reinterpret_cast<const float2*>(region)[m * ROW + i * 32 + lane];
     } else {
-        const unsigned v = reinterpret_cast<const unsigned*>(region)[m * 64 + i * 32 + lane];
+        const unsigned v = reinterpret_cast<const unsigned*>(region)[m * ROW + i * 32 + lane];
         const unsigned sw = __byte_perm(v, 0u, 0x2301);
         const int re = (int)(short)(sw & 0xffffu), im = (int)sw >> 16;
         return make_float2((float)re, (float)im);
@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(Cfg<LG>::THREADS, Cfg<LG>::MIN_CTAS)
 wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap) {
     using C = Cfg<LG>;
     constexpr int N = C::N, G = C::G, FPC = C::FPC;
-    static_assert(!STAGED || (C::CAN_STAGE && C::SPLIT && C::NB0 == 2 && C::TW_DIRECT), "staged input: one 16384-point frame per CTA");
+    static_assert(!STAGED || (C::CAN_STAGE && C::SPLIT && C::NB0 * C::R0 == 32 && C::M0 == 1024), "staged input: one 8192 / 16384-point frame per CTA");
     extern __shared__ __align__(16) unsigned char smem[];
     float2* data = reinterpret_cast<float2*>(smem + C::SM_DATA);
     float2* tw0 = reinterpret_cast<float2*>(smem + C::SM_TW0);
@@ -858,10 +858,10 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
     float2 w1r[C::W1_MODE == 2 ? C::NB0 : 1];
     if constexpr (C::W1_MODE == 1) {
 #pragma unroll
-        for (int i = 0; i < C::NB0; ++i) w1s[threadIdx.x + i * C::THREADS] = __ldg(kp.wtab + t + i * G);
+        for (int i = 0; i < C::NB0; ++i) w1s[threadIdx.x + i * C::THREADS] = __ldg(kp.wtab + (STAGED ? (t >> 5) * (32 * C::NB0) + i * 32 + (t & 31) : t + i * G));
     } else if constexpr (C::W1_MODE == 2) {
 #pragma unroll
-        for (int i = 0; i < C::NB0; ++i) w1r[i] = __ldg(kp.wtab + t + i * G);
+        for (int i = 0; i < C::NB0; ++i) w1r[i] = __ldg(kp.wtab + (STAGED ? (t >> 5) * (32 * C::NB0) + i * 32 + (t & 31) : t + i * G));
     } else if constexpr (C::W1_MODE == 3) {
         for (int e = threadIdx.x; e < C::M0; e += blockDim.x) w1s[e] = kp.wtab[e];
         __syncthreads();
@@ -883,7 +883,7 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
     }
     // first-pass column of butterfly i of this thread
     auto col_of = [&](int i) -> int {
-        if constexpr (STAGED) return (t >> 5) * 64 + i * 32 + (t & 31);
+        if constexpr (STAGED) return (t >> 5) * (32 * C::NB0) + i * 32 + (t & 31);      // warp w owns columns 32 NB0 w ..
         else return t + i * G;
     };
     unsigned tm_tw = 0u;                      // this thread's tensor-memory words (TW_DIRECT)
@@ -940,18 +940,21 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
         // passes.  Right after the last-pass loads the region is free again and lanes 0..15 issue the 16 row copies
         // (512 bytes each) of the next frame.
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        unsigned char* region = reinterpret_cast<unsigned char*>(d + (size_t)warp * (1024 + 64));
+        unsigned char* region = reinterpret_cast<unsigned char*>(d + (size_t)warp * (1024 + 64));      // 8704 bytes >= the 8 KB tile
         const unsigned char* iq8 = static_cast<const unsigned char*>(kp.iq);
-        // one tile [16 rows][64 samples] of frame `fr` (global frame number): rows 16 fr .. 16 fr + 15 of the input seen as
-        // [frames x 16][1024 samples], columns 64 w .. 64 w + 63; one UTMALDG by one lane
+        // one tile [R0 rows][32 NB0 samples] (8 KB) of frame `fr` (global frame number): rows R0 fr .. of the input seen as
+        // [frames x R0][1024 samples], columns 32 NB0 w ..; one UTMALDG by one lane
         constexpr int inner_per_sample = (FMT == SSDR_IQ_CF32) ? 2 : 1;      // tensor-map elements are 32-bit words
+        constexpr int ROW = 32 * C::NB0;                                     // samples per tile row
         auto stage_issue = [&](int fr) {
             if (lane == 0) {
-                mbar_expect_tx(tbar, 16u * 64u * sample_bytes);
-                tma_tile_2d(region, &tmap, warp * 64 * inner_per_sample, fr * 16, tbar);
+                mbar_expect_tx(tbar, (unsigned)(C::R0 * ROW) * sample_bytes);
+                tma_tile_2d(region, &tmap, warp * ROW * inner_per_sample, fr * C::R0, tbar);
             }
         };
-        const int j0 = col_of(0), j1 = col_of(1);
+        int jc[C::NB0];
+#pragma unroll
+        for (int i = 0; i < C::NB0; ++i) jc[i] = col_of(i);
         for (int ch = blockIdx.x; ch < kp.batch; ch += ch_stride) {
             size_t off = (size_t)ch * kp.n_avg * N;
             int fr = ch * kp.n_avg;                     // global frame number
@@ -965,35 +968,29 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
                     const size_t nxt = last ? (size_t)(ch + ch_stride) * kp.n_avg * N : off + N;
                     if (!last || ch + ch_stride < kp.batch) prefetch_l2(iq8 + nxt * sample_bytes, (unsigned)N * sample_bytes);
                 }
-                float2 xa[C::R0], xb[C::R0];
+                float2 x[C::NB0][C::R0];
                 mbar_wait(tbar, frames_done & 1u);
 #pragma unroll
-                for (int m = 0; m < C::R0; ++m) xa[m] = staged_sample<FMT>(region, m, 0, lane);
+                for (int i = 0; i < C::NB0; ++i)
 #pragma unroll
-                for (int m = 0; m < C::R0; ++m) xb[m] = staged_sample<FMT>(region, m, 1, lane);
+                    for (int m = 0; m < C::R0; ++m) x[i][m] = staged_sample<FMT, ROW>(region, m, i, lane);
                 TRACE(1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar);        // this warp's region is consumed (release: the loads above are ordered before)
-                // both butterflies BEFORE the wait: a warp that finished the previous frame early does all its first-pass
+                // all first-pass butterflies BEFORE the wait: a warp that finished the previous frame early does its first-pass
                 // arithmetic while the late warps still run their last pass; after the wait only the stores are left
-                first_math<C, WINDOW>(xa, 0, tw0, win, t, make_float2(1.f, 0.f), tm_tw, j0);
-#if SSDR_EXP & 512        // timing model of the uneven first-pass split (3, 2, 2, 1 butterflies by stagger level); WRONG results
-                if (((threadIdx.x >> 7) & 3) != 3) first_math<C, WINDOW>(xb, 1, tw0, win, t, make_float2(1.f, 0.f), tm_tw, j1);
-                if (((threadIdx.x >> 7) & 3) == 0) first_math<C, WINDOW>(xa, 0, tw0, win, t, make_float2(1.f, 0.f), tm_tw, j0);
-#else
-                first_math<C, WINDOW>(xb, 1, tw0, win, t, make_float2(1.f, 0.f), tm_tw, j1);
-#endif
+#pragma unroll
+                for (int i = 0; i < C::NB0; ++i) first_math<C, WINDOW>(x[i], i, tw0, win, t, w1_of(i), tm_tw, jc[i]);
                 TRACE(2);
                 mbar_wait(bar, frames_done & 1u);       // ... and so is everybody's
                 TRACE(3);
-                first_store<C>(xa, 0, d, t, j0);
-                TRACE(4);
-                first_store<C>(xb, 1, d, t, j1);
+#pragma unroll
+                for (int i = 0; i < C::NB0; ++i) first_store<C>(x[i], i, d, t, jc[i]);
                 TRACE(5);
                 __syncthreads();
                 TRACE(6);
                 {   // stagger of the warp-local passes (section 5.1); the staged kernel is flat between 200 and 400 cycles per level
-                    const int lvl = (threadIdx.x >> 7) & 3;
+                    const int lvl = (threadIdx.x >> (LG == 14 ? 7 : 6)) & 3;
                     const int stg = kp.stagger > 0 ? kp.stagger : 300;
                     if (lvl && stg > 1) { const long long c0 = clock64(); while (clock64() - c0 < lvl * stg) { } }
                 }
@@ -1500,7 +1497,7 @@ __global__ void __launch_bounds__(1024) wf_colour_big_kernel(const WfKernelParam
 // Tensor map of the input seen as [frames x 16 rows][1024 samples] (32-bit words), box = 16 rows x 64 samples: the tile one
 // warp of the staged 16384-point kernel pulls per frame.  The driver's encoder is reached through the runtime
 // (cudaGetDriverEntryPoint), so the library does not link libcuda.
-static int make_stage_tmap(CUtensorMap* tm, const void* iq, int fmt, size_t frames) {
+static int make_stage_tmap(CUtensorMap* tm, const void* iq, int fmt, size_t frames, int rows_per_frame, int cols_per_warp) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static encode_fn encode = [] {
@@ -1511,9 +1508,9 @@ static int make_stage_tmap(CUtensorMap* tm, const void* iq, int fmt, size_t fram
     }();
     if (!encode) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SSDR_E_CUDA; }
     const cuuint32_t words = (fmt == SSDR_IQ_CF32) ? 2u : 1u;             // 32-bit words per sample
-    const cuuint64_t gdim[2] = {1024ull * words, (cuuint64_t)frames * 16ull};
+    const cuuint64_t gdim[2] = {1024ull * words, (cuuint64_t)frames * (cuuint64_t)rows_per_frame};
     const cuuint64_t gstride[1] = {1024ull * words * 4ull};
-    const cuuint32_t box[2] = {64u * words, 16u};
+    const cuuint32_t box[2] = {(cuuint32_t)cols_per_warp * words, (cuuint32_t)rows_per_frame};      // 16 x 64 (N = 16384) or 8 x 128 (N = 8192) samples: 8 KB as complex64
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(iq), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1545,7 +1542,7 @@ static int launch_fft(const WfKernelParams& kp, int fmt, int window, cudaStream_
         // (the comparison arm of profiles/).
         static const bool staged_on = [] { const char* e = getenv("SSDR_WF_STAGED"); return !(e && e[0] == '0'); }();
         if (staged_on && kp.prefetch && ((uintptr_t)kp.iq & 15u) == 0) {
-            const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg);
+            const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg, C::R0, 32 * C::NB0);
             if (rc) return rc;
             if (fmt == SSDR_IQ_CF32) return window ? launch(wf_fft_kernel<LG, SSDR_IQ_CF32, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_CF32, false, true>);
             return window ? launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, false, true>);
