@@ -932,13 +932,13 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
     int tr_frame = 0;
 #endif
     if constexpr (STAGED) {
-        // ---- TMA-staged frame loop (16384 points, local input) ---------------------------------------------------
-        // Per frame and warp: wait for the warp's tile (bulk-copied into its own region of the frame buffer while the
-        // previous frame's last pass and quantiser ran), pull the 2 x 16 samples of each lane into registers, tell the
-        // CTA the region is consumed (mbarrier `bar`, 16 arrivals), first butterfly, wait until EVERY region is consumed
-        // (only then may first-pass outputs overwrite them), stores, second butterfly, stores, CTA barrier, warp-local
-        // passes.  Right after the last-pass loads the region is free again and lanes 0..15 issue the 16 row copies
-        // (512 bytes each) of the next frame.
+        // ---- TMA-staged frame loop (8192 / 16384 points, local input) ---------------------------------
+        // Per frame and warp: wait for the warp's tile (copied by the TMA engine into the warp's own 1024-point region of the
+        // frame buffer while the previous frame's last pass and quantiser ran), pull the NB0 x R0 samples of each lane into
+        // registers, tell the CTA the region is consumed (mbarrier `bar`, one arrival per warp), all first-pass butterflies,
+        // wait until EVERY region is consumed (only then may first-pass outputs overwrite them), stores, CTA barrier,
+        // warp-local passes.  Behind the first butterfly level of the last pass the region is free again and one lane issues
+        // the tile copy of the next frame (one UTMALDG).
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         unsigned char* region = reinterpret_cast<unsigned char*>(d + (size_t)warp * (1024 + 64));      // 8704 bytes >= the 8 KB tile
         const unsigned char* iq8 = static_cast<const unsigned char*>(kp.iq);
