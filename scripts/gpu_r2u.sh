@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 final evidence (one gpurun call): full GPU suite, smoke, bench both arms, launch list, ncu of the three hot kernels, memcheck.
-TAG=${1:-r2u}
+TAG=${1:-r2z}
 bash scripts/gpu_full.sh $TAG > gpurun_out/full_$TAG.log 2>&1
 timeout 900 compute-sanitizer --tool memcheck python scripts/gpu_sanitize.py > gpurun_out/sanitize_memcheck_$TAG.log 2>&1
 echo "== memcheck rc=$?"; grep -E "ERROR SUMMARY|Error" gpurun_out/sanitize_memcheck_$TAG.log | head -5
