@@ -133,7 +133,7 @@ struct Cfg {
     // STAGED (LG 14, local input): the raw samples of a frame are bulk-copied by the TMA engine into the frame buffer
     // itself -- each warp's own 1024-point region, free from the moment the warp has loaded its last-pass inputs -- one
     // frame ahead; no global load in the frame loop.  Column mapping: warp w owns first-pass columns 64 w .. 64 w + 63.
-    static constexpr bool CAN_STAGE = (LG == 14 || LG == 13);      // one frame per CTA, 8 KB tile per warp = its region
+    static constexpr bool CAN_STAGE = (LG == 14 || LG == 13 || LG == 10);      // 8 KB tile per warp = its region (LG 10: the whole frame, one warp per channel)
 };
 
 struct WfKernelParams {
@@ -831,7 +831,8 @@ __global__ void __launch_bounds__(Cfg<LG>::THREADS, Cfg<LG>::MIN_CTAS)
 wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap) {
     using C = Cfg<LG>;
     constexpr int N = C::N, G = C::G, FPC = C::FPC;
-    static_assert(!STAGED || (C::CAN_STAGE && C::SPLIT && C::NB0 * C::R0 == 32 && C::M0 == 1024), "staged input: one 8192 / 16384-point frame per CTA");
+    static_assert(!STAGED || (C::CAN_STAGE && ((C::SPLIT && C::NB0 * C::R0 == 32 && C::M0 == 1024) || (C::G == 32 && C::NP == 2))),
+                  "staged input: one 8192 / 16384-point frame per CTA, or one 1024-point frame per warp");
     extern __shared__ __align__(16) unsigned char smem[];
     float2* data = reinterpret_cast<float2*>(smem + C::SM_DATA);
     float2* tw0 = reinterpret_cast<float2*>(smem + C::SM_TW0);
@@ -876,8 +877,8 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + C::SM_MBAR);
     unsigned long long* tbar = reinterpret_cast<unsigned long long*>(smem + C::SM_TBAR) + (threadIdx.x >> 5);   // STAGED: this warp's
     unsigned frames_done = 0;                 // frames this group has finished (mbarrier phase counter)
-    if constexpr (C::SPLIT) {
-        if (threadIdx.x == 0) mbar_init(bar, G / 32);
+    if constexpr (C::SPLIT || STAGED) {
+        if constexpr (C::SPLIT) { if (threadIdx.x == 0) mbar_init(bar, G / 32); }
         if constexpr (STAGED) { if ((threadIdx.x & 31) == 0) mbar_init(tbar, 1); }
         __syncthreads();
     }
@@ -931,6 +932,56 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
 #ifdef SSDR_TRACE
     int tr_frame = 0;
 #endif
+    if constexpr (STAGED && C::G == 32) {
+        // ---- TMA-staged frame loop, one warp per channel (1024 points = the reference's waterfall size, utils_supersdr.py:596):
+        // the warp's whole frame is ONE tile [32 rows][32 samples] that lands in the warp's own frame buffer while the previous
+        // frame's last pass runs; no barrier beyond the warp's own.
+        const int lane = t;
+        unsigned char* region = reinterpret_cast<unsigned char*>(d);
+        const unsigned char* iq8 = static_cast<const unsigned char*>(kp.iq);
+        auto stage_issue = [&](int fr) {
+            if (lane == 0) {
+                mbar_expect_tx(tbar, (unsigned)(C::R0 * 32) * sample_bytes);
+                tma_tile_2d(region, &tmap, 0, fr * C::R0, tbar);
+            }
+        };
+        for (int ch = blockIdx.x * FPC + slot; ch < kp.batch; ch += ch_stride) {
+            size_t off = (size_t)ch * kp.n_avg * N;
+            int fr = ch * kp.n_avg;
+            if (lane == 0) fence_proxy_async();         // the row stage wrote the buffer through the generic proxy
+            stage_issue(fr);
+#pragma unroll 1
+            for (int f = 0; f < kp.n_avg; ++f) {
+                if (kp.prefetch && t == 0) {
+                    const bool last = (f + 1 == kp.n_avg);
+                    const size_t nxt = last ? (size_t)(ch + ch_stride) * kp.n_avg * N : off + N;
+                    if (!last || ch + ch_stride < kp.batch) prefetch_l2(iq8 + nxt * sample_bytes, (unsigned)N * sample_bytes);
+                }
+                float2 x[C::R0];
+                mbar_wait(tbar, frames_done & 1u);
+#pragma unroll
+                for (int m = 0; m < C::R0; ++m) x[m] = staged_sample<FMT, 32>(region, m, 0, lane);
+                __syncwarp();                           // every lane has its samples: the outputs may overwrite the tile
+                first_math<C, WINDOW>(x, 0, tw0, win, t, make_float2(1.f, 0.f), 0u, t);
+                first_store<C>(x, 0, d, t, t);
+                __syncwarp();
+                const bool more = (f + 1 < kp.n_avg);
+                ++fr;
+                pass_last<C>(d, t, accs, f == 0, kp, bar, [&]() { __syncwarp(); if (more) stage_issue(fr); });
+                ++frames_done;
+                off += N;
+            }
+            unsigned acc[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 a = accs[c * C::THREADS];
+                acc[4 * c] = a.x; acc[4 * c + 1] = a.y; acc[4 * c + 2] = a.z; acc[4 * c + 3] = a.w;
+            }
+            if (kp.sums) sums_stage<C>(reinterpret_cast<unsigned*>(d), slot, t, ch, acc, kp, t);
+            else colour_stage<C, false>(reinterpret_cast<float*>(d), red, slot, t, ch, acc, kp, t, 1, 2 * C::PADN);
+            __syncwarp();                               // the row stage has been read before the next channel's tile lands
+        }
+    } else
     if constexpr (STAGED) {
         // ---- TMA-staged frame loop (8192 / 16384 points, local input) ---------------------------------
         // Per frame and warp: wait for the warp's tile (copied by the TMA engine into the warp's own 1024-point region of the
@@ -1497,7 +1548,7 @@ __global__ void __launch_bounds__(1024) wf_colour_big_kernel(const WfKernelParam
 // Tensor map of the input seen as [frames x 16 rows][1024 samples] (32-bit words), box = 16 rows x 64 samples: the tile one
 // warp of the staged 16384-point kernel pulls per frame.  The driver's encoder is reached through the runtime
 // (cudaGetDriverEntryPoint), so the library does not link libcuda.
-static int make_stage_tmap(CUtensorMap* tm, const void* iq, int fmt, size_t frames, int rows_per_frame, int cols_per_warp) {
+static int make_stage_tmap(CUtensorMap* tm, const void* iq, int fmt, size_t frames, int rows_per_frame, int cols_per_warp, int row_len) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static encode_fn encode = [] {
@@ -1508,8 +1559,8 @@ static int make_stage_tmap(CUtensorMap* tm, const void* iq, int fmt, size_t fram
     }();
     if (!encode) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SSDR_E_CUDA; }
     const cuuint32_t words = (fmt == SSDR_IQ_CF32) ? 2u : 1u;             // 32-bit words per sample
-    const cuuint64_t gdim[2] = {1024ull * words, (cuuint64_t)frames * (cuuint64_t)rows_per_frame};
-    const cuuint64_t gstride[1] = {1024ull * words * 4ull};
+    const cuuint64_t gdim[2] = {(cuuint64_t)row_len * words, (cuuint64_t)frames * (cuuint64_t)rows_per_frame};      // row_len = M0 samples
+    const cuuint64_t gstride[1] = {(cuuint64_t)row_len * words * 4ull};
     const cuuint32_t box[2] = {(cuuint32_t)cols_per_warp * words, (cuuint32_t)rows_per_frame};      // 16 x 64 (N = 16384) or 8 x 128 (N = 8192) samples: 8 KB as complex64
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(iq), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1542,7 +1593,7 @@ static int launch_fft(const WfKernelParams& kp, int fmt, int window, cudaStream_
         // (the comparison arm of profiles/).
         static const bool staged_on = [] { const char* e = getenv("SSDR_WF_STAGED"); return !(e && e[0] == '0'); }();
         if (staged_on && kp.prefetch && ((uintptr_t)kp.iq & 15u) == 0) {
-            const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg, C::R0, 32 * C::NB0);
+            const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg, C::R0, (C::G == 32) ? 32 : 32 * C::NB0, C::M0);
             if (rc) return rc;
             if (fmt == SSDR_IQ_CF32) return window ? launch(wf_fft_kernel<LG, SSDR_IQ_CF32, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_CF32, false, true>);
             return window ? launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, false, true>);
