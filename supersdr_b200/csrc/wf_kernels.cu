@@ -129,11 +129,14 @@ struct Cfg {
     static constexpr size_t SM_RED = SM_WIN + (size_t)(N / 2) * sizeof(float);
     static constexpr size_t SM_MBAR = SM_RED + (size_t)FPC * 8 * sizeof(int);
     static constexpr size_t SM_TBAR = SM_MBAR + 16;        // mbarrier + the tensor-memory base address slot
-    static constexpr size_t SM_BYTES = SM_TBAR + 16 * 8;   // STAGED: one transaction barrier per warp
+    static constexpr size_t SM_BYTES = SM_TBAR + 32 * 8;   // STAGED: one transaction barrier per warp (N >= 8192) / per frame group (N <= 1024)
     // STAGED (LG 14, local input): the raw samples of a frame are bulk-copied by the TMA engine into the frame buffer
     // itself -- each warp's own 1024-point region, free from the moment the warp has loaded its last-pass inputs -- one
     // frame ahead; no global load in the frame loop.  Column mapping: warp w owns first-pass columns 64 w .. 64 w + 63.
-    static constexpr bool CAN_STAGE = (LG == 14 || LG == 13 || LG == 10);      // 8 KB tile per warp = its region (LG 10: the whole frame, one warp per channel)
+    // staged input: 8 KB tile per warp = its region (LG 13, 14) / the whole frame of a frame group (LG 9, 10).  Measured (B200, 65536
+    // channels x 10 frames, fraction of the HBM bandwidth, staged / direct): 1024: 0.677 / 0.528, 512: 0.658 / 0.609, 256: 0.580 / 0.601
+    // (four groups per warp: the tensor copy is a uniform-datapath instruction, ptxas serialises the four issuing lanes) -> 256 stays direct
+    static constexpr bool CAN_STAGE = (LG == 14 || LG == 13 || LG == 10 || LG == 9);
 };
 
 struct WfKernelParams {
@@ -831,7 +834,7 @@ __global__ void __launch_bounds__(Cfg<LG>::THREADS, Cfg<LG>::MIN_CTAS)
 wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap) {
     using C = Cfg<LG>;
     constexpr int N = C::N, G = C::G, FPC = C::FPC;
-    static_assert(!STAGED || (C::CAN_STAGE && ((C::SPLIT && C::NB0 * C::R0 == 32 && C::M0 == 1024) || (C::G == 32 && C::NP == 2))),
+    static_assert(!STAGED || (C::CAN_STAGE && ((C::SPLIT && C::NB0 * C::R0 == 32 && C::M0 == 1024) || (C::G <= 32 && C::NP == 2))),
                   "staged input: one 8192 / 16384-point frame per CTA, or one 1024-point frame per warp");
     extern __shared__ __align__(16) unsigned char smem[];
     float2* data = reinterpret_cast<float2*>(smem + C::SM_DATA);
@@ -875,11 +878,11 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
     };
 
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + C::SM_MBAR);
-    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(smem + C::SM_TBAR) + (threadIdx.x >> 5);   // STAGED: this warp's
+    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(smem + C::SM_TBAR) + (C::G <= 32 ? threadIdx.x / G : threadIdx.x >> 5);   // STAGED: this warp's / group's
     unsigned frames_done = 0;                 // frames this group has finished (mbarrier phase counter)
     if constexpr (C::SPLIT || STAGED) {
         if constexpr (C::SPLIT) { if (threadIdx.x == 0) mbar_init(bar, G / 32); }
-        if constexpr (STAGED) { if ((threadIdx.x & 31) == 0) mbar_init(tbar, 1); }
+        if constexpr (STAGED) { if ((C::G <= 32 ? t : (threadIdx.x & 31)) == 0) mbar_init(tbar, 1); }
         __syncthreads();
     }
     // first-pass column of butterfly i of this thread
@@ -932,15 +935,14 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
 #ifdef SSDR_TRACE
     int tr_frame = 0;
 #endif
-    if constexpr (STAGED && C::G == 32) {
-        // ---- TMA-staged frame loop, one warp per channel (1024 points = the reference's waterfall size, utils_supersdr.py:596):
-        // the warp's whole frame is ONE tile [32 rows][32 samples] that lands in the warp's own frame buffer while the previous
-        // frame's last pass runs; no barrier beyond the warp's own.
-        const int lane = t;
+    if constexpr (STAGED && C::G <= 32) {
+        // ---- TMA-staged frame loop, one frame group (a warp or part of one) per channel: 256 .. 1024 points; 1024 is the
+        // reference's waterfall size (utils_supersdr.py:596).  The group's whole frame is ONE tile [R0 rows][32 samples] that lands
+        // in the group's own frame buffer while the previous frame's last pass runs; no barrier beyond the group's own.
         unsigned char* region = reinterpret_cast<unsigned char*>(d);
         const unsigned char* iq8 = static_cast<const unsigned char*>(kp.iq);
         auto stage_issue = [&](int fr) {
-            if (lane == 0) {
+            if (t == 0) {
                 mbar_expect_tx(tbar, (unsigned)(C::R0 * 32) * sample_bytes);
                 tma_tile_2d(region, &tmap, 0, fr * C::R0, tbar);
             }
@@ -948,7 +950,7 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
         for (int ch = blockIdx.x * FPC + slot; ch < kp.batch; ch += ch_stride) {
             size_t off = (size_t)ch * kp.n_avg * N;
             int fr = ch * kp.n_avg;
-            if (lane == 0) fence_proxy_async();         // the row stage wrote the buffer through the generic proxy
+            if (t == 0) fence_proxy_async();            // the row stage wrote the buffer through the generic proxy
             stage_issue(fr);
 #pragma unroll 1
             for (int f = 0; f < kp.n_avg; ++f) {
@@ -957,17 +959,22 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
                     const size_t nxt = last ? (size_t)(ch + ch_stride) * kp.n_avg * N : off + N;
                     if (!last || ch + ch_stride < kp.batch) prefetch_l2(iq8 + nxt * sample_bytes, (unsigned)N * sample_bytes);
                 }
-                float2 x[C::R0];
+                float2 x[C::NB0][C::R0];
                 mbar_wait(tbar, frames_done & 1u);
 #pragma unroll
-                for (int m = 0; m < C::R0; ++m) x[m] = staged_sample<FMT, 32>(region, m, 0, lane);
-                __syncwarp();                           // every lane has its samples: the outputs may overwrite the tile
-                first_math<C, WINDOW>(x, 0, tw0, win, t, make_float2(1.f, 0.f), 0u, t);
-                first_store<C>(x, 0, d, t, t);
-                __syncwarp();
+                for (int i = 0; i < C::NB0; ++i)
+#pragma unroll
+                    for (int m = 0; m < C::R0; ++m) x[i][m] = staged_sample<FMT, 32>(region, m, 0, t + i * G);
+                group_sync<C>(slot);                    // every thread of the group has its samples: the outputs may overwrite the tile
+#pragma unroll
+                for (int i = 0; i < C::NB0; ++i) {
+                    first_math<C, WINDOW>(x[i], i, tw0, win, t, make_float2(1.f, 0.f));
+                    first_store<C>(x[i], i, d, t);
+                }
+                group_sync<C>(slot);
                 const bool more = (f + 1 < kp.n_avg);
                 ++fr;
-                pass_last<C>(d, t, accs, f == 0, kp, bar, [&]() { __syncwarp(); if (more) stage_issue(fr); });
+                pass_last<C>(d, t, accs, f == 0, kp, bar, [&]() { group_sync<C>(slot); if (more) stage_issue(fr); });
                 ++frames_done;
                 off += N;
             }
@@ -979,7 +986,7 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
             }
             if (kp.sums) sums_stage<C>(reinterpret_cast<unsigned*>(d), slot, t, ch, acc, kp, t);
             else colour_stage<C, false>(reinterpret_cast<float*>(d), red, slot, t, ch, acc, kp, t, 1, 2 * C::PADN);
-            __syncwarp();                               // the row stage has been read before the next channel's tile lands
+            group_sync<C>(slot);                        // the row stage has been read before the next channel's tile lands
         }
     } else
     if constexpr (STAGED) {
@@ -1593,7 +1600,7 @@ static int launch_fft(const WfKernelParams& kp, int fmt, int window, cudaStream_
         // (the comparison arm of profiles/).
         static const bool staged_on = [] { const char* e = getenv("SSDR_WF_STAGED"); return !(e && e[0] == '0'); }();
         if (staged_on && kp.prefetch && ((uintptr_t)kp.iq & 15u) == 0) {
-            const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg, C::R0, (C::G == 32) ? 32 : 32 * C::NB0, C::M0);
+            const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg, C::R0, (C::G <= 32) ? 32 : 32 * C::NB0, C::M0);
             if (rc) return rc;
             if (fmt == SSDR_IQ_CF32) return window ? launch(wf_fft_kernel<LG, SSDR_IQ_CF32, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_CF32, false, true>);
             return window ? launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, false, true>);
