@@ -129,14 +129,17 @@ struct Cfg {
     static constexpr size_t SM_RED = SM_WIN + (size_t)(N / 2) * sizeof(float);
     static constexpr size_t SM_MBAR = SM_RED + (size_t)FPC * 8 * sizeof(int);
     static constexpr size_t SM_TBAR = SM_MBAR + 16;        // mbarrier + the tensor-memory base address slot
-    static constexpr size_t SM_BYTES = SM_TBAR + 32 * 8;   // STAGED: one transaction barrier per warp (N >= 8192) / per frame group (N <= 1024)
+    static constexpr size_t SM_GBAR = SM_TBAR + 32 * 8;    // STAGED: one transaction barrier per warp (N >= 2048) / per frame group (N <= 1024)
+    static constexpr size_t SM_BYTES = SM_GBAR + 8 * 8;    // STAGED, several multi-warp frame groups per CTA (N = 2048, 4096): one "consumed" barrier per group
     // STAGED (LG 14, local input): the raw samples of a frame are bulk-copied by the TMA engine into the frame buffer
     // itself -- each warp's own 1024-point region, free from the moment the warp has loaded its last-pass inputs -- one
     // frame ahead; no global load in the frame loop.  Column mapping: warp w owns first-pass columns 64 w .. 64 w + 63.
     // staged input: 8 KB tile per warp = its region (LG 13, 14) / the whole frame of a frame group (LG 9, 10).  Measured (B200, 65536
     // channels x 10 frames, fraction of the HBM bandwidth, staged / direct): 1024: 0.677 / 0.528, 512: 0.658 / 0.609, 256: 0.580 / 0.601
     // (four groups per warp: the tensor copy is a uniform-datapath instruction, ptxas serialises the four issuing lanes) -> 256 stays direct
-    static constexpr bool CAN_STAGE = (LG == 14 || LG == 13 || LG == 10 || LG == 9);
+    static constexpr bool CAN_STAGE = (LG >= 9);
+    // tile rows wider than 256 tensor-map elements (N = 2048, 4096: 512 / 256 samples per row) are fetched as R0 plain bulk copies
+    static constexpr bool STAGE_BULK = (LG == 11 || LG == 12);
 };
 
 struct WfKernelParams {
@@ -834,8 +837,8 @@ __global__ void __launch_bounds__(Cfg<LG>::THREADS, Cfg<LG>::MIN_CTAS)
 wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap) {
     using C = Cfg<LG>;
     constexpr int N = C::N, G = C::G, FPC = C::FPC;
-    static_assert(!STAGED || (C::CAN_STAGE && ((C::SPLIT && C::NB0 * C::R0 == 32 && C::M0 == 1024) || (C::G <= 32 && C::NP == 2))),
-                  "staged input: one 8192 / 16384-point frame per CTA, or one 1024-point frame per warp");
+    static_assert(!STAGED || (C::CAN_STAGE && ((C::G > 32 && C::NB0 * C::R0 == 32 && C::M0 == 1024) || (C::G <= 32 && C::NP == 2))),
+                  "staged input: 1024-point regions per warp (N >= 2048), or the whole frame per frame group (N <= 1024)");
     extern __shared__ __align__(16) unsigned char smem[];
     float2* data = reinterpret_cast<float2*>(smem + C::SM_DATA);
     float2* tw0 = reinterpret_cast<float2*>(smem + C::SM_TW0);
@@ -870,26 +873,28 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
         for (int e = threadIdx.x; e < C::M0; e += blockDim.x) w1s[e] = kp.wtab[e];
         __syncthreads();
     }
+    // first-pass column of butterfly i of this thread
+    auto col_of = [&](int i) -> int {
+        if constexpr (STAGED) return (t >> 5) * (32 * C::NB0) + i * 32 + (t & 31);      // warp w owns columns 32 NB0 w ..
+        else return t + i * G;
+    };
     auto w1_of = [&](int i) -> float2 {
         if constexpr (C::W1_MODE == 1) return w1s[threadIdx.x + i * C::THREADS];
         else if constexpr (C::W1_MODE == 2) return w1r[i];
-        else if constexpr (C::W1_MODE == 3) return w1s[t + i * G];
+        else if constexpr (C::W1_MODE == 3) return w1s[col_of(i)];
         else return make_float2(1.f, 0.f);
     };
 
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + C::SM_MBAR);
     unsigned long long* tbar = reinterpret_cast<unsigned long long*>(smem + C::SM_TBAR) + (C::G <= 32 ? threadIdx.x / G : threadIdx.x >> 5);   // STAGED: this warp's / group's
     unsigned frames_done = 0;                 // frames this group has finished (mbarrier phase counter)
+    if constexpr (STAGED && C::G > 32) bar = reinterpret_cast<unsigned long long*>(smem + C::SM_GBAR) + slot;      // this frame group's
     if constexpr (C::SPLIT || STAGED) {
-        if constexpr (C::SPLIT) { if (threadIdx.x == 0) mbar_init(bar, G / 32); }
+        if constexpr (STAGED && C::G > 32) { if (t == 0) mbar_init(bar, G / 32); }
+        else if constexpr (C::SPLIT) { if (threadIdx.x == 0) mbar_init(bar, G / 32); }
         if constexpr (STAGED) { if ((C::G <= 32 ? t : (threadIdx.x & 31)) == 0) mbar_init(tbar, 1); }
         __syncthreads();
     }
-    // first-pass column of butterfly i of this thread
-    auto col_of = [&](int i) -> int {
-        if constexpr (STAGED) return (t >> 5) * (32 * C::NB0) + i * 32 + (t & 31);      // warp w owns columns 32 NB0 w ..
-        else return t + i * G;
-    };
     unsigned tm_tw = 0u;                      // this thread's tensor-memory words (TW_DIRECT)
     unsigned* tm_slot = reinterpret_cast<unsigned*>(smem + C::SM_MBAR) + 2;
     if constexpr (C::TW_DIRECT) {
@@ -997,23 +1002,31 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
         // wait until EVERY region is consumed (only then may first-pass outputs overwrite them), stores, CTA barrier,
         // warp-local passes.  Behind the first butterfly level of the last pass the region is free again and one lane issues
         // the tile copy of the next frame (one UTMALDG).
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int warp = t >> 5, lane = t & 31;         // warp within the frame group = its 1024-point region
         unsigned char* region = reinterpret_cast<unsigned char*>(d + (size_t)warp * (1024 + 64));      // 8704 bytes >= the 8 KB tile
         const unsigned char* iq8 = static_cast<const unsigned char*>(kp.iq);
         // one tile [R0 rows][32 NB0 samples] (8 KB) of frame `fr` (global frame number): rows R0 fr .. of the input seen as
-        // [frames x R0][1024 samples], columns 32 NB0 w ..; one UTMALDG by one lane
+        // [frames x R0][1024 samples], columns 32 NB0 w ..; one UTMALDG by one lane -- or, where a row is wider than a tensor-map
+        // box may be (N = 2048, 4096), R0 plain bulk copies of one row each by the same lane
         constexpr int inner_per_sample = (FMT == SSDR_IQ_CF32) ? 2 : 1;      // tensor-map elements are 32-bit words
         constexpr int ROW = 32 * C::NB0;                                     // samples per tile row
         auto stage_issue = [&](int fr) {
             if (lane == 0) {
                 mbar_expect_tx(tbar, (unsigned)(C::R0 * ROW) * sample_bytes);
-                tma_tile_2d(region, &tmap, warp * ROW * inner_per_sample, fr * C::R0, tbar);
+                if constexpr (C::STAGE_BULK) {
+#pragma unroll
+                    for (int m = 0; m < C::R0; ++m)
+                        bulk_g2s(region + (size_t)m * ROW * sample_bytes, iq8 + ((size_t)fr * N + (size_t)m * 1024 + (size_t)warp * ROW) * sample_bytes,
+                                 (unsigned)ROW * sample_bytes, tbar);
+                } else {
+                    tma_tile_2d(region, &tmap, warp * ROW * inner_per_sample, fr * C::R0, tbar);
+                }
             }
         };
         int jc[C::NB0];
 #pragma unroll
         for (int i = 0; i < C::NB0; ++i) jc[i] = col_of(i);
-        for (int ch = blockIdx.x; ch < kp.batch; ch += ch_stride) {
+        for (int ch = blockIdx.x * FPC + slot; ch < kp.batch; ch += ch_stride) {
             size_t off = (size_t)ch * kp.n_avg * N;
             int fr = ch * kp.n_avg;                     // global frame number
             if (lane == 0) fence_proxy_async();         // the row stage wrote the buffer through the generic proxy
@@ -1045,11 +1058,11 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
                 for (int i = 0; i < C::NB0; ++i) first_store<C>(x[i], i, d, t, jc[i]);
                 TRACE(5);
-                __syncthreads();
+                group_sync<C>(slot);
                 TRACE(6);
                 {   // stagger of the warp-local passes (section 5.1); the staged kernel is flat between 200 and 400 cycles per level
-                    const int lvl = (threadIdx.x >> (LG == 14 ? 7 : 6)) & 3;
-                    const int stg = kp.stagger > 0 ? kp.stagger : 300;
+                    const int lvl = (LG >= 13) ? ((threadIdx.x >> (LG == 14 ? 7 : 6)) & 3) : ((threadIdx.x >> 5) & 3);
+                    const int stg = kp.stagger > 0 ? kp.stagger : (LG >= 13 ? 300 : C::STAGGER);
                     if (lvl && stg > 1) { const long long c0 = clock64(); while (clock64() - c0 < lvl * stg) { } }
                 }
                 TRACE(7);
@@ -1080,7 +1093,7 @@ wf_fft_kernel(const WfKernelParams kp, const __grid_constant__ CUtensorMap tmap)
             }
             if (kp.sums) sums_stage<C>(reinterpret_cast<unsigned*>(d), slot, t, ch, acc, kp, (t >> 5) + C::R0 * (t & 31));
             else colour_stage<C, false>(reinterpret_cast<float*>(d), red, slot, t, ch, acc, kp, (t >> 5) + C::R0 * (t & 31), 32, 2 * C::PADN);
-            __syncthreads();                            // the row stage has been read before the next channel's tile lands
+            group_sync<C>(slot);                        // the row stage has been read before the next channel's tile lands
         }
     } else {
     for (int ch = blockIdx.x * FPC + slot; ch < kp.batch; ch += ch_stride) {
@@ -1600,8 +1613,10 @@ static int launch_fft(const WfKernelParams& kp, int fmt, int window, cudaStream_
         // (the comparison arm of profiles/).
         static const bool staged_on = [] { const char* e = getenv("SSDR_WF_STAGED"); return !(e && e[0] == '0'); }();
         if (staged_on && kp.prefetch && ((uintptr_t)kp.iq & 15u) == 0) {
-            const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg, C::R0, (C::G <= 32) ? 32 : 32 * C::NB0, C::M0);
-            if (rc) return rc;
+            if constexpr (!C::STAGE_BULK) {
+                const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg, C::R0, (C::G <= 32) ? 32 : 32 * C::NB0, C::M0);
+                if (rc) return rc;
+            }
             if (fmt == SSDR_IQ_CF32) return window ? launch(wf_fft_kernel<LG, SSDR_IQ_CF32, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_CF32, false, true>);
             return window ? launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, false, true>);
         }

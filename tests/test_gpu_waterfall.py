@@ -294,10 +294,10 @@ def test_large_frames_fused_kernel_equals_three_kernel_path(ssdr, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N", [16384, 8192, 1024, 512])
+@pytest.mark.parametrize("N", [16384, 8192, 4096, 2048, 1024, 512])
 @pytest.mark.parametrize("fmt", ["cf32", "s16be"])
 def test_staged_kernel_equals_direct_load_kernel(ssdr, fmt, N):
-    """512-, 1024-, 8192- and 16384-point frames take the TMA-staged kernel (one tensor-map tile per warp and frame) when the
+    """512- to 16384-point frames take the TMA-staged kernel (one tensor-map tile per warp and frame) when the
     input is local, the direct-load kernel when it is flagged as peer (NVLink) input.  Same arithmetic routines, so every
     output must be bit-identical -- on more channels than CTAs, so that a CTA walks several channels (the tile of the next
     channel is issued behind the row stage).  An input pointer that is not 16-byte aligned is refused (header contract)."""
