@@ -604,7 +604,9 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
         const int want = kp.p_lo + 1;
         int v_lo, cnt_lo, mn = 0x7fffffff;
         const int nbins = 255 * kp.n_avg + 1;
-        if (G >= 256 && nbins + 32 <= stage_words) {
+        // (groups of at least 256 threads always; smaller whole-warp groups when the key range is small against the group, i.e. at
+        // n_avg <= 2 for a 1024-bin warp -- the reference's default averaging_n = 1 -- where eight bisection rounds cost 5 x the histogram)
+        if (G >= 32 && (G >= 256 || nbins <= 16 * G) && nbins + 32 <= stage_words) {
             // ---- rank p_lo (0-based) from a histogram of the keys in the (idle) frame buffer: 32 shared-memory
             // atomics per thread, one scan.  The first barrier above already ordered every warp's last FFT pass.
             unsigned* hist = reinterpret_cast<unsigned*>(stage);
@@ -741,7 +743,9 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
     // its value up instead of repeating the two divisions.
     const int nkeys = 255 * kp.n_avg + 1;
     constexpr int row_words = LINEAR ? N + N / 32 : N;          // extent of the row stage (padded when LINEAR)
-    const bool use_lut = (G >= 256) && (4 * nkeys <= N) && (row_words + nkeys <= stage_words);
+    // (worth it when filling the table costs at most half of the per-bin evaluations: nkeys / G <= 16 -- large groups at any
+    // n_avg <= ~25, and a 1024-bin warp-sized group at n_avg <= 2, the reference's default averaging_n = 1, utils_supersdr.py:615)
+    const bool use_lut = (2 * nkeys <= 32 * G) && (4 * nkeys <= N) && (row_words + nkeys <= stage_words);
     if (use_lut) {
         float* lut = stage + row_words;
         auto fill = [&](auto fast) { for (int k = t; k < nkeys; k += G) lut[k] = colour_of((float)k, fast); };
