@@ -604,9 +604,12 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
         const int want = kp.p_lo + 1;
         int v_lo, cnt_lo, mn = 0x7fffffff;
         const int nbins = 255 * kp.n_avg + 1;
-        // (groups of at least 256 threads always; smaller whole-warp groups when the key range is small against the group, i.e. at
-        // n_avg <= 2 for a 1024-bin warp -- the reference's default averaging_n = 1 -- where eight bisection rounds cost 5 x the histogram)
-        if (G >= 32 && (G >= 256 || nbins <= 16 * G) && nbins + 32 <= stage_words) {
+        // Histogram or bisection?  Groups of at least 64 threads: histogram whenever it fits.  A warp-sized group (1024 bins): in
+        // the FFT kernel up to 16 bins per thread (n_avg <= 2; beyond that the bisection, pure ALU work, overlaps the other warps'
+        // transforms better than shared-memory atomics: 0.540 / 0.636 of HBM at n_avg = 4 / 8 against 0.524 / 0.609), in the
+        // line-entry kernel, where the row stage is all there is, whenever it fits (n_avg = 4: 1.42 -> 2.08 Glines/s; 4096 bins
+        // x 10 lines: 0.43 -> 0.65 of HBM).  n_avg = 1, the reference's default (utils_supersdr.py:615): 407 -> 532 Mlines/s.
+        if (G >= 32 && (G >= 64 || LINEAR || nbins <= 16 * G) && nbins + 32 <= stage_words) {
             // ---- rank p_lo (0-based) from a histogram of the keys in the (idle) frame buffer: 32 shared-memory
             // atomics per thread, one scan.  The first barrier above already ordered every warp's last FFT pass.
             unsigned* hist = reinterpret_cast<unsigned*>(stage);
