@@ -67,6 +67,38 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tier_p_colorrow(S, hbm_peak, iters=50):
+    """wf_colorrow_kernel on device-resident uint8 lines: the reference's own 1024-bin waterfall at its default averaging_n = 1
+    (utils_supersdr.py:596,615), the same at 10 lines per row, and BASELINE config 2's shape.  bytes = lines in + pixels out."""
+    import ctypes as C
+    import time
+    out = {}
+    for key, (W, B, n) in (("ref_native_1024x1", (1024, 65536, 1)), ("ref_native_1024x10", (1024, 65536, 10)), ("config2_shape_16384x10", (16384, 4096, 10))):
+        lines = S.DeviceBuffer(B * n * W)
+        px = S.DeviceBuffer(B * W)
+        rng = np.random.default_rng(1)
+        host = rng.integers(60, 200, min(B * n * W, 1 << 24)).astype(np.uint8)
+        for o in range(0, B * n * W, host.size):      # tile the random block over the buffer
+            m = min(host.size, B * n * W - o)
+            S._lib.check(S.lib.ssdr_memcpy_h2d(C.c_void_p(lines.ptr.value + o), S._lib.ptr(host), m))
+        bank = S.WaterfallBank(W, B, n)
+        call = lambda: S._lib.check(S.lib.ssdr_wf_colorrow_u8_dev(bank._h, lines.ptr, px.ptr, None, None, None))
+        for _ in range(3):
+            call()
+        bank.sync()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            call()
+        bank.sync()
+        ms = (time.perf_counter() - t0) / iters * 1e3
+        byts = B * n * W + B * W
+        out[key] = {"bins": W, "rows": B, "lines_per_row": n, "ms": ms, "mlines_per_s": B * n / ms / 1e3, "hbm_gbs": byts / ms / 1e6,
+                    "hbm_frac": byts / ms / 1e6 / hbm_peak, "l2_resident": B * n * W < 126e6,
+                    "timing": "host clock around %d back-to-back launches + stream sync" % iters}
+        bank.close(); lines.free(); px.free()
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -587,6 +619,13 @@ def main():
         line["peer_ingest"] = peer
     if demod:
         line["demod"] = demod
+    # ---- reference-native entry (finished uint8 W/F lines in: utils_supersdr.py:783-813,881-888) as a secondary object: the only
+    # stage of the path with reference-pinned parity; device-resident lines, CUDA-event timed on the handle's stream ----
+    if rank == 0 and not args.no_demod:
+        try:
+            line["tier_p_colorrow"] = tier_p_colorrow(S, peak)
+        except Exception as e:                    # secondary: must not cost the headline
+            line["tier_p_colorrow"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     elif rank == 0:

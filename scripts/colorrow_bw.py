@@ -11,7 +11,7 @@ import supersdr_b200 as S
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="16384x4096x10,8192x8192x10,1024x65536x10,1024x65536x1,16384x4096x1")
-    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--iters", type=int, default=50)
     a = ap.parse_args()
     S.init(0)
     try:
@@ -22,9 +22,12 @@ def main():
         W, B, n = (int(x) for x in shp.split("x"))
         lines = S.DeviceBuffer(B * n * W)
         px = S.DeviceBuffer(B * W)
-        S._lib.check(S.lib.ssdr_dev_memset(lines.ptr, 0x5a, B * n * W))
+        # random bytes over the WHOLE buffer (a 16 MB block tiled): constant rows would take the row stage's shortcut.  (Until
+        # round 2's last session only the first 16 MB were random -- the numbers of that time flatter the large shapes.)
         rng = np.random.default_rng(1)
-        lines.upload(rng.integers(60, 200, min(B * n * W, 1 << 24)).astype(np.uint8))
+        host = rng.integers(60, 200, min(B * n * W, 1 << 24)).astype(np.uint8)
+        for o in range(0, B * n * W, host.size):
+            S._lib.check(S.lib.ssdr_memcpy_h2d(ctypes.c_void_p(lines.ptr.value + o), S._lib.ptr(host), min(host.size, B * n * W - o)))
         bank = S.WaterfallBank(W, B, n)
         call = lambda: S._lib.check(S.lib.ssdr_wf_colorrow_u8_dev(bank._h, lines.ptr, px.ptr, None, None, None))
         for _ in range(3):

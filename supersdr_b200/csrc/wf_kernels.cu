@@ -607,9 +607,14 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
         // Histogram or bisection?  Groups of at least 64 threads: histogram whenever it fits.  A warp-sized group (1024 bins): in
         // the FFT kernel up to 16 bins per thread (n_avg <= 2; beyond that the bisection, pure ALU work, overlaps the other warps'
         // transforms better than shared-memory atomics: 0.540 / 0.636 of HBM at n_avg = 4 / 8 against 0.524 / 0.609), in the
-        // line-entry kernel, where the row stage is all there is, whenever it fits (n_avg = 4: 1.42 -> 2.08 Glines/s; 4096 bins
-        // x 10 lines: 0.43 -> 0.65 of HBM).  n_avg = 1, the reference's default (utils_supersdr.py:615): 407 -> 532 Mlines/s.
-        if (G >= 32 && (G >= 64 || LINEAR || nbins <= 16 * G) && nbins + 32 <= stage_words) {
+        // line-entry kernel, where the row stage is all there is, whenever it fits.  Measured against the old rule (groups of
+        // >= 256 threads only; random lines, B200): line entry 4096 bins x 10 lines 0.44 -> 0.55 of HBM, 1024 bins x 1 line (the
+        // reference's default averaging_n = 1, utils_supersdr.py:615) 414 -> 469 Mlines/s; FFT entry at n_avg = 1: 1024 / 2048 /
+        // 4096 points 0.31 / 0.27 / 0.27 -> 0.35 / 0.31 / 0.32.
+#ifndef SSDR_HIST_SMALL_GROUPS
+#define SSDR_HIST_SMALL_GROUPS 1      // 0: histogram only for groups of >= 256 threads (the rule before round 2's last session; comparison builds)
+#endif
+        if (G >= 32 && (G >= 256 || (SSDR_HIST_SMALL_GROUPS && (G >= 64 || LINEAR || nbins <= 16 * G))) && nbins + 32 <= stage_words) {
             // ---- rank p_lo (0-based) from a histogram of the keys in the (idle) frame buffer: 32 shared-memory
             // atomics per thread, one scan.  The first barrier above already ordered every warp's last FFT pass.
             unsigned* hist = reinterpret_cast<unsigned*>(stage);
@@ -748,7 +753,7 @@ SSDR_DEV void colour_stage(float* stage, int* red, int slot, int t, int ch, unsi
     constexpr int row_words = LINEAR ? N + N / 32 : N;          // extent of the row stage (padded when LINEAR)
     // (worth it when filling the table costs at most half of the per-bin evaluations: nkeys / G <= 16 -- large groups at any
     // n_avg <= ~25, and a 1024-bin warp-sized group at n_avg <= 2, the reference's default averaging_n = 1, utils_supersdr.py:615)
-    const bool use_lut = (2 * nkeys <= 32 * G) && (4 * nkeys <= N) && (row_words + nkeys <= stage_words);
+    const bool use_lut = (SSDR_HIST_SMALL_GROUPS ? (2 * nkeys <= 32 * G) : (G >= 256)) && (4 * nkeys <= N) && (row_words + nkeys <= stage_words);
     if (use_lut) {
         float* lut = stage + row_words;
         auto fill = [&](auto fast) { for (int k = t; k < nkeys; k += G) lut[k] = colour_of((float)k, fast); };
