@@ -342,6 +342,9 @@ SSDR_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
         "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra WAIT_%=;\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
+// (A guarded variant of this wait -- trap after 2^32 cycles instead of spinning for ever on a lost tile copy -- was measured: it
+// costs 1.5 % on config 2 and 3 % at 1024 points even when only the tile waits carry it, so the waits stay plain; the tile
+// geometry is fixed at compile time per size and covered by the parity tests at every size and both sample formats.)
 
 // ---- TMA staging of the raw frame (STAGED kernels) ----------------------------------------------
 // expect `bytes` of bulk-copy traffic on the barrier and arrive once
@@ -1624,11 +1627,12 @@ static int launch_fft(const WfKernelParams& kp, int fmt, int window, cudaStream_
         // requests on peer addresses are pathologically slow (section 7).  SSDR_WF_STAGED=0 selects the direct-load kernel
         // (the comparison arm of profiles/).
         static const bool staged_on = [] { const char* e = getenv("SSDR_WF_STAGED"); return !(e && e[0] == '0'); }();
-        if (staged_on && kp.prefetch && ((uintptr_t)kp.iq & 15u) == 0) {
-            if constexpr (!C::STAGE_BULK) {
-                const int rc = make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg, C::R0, (C::G <= 32) ? 32 : 32 * C::NB0, C::M0);
-                if (rc) return rc;
-            }
+        bool staged = staged_on && kp.prefetch && ((uintptr_t)kp.iq & 15u) == 0;
+        if constexpr (!C::STAGE_BULK) {
+            // a driver without cuTensorMapEncodeTiled (or an input the encoder refuses) takes the direct-load GPU kernel
+            if (staged && make_stage_tmap(&tmap, kp.iq, fmt, (size_t)kp.batch * kp.n_avg, C::R0, (C::G <= 32) ? 32 : 32 * C::NB0, C::M0) != SSDR_OK) staged = false;
+        }
+        if (staged) {
             if (fmt == SSDR_IQ_CF32) return window ? launch(wf_fft_kernel<LG, SSDR_IQ_CF32, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_CF32, false, true>);
             return window ? launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, true, true>) : launch(wf_fft_kernel<LG, SSDR_IQ_S16BE, false, true>);
         }
