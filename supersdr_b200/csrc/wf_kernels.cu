@@ -1583,6 +1583,9 @@ __global__ void __launch_bounds__(1024) wf_colour_big_kernel(const WfKernelParam
 // Tensor map of the input seen as [frames x 16 rows][1024 samples] (32-bit words), box = 16 rows x 64 samples: the tile one
 // warp of the staged 16384-point kernel pulls per frame.  The driver's encoder is reached through the runtime
 // (cudaGetDriverEntryPoint), so the library does not link libcuda.
+#ifndef SSDR_TMAP_L2
+#define SSDR_TMAP_L2 CU_TENSOR_MAP_L2_PROMOTION_L2_128B      // measured: NONE / 128B / 256B make no difference
+#endif
 static int make_stage_tmap(CUtensorMap* tm, const void* iq, int fmt, size_t frames, int rows_per_frame, int cols_per_warp, int row_len) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1599,7 +1602,7 @@ static int make_stage_tmap(CUtensorMap* tm, const void* iq, int fmt, size_t fram
     const cuuint32_t box[2] = {(cuuint32_t)cols_per_warp * words, (cuuint32_t)rows_per_frame};      // 16 x 64 (N = 16384) or 8 x 128 (N = 8192) samples: 8 KB as complex64
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(iq), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_SWIZZLE_NONE, SSDR_TMAP_L2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SSDR_E_CUDA; }
     return SSDR_OK;
 }
