@@ -1,11 +1,12 @@
 #!/bin/bash
-# bounded mbarrier wait: parity + bench + sweep rows; EVERY command under its own timeout
-timeout 600 python -m pytest tests/test_gpu_waterfall.py tests/test_gpu_bench_shapes.py -m gpu -q -x -k "not demod" 2>&1 | tail -2
-timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-demod --no-e2e 2>&1 | python -c "
+# fast atan2 of the NBFM detector: parity (both engines, float64 oracle at 1e-5) + per-mode throughput + bench lines; all under timeouts
+timeout 600 python -m pytest tests/test_gpu_audio.py tests/test_gpu_bench_shapes.py -m gpu -q 2>&1 | tail -6
+timeout 300 python scripts/demod_modes.py --modes usb,am,nbfm 2>&1 | cut -c1-130
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('bench', d['ms_per_step'], d['roofline']['frac'])
+        d = json.loads(l)
+        for k, v in (d.get('demod') or {}).items():
+            print(' ', k, {e: (round(x['value'] / 1e3, 1), x.get('pcm_checksum'), x.get('pcm_checksum_ok')) for e, x in v['engines'].items()})
 "
-timeout 120 python scripts/sweep.py --sizes 512,1024 --batches 65536 --n-avg 10 --max-bytes 9e9 | cut -c1-150
-timeout 120 python scripts/sweep.py --sizes 2048,4096,8192 --batches 4096 --n-avg 10 --max-bytes 9e9 | cut -c1-150
