@@ -140,8 +140,15 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
             prv = z;
         }
     } else if (cp.mode == SSDR_MODE_AM) {
-        // carrier tracker dc[k] = dc[k-1] + beta (mag[k] - dc[k-1]) in float64: lane-local
-        // recurrence from a zero (lane 0: true) carry-in, then an affine warp scan.
+        // carrier tracker dc[k] = dc[k-1] + beta (mag[k] - dc[k-1]): lane-local recurrence from a zero (lane 0: true) carry-in,
+        // then an affine warp scan.  SSDR_DEMOD_AM_F64 = 1 keeps the float64 recurrence of round 1; the default is float32
+        // (round 2): the tracker is a leaky integrator (it forgets rounding errors with its time constant), its steady-state
+        // error is ~4e-7 of the carrier, the same order as the float32 rounding of |z2| that enters it -- and the float64
+        // conversions and DFMA chains made AM 1.4 x as dear as USB.
+#ifndef SSDR_DEMOD_AM_F64
+#define SSDR_DEMOD_AM_F64 0
+#endif
+#if SSDR_DEMOD_AM_F64
         double B = (lane == 0) ? st.dc : 0.0;
 #pragma unroll
         for (int r = 0; r < SPL; ++r) B = B + kDemodAmBeta * ((double)mag[r] - B);
@@ -160,6 +167,26 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
             d = d + kDemodAmBeta * ((double)mag[r] - d);
             a[r] = (float)((double)mag[r] - d);
         }
+#else
+        constexpr float beta = (float)kDemodAmBeta;
+        float B = (lane == 0) ? (float)st.dc : 0.0f;
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) B = fmaf(beta, mag[r] - B, B);
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const float up = LM::up(B, 1 << s);
+            if (lane >= (1 << s)) B = fmaf((float)kp.am_pow16[s], up, B);   // (om^16)^(2^s)
+        }
+        float carry = LM::up(B, 1);
+        if (lane == 0) carry = (float)st.dc;
+        st.dc = (double)LM::from(B, 31);
+        float d = carry;
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) {
+            d = fmaf(beta, mag[r] - d, d);
+            a[r] = mag[r] - d;
+        }
+#endif
     } else {
         // one NCO evaluation per four samples (the phase accumulator is exact), the other three by rotation
         float c2, s2;
