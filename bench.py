@@ -41,8 +41,10 @@ WORKLOAD = "config[1]: batch=4096 ch/GPU x 10 frames x 16384-pt complex64 IQ -> 
 # one call), per engine -- pinned after tests/test_gpu_bench_shapes.py verified those very outputs against the float64
 # oracle on a B200.  bench.py prints the checksum it measures and whether it equals the pinned one.
 DEMOD_CHECKSUMS = {
-    "config3_usb": {"ffma": 297247085015311913, "tcgen05": 297247095484791993},
-    "config4_mixed": {"ffma": 291346432542179212, "tcgen05": 291346590091710117},      # re-pinned: fast atan2 (NBFM), float32 carrier tracker (AM)
+    # re-pinned in round 2 with every arithmetic change of the back end: fast atan2 (NBFM), float32 carrier tracker (AM),
+    # log2-of-power AGC + approximate RSSI logarithm (all modes)
+    "config3_usb": {"ffma": 297247096073910206, "tcgen05": 297247106553671661},
+    "config4_mixed": {"ffma": 291346435913516837, "tcgen05": 291346593460303034},
 }
 
 

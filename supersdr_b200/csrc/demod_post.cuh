@@ -101,24 +101,28 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
                                                  int ch, int b, size_t s0, DemodRegs& st) {
     constexpr int SPL = kDemodSpl, FR = SSDR_FRAME;
     const int lane = LM::logical(threadIdx.x & 31);
-    // ---- magnitude, RSSI -----------------------------------------------------------------
-    float mag[SPL];
-    float psum = 0.f, bmax = 0.f;
+    // ---- power, RSSI, block peak ---------------------------------------------------------------
+    // Everything that only compares or takes logarithms of |z| works on the POWER |z|^2 (round 2): the square root is
+    // monotonic, so the block peak is one sqrt of the largest power, and the AGC (below) takes log2 of powers; only the AM
+    // detector needs the 16 magnitudes.
+    float pw[SPL];
+    float psum = 0.f, pmax = 0.f;
 #pragma unroll
     for (int r = 0; r < SPL; ++r) {
-        float p = acc[r].x * acc[r].x + acc[r].y * acc[r].y;
-        psum += p;
-        mag[r] = sqrt_approx(p);
-        bmax = fmaxf(bmax, mag[r]);
+        pw[r] = acc[r].x * acc[r].x + acc[r].y * acc[r].y;
+        psum += pw[r];
+        pmax = fmaxf(pmax, pw[r]);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        psum += __shfl_xor_sync(0xffffffffu, psum, o);
-        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-    }
-    if (kp.rssi && lane == 0) {
-        float mp = fmaxf(psum * (1.0f / FR), 1e-30f);
-        kp.rssi[(size_t)ch * (kp.pitch / FR) + b] = 10.0f * log10f(mp * (1.0f / (SSDR_FS * SSDR_FS))) + kDemodFsDbm;
+    for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+    const float bmax = sqrt_approx(pmax);
+    if (kp.rssi) {                                           // warp-uniform; no divergent library call on the frame's critical path
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        // 10 log10(mean |z|^2 / FS^2) + FS_DBM with FS = 2^15; lg2.approx: ~1e-6 dB (the tests allow 1e-3)
+        static_assert(SSDR_FS == 32768.0f, "RSSI and AGC constants assume FS = 2^15");
+        const float db = fmaf(lg2_approx(fmaxf(psum * (1.0f / FR), 1e-30f)) - 30.0f, 3.0102999566398120f, kDemodFsDbm);
+        if (lane == 0) kp.rssi[(size_t)ch * (kp.pitch / FR) + b] = db;
     }
     // ---- detector --------------------------------------------------------------------------
     float a[SPL];
@@ -148,6 +152,9 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
 #ifndef SSDR_DEMOD_AM_F64
 #define SSDR_DEMOD_AM_F64 0
 #endif
+        float mag[SPL];
+#pragma unroll
+        for (int r = 0; r < SPL; ++r) mag[r] = sqrt_approx(pw[r]);
 #if SSDR_DEMOD_AM_F64
         double B = (lane == 0) ? st.dc : 0.0;
 #pragma unroll
@@ -213,16 +220,23 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
 #pragma unroll
         for (int r = 0; r < SPL; ++r) out[r] = a[r] * cp.man_gain;
     } else {
-        // hang: hm[k] = max(max(ring), prefix max of mag)
-        float hb = st.ring;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) hb = fmaxf(hb, __shfl_xor_sync(0xffffffffu, hb, o));
-        float m[SPL];
-        float run = 0.f;
-#pragma unroll
-        for (int r = 0; r < SPL; ++r) { run = fmaxf(run, mag[r]); m[r] = cp.agc_hang ? run : mag[r]; }
+        // Envelope and gain in the log2-of-POWER domain (round 2; the linear form -- u[k] = hm[k] 2^(k c2), prefix max, e[k] =
+        // M[k] 2^(-k c2), gain = AGC_OUT 2^(max(log2(e / FS), knee2) (slope/100 - 1)) -- cost 13 instructions per sample,
+        // this one 9, with the same two MUFU per sample and no square root):
+        //   Q[k] = log2(hm[k]^2),  U[k] = Q[k] + 2 k c2,  M[k] = max(prefix max U, 2 log2(e_in) - 2 c2),  2 log2 e[k] = M[k] - 2 k c2,
+        //   gain = 2^(max(2 log2 e, 2 (knee2 + 15)) (slope/100 - 1) / 2 + log2(AGC_OUT) - 15 (slope/100 - 1)).
+        // k = 16 lane + r: the lane part of 2 k c2 is added for the cross-lane scan only.  Silence (log2 0 = -inf) stays -inf
+        // through max / fma and ends at the knee; no inf - inf can occur.
+        static_assert(kDemodAgcOut == 0.5f, "log2(AGC_OUT) = -1 below");
+        float q[SPL];                                        // hm^2: hang = max(max(ring), prefix max of |z|)
         if (cp.agc_hang) {
-            float excl = run;                          // inclusive scan of lane maxima
+            float hb = st.ring;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) hb = fmaxf(hb, __shfl_xor_sync(0xffffffffu, hb, o));
+            float run = 0.f;
+#pragma unroll
+            for (int r = 0; r < SPL; ++r) { run = fmaxf(run, pw[r]); q[r] = run; }
+            float excl = run;                                // inclusive scan of lane maxima
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
                 float up = LM::up(excl, 1 << s);
@@ -230,44 +244,41 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
             }
             excl = LM::up(excl, 1);
             if (lane == 0) excl = 0.f;
-            excl = fmaxf(excl, hb);
+            excl = fmaxf(excl, hb * hb);
 #pragma unroll
-            for (int r = 0; r < SPL; ++r) m[r] = fmaxf(m[r], excl);
+            for (int r = 0; r < SPL; ++r) q[r] = fmaxf(q[r], excl);
+        } else {
+#pragma unroll
+            for (int r = 0; r < SPL; ++r) q[r] = pw[r];
         }
-        // u[k] = hm[k] 2^(k c2); M = prefix max with seed e_in 2^(-c2); e[k] = M[k] 2^(-k c2).  k = 16 lane + r:
-        // 2^(+-k c2) = 2^(+-16 lane c2) * (2^(+-c2))^r, the second factor by a running product (16 steps)
-        const float up1 = ex2_approx(cp.c2), dn1 = ex2_approx(-cp.c2);
-        float upk = ex2_approx((float)(SPL * lane) * cp.c2), dnk = ex2_approx(-(float)(SPL * lane) * cp.c2);
-        float mrun = 0.f;
-        float u[SPL];
-        float dn[SPL];
+        const float c2d = 2.0f * cp.c2;
+        const float ninf = __int_as_float(0xff800000);
+        float W[SPL];
+        float w = ninf;
 #pragma unroll
         for (int r = 0; r < SPL; ++r) {
-            u[r] = m[r] * upk;
-            dn[r] = dnk;
-            upk *= up1; dnk *= dn1;
-            mrun = fmaxf(mrun, u[r]);
-            u[r] = mrun;
+            w = fmaxf(w, fmaf((float)r, c2d, lg2_approx(q[r])));
+            W[r] = w;
         }
-        float pre = mrun;
+        const float base = (float)(SPL * lane) * c2d;
+        float pre = w + base;
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
             float up = LM::up(pre, 1 << s);
             if (lane >= (1 << s)) pre = fmaxf(pre, up);
         }
         pre = LM::up(pre, 1);
-        if (lane == 0) pre = 0.f;
-        pre = fmaxf(pre, st.e_in * dn1);
-        float e_last = 0.f;
+        if (lane == 0) pre = ninf;
+        pre = fmaxf(pre, fmaf(2.0f, lg2_approx(st.e_in), -c2d)) - base;
+        const float knee = 2.0f * (cp.knee2 + 15.0f), gs = 0.5f * cp.slope_m1, gc = fmaf(-15.0f, cp.slope_m1, -1.0f);
+        float e2_last = ninf;
 #pragma unroll
         for (int r = 0; r < SPL; ++r) {
-            float e = fmaxf(u[r], pre) * dn[r];
-            float m2 = lg2_approx(e * (1.0f / SSDR_FS));
-            float g = kDemodAgcOut * ex2_approx(fmaxf(m2, cp.knee2) * cp.slope_m1);
-            out[r] = a[r] * g;
-            e_last = e;
+            const float e2 = fmaf(-(float)r, c2d, fmaxf(W[r], pre));
+            out[r] = a[r] * ex2_approx(fmaf(fmaxf(e2, knee), gs, gc));
+            e2_last = e2;
         }
-        st.e_in = LM::from(e_last, 31);
+        st.e_in = ex2_approx(0.5f * LM::from(e2_last, 31));
     }
     // ---- outputs: 16 consecutive samples per lane ----------------------------------------------
     const size_t o0 = s0 + (size_t)SPL * lane;
