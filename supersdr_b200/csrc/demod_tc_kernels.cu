@@ -41,6 +41,9 @@
 #ifndef SSDR_TC_LASTARRIVER
 #define SSDR_TC_LASTARRIVER 1     // 1: the last warp of a tile to arrive issues the MMAs; 0: tile barrier, fixed issuer thread
 #endif
+#ifndef SSDR_TC_ISSUE_BLOCK
+#define SSDR_TC_ISSUE_BLOCK 1     // 1: the frame's 30 MMAs + commit as one asm block (one elect); 0: one asm statement per MMA
+#endif
 #ifndef SSDR_TC_TILES
 #define SSDR_TC_TILES 4           // tiles (groups of four warps) per CTA: 16 warps at 128 registers
 #endif
@@ -112,7 +115,20 @@ constexpr unsigned SMEM_BYTES = B_BYTES + B16_BYTES + TILES * (TILE_BYTES + WARP
 constexpr unsigned TMEM_COLS = TILES > 2 ? 512 : 256;       // two accumulators of 64 columns per tile, allocation is a power of two
 
 __device__ __forceinline__ unsigned swz(unsigned off) { return off ^ (((off >> 7) & 7u) << 4); }   // off from a 1024-aligned base
-__device__ __forceinline__ float tf32_hi(float x) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+// x rounded to TF32 (10 mantissa bits), nearest with ties away from zero = cvt.rna.tf32.f32 for every finite x: half an ulp
+// added to the magnitude bits, low 13 bits cleared.  ptxas expands the cvt to four instructions (add, |x| >= inf test, select,
+// mask) to keep inf / NaN payloads; the operands here are finite (int16-scale IQ times unit-gain taps), so two suffice --
+// 64 instructions per lane and frame less on the mixer's store path, bit-identical results.
+#ifndef SSDR_TC_CVT_RNA
+#define SSDR_TC_CVT_RNA 0
+#endif
+__device__ __forceinline__ float tf32_hi(float x) {
+#if SSDR_TC_CVT_RNA
+    unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u);
+#else
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+#endif
+}
 
 __device__ __forceinline__ uint64_t desc_sw128(unsigned addr, unsigned sbo) {
     uint64_t d = 0;
@@ -166,6 +182,84 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
         : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// The 30 MMAs + commit of one frame as ONE instruction block (round 2): one elect.sync for all of them, the descriptor
+// low words stepped by immediates -- issued as separate asm statements each MMA carried its own ELECT / VOTEU pair and
+// re-materialised its constants (~14 instructions per MMA).  The immediates are the operand geometry in 16-byte units:
+//   TF32 step (c, j): A + 8 c + 2 j (row shift c x 128 bytes, K step j x 32 bytes), B + 512 c + 2 j (K chunk c x B_ATOM);
+//   bf16 step (c, j): A16 + 2 j x A16_LBO / 16 + c, B16 + (4 c + 2 j) x B16_LBO / 16.
+static_assert(ROWB == 128 && B_ATOM == 8192 && A16_LBO == 3104 && B16_LBO == 512 && KCH == 5, "immediates of tc_issue_block");
+__device__ __forceinline__ void tc_issue_block(unsigned td, unsigned a_lo, unsigned a_hi, unsigned b_lo, unsigned b_hi, unsigned a16_lo,
+                                               unsigned a16_hi, unsigned b16_lo, unsigned b16_hi, unsigned i64, unsigned i16, unsigned barp) {
+    asm volatile(
+        "{\n\t.reg .pred p, acc;\n\t.reg .b64 da, db;\n\t.reg .b32 ta, tb;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "setp.ne.b32 acc, 0, 0;\n\t"
+        "add.u32 ta, %1, 0;\n\tadd.u32 tb, %3, 0;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "setp.eq.b32 acc, 0, 0;\n\t"
+        "add.u32 ta, %1, 2;\n\tadd.u32 tb, %3, 2;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 4;\n\tadd.u32 tb, %3, 4;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 6;\n\tadd.u32 tb, %3, 6;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %5, 0;\n\tadd.u32 tb, %7, 0;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "add.u32 ta, %5, 388;\n\tadd.u32 tb, %7, 64;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "add.u32 ta, %1, 8;\n\tadd.u32 tb, %3, 512;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 10;\n\tadd.u32 tb, %3, 514;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 12;\n\tadd.u32 tb, %3, 516;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 14;\n\tadd.u32 tb, %3, 518;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %5, 1;\n\tadd.u32 tb, %7, 128;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "add.u32 ta, %5, 389;\n\tadd.u32 tb, %7, 192;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "add.u32 ta, %1, 16;\n\tadd.u32 tb, %3, 1024;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 18;\n\tadd.u32 tb, %3, 1026;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 20;\n\tadd.u32 tb, %3, 1028;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 22;\n\tadd.u32 tb, %3, 1030;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %5, 2;\n\tadd.u32 tb, %7, 256;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "add.u32 ta, %5, 390;\n\tadd.u32 tb, %7, 320;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "add.u32 ta, %1, 24;\n\tadd.u32 tb, %3, 1536;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 26;\n\tadd.u32 tb, %3, 1538;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 28;\n\tadd.u32 tb, %3, 1540;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 30;\n\tadd.u32 tb, %3, 1542;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %5, 3;\n\tadd.u32 tb, %7, 384;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "add.u32 ta, %5, 391;\n\tadd.u32 tb, %7, 448;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "add.u32 ta, %1, 32;\n\tadd.u32 tb, %3, 2048;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 34;\n\tadd.u32 tb, %3, 2050;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 36;\n\tadd.u32 tb, %3, 2052;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %1, 38;\n\tadd.u32 tb, %3, 2054;\n\tmov.b64 da, {ta, %2};\n\tmov.b64 db, {tb, %4};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %9, acc;\n\t"
+        "add.u32 ta, %5, 4;\n\tadd.u32 tb, %7, 512;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "add.u32 ta, %5, 392;\n\tadd.u32 tb, %7, 576;\n\tmov.b64 da, {ta, %6};\n\tmov.b64 db, {tb, %8};\n\t"
+        "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %10, acc;\n\t"
+        "@p tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t}"
+        ::"r"(td), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(a16_lo), "r"(a16_hi), "r"(b16_lo), "r"(b16_hi), "r"(i64), "r"(i16), "r"(barp)
+        : "memory");
 }
 
 struct alignas(8) TcShared {
@@ -395,6 +489,9 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                     const uint64_t dA16 = desc_none(aA16, A16_LBO, GROWS * 16u), dB16 = desc_none(aB16, B16_LBO, 128u);
                     const unsigned a_lo = (unsigned)dA, a_hi = (unsigned)(dA >> 32), b_lo = (unsigned)dB, b_hi = (unsigned)(dB >> 32);
                     const unsigned a16_lo = (unsigned)dA16, a16_hi = (unsigned)(dA16 >> 32), b16_lo = (unsigned)dB16, b16_hi = (unsigned)(dB16 >> 32);
+#if SSDR_TC_ISSUE_BLOCK
+                    tc_issue_block(td, a_lo, a_hi, b_lo, b_hi, a16_lo, a16_hi, b16_lo, b16_hi, i64, i16, barp);
+#else
 #pragma unroll
                     for (int c = 0; c < KCH; ++c) {
 #pragma unroll
@@ -409,6 +506,7 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                         }
                     }
                     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(barp) : "memory");
+#endif
                 }
             }
             __syncwarp();
