@@ -51,6 +51,18 @@ __device__ __forceinline__ void nco(unsigned ph, float& c, float& s) {
     __sincosf(a, &s, &c);
 }
 
+// Complex products as two packed fp32x2 instructions (FMUL2 + FFMA2; the half swap, the broadcast and the half negation are
+// operand modifiers on sm_100a) instead of four scalar ones: the NCO rotations and the mixer are a quarter of the
+// demodulator's per-sample instructions.
+__device__ __forceinline__ float2 cmul2(float2 u, float2 w) {            // u w
+    const float2 t = __fmul2_rn(make_float2(u.y, u.x), make_float2(w.y, w.y));
+    return __ffma2_rn(u, make_float2(w.x, w.x), make_float2(-t.x, t.y));
+}
+__device__ __forceinline__ float2 cmulc2(float2 u, float2 w) {           // u conj(w)
+    const float2 t = __fmul2_rn(make_float2(u.y, u.x), make_float2(w.y, w.y));
+    return __ffma2_rn(u, make_float2(w.x, w.x), make_float2(t.x, -t.y));
+}
+
 // logical lane = physical lane
 struct LanesNatural {
     __device__ __forceinline__ static int logical(int lane) { return lane; }
@@ -106,13 +118,16 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
     // monotonic, so the block peak is one sqrt of the largest power, and the AGC (below) takes log2 of powers; only the AM
     // detector needs the 16 magnitudes.
     float pw[SPL];
-    float psum = 0.f, pmax = 0.f;
+    float pmax = 0.f;
+    float2 ps2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < SPL; ++r) {
+    for (int r = 0; r < SPL; r += 2) {
         pw[r] = acc[r].x * acc[r].x + acc[r].y * acc[r].y;
-        psum += pw[r];
-        pmax = fmaxf(pmax, pw[r]);
+        pw[r + 1] = acc[r + 1].x * acc[r + 1].x + acc[r + 1].y * acc[r + 1].y;
+        ps2 = __fadd2_rn(ps2, make_float2(pw[r], pw[r + 1]));
+        pmax = fmaxf(pmax, fmaxf(pw[r], pw[r + 1]));
     }
+    float psum = ps2.x + ps2.y;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
     const float bmax = sqrt_approx(pmax);
@@ -196,18 +211,16 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
 #endif
     } else {
         // one NCO evaluation per four samples (the phase accumulator is exact), the other three by rotation
-        float c2, s2;
-        nco(cp.inc2, c2, s2);
+        float2 r2;
+        nco(cp.inc2, r2.x, r2.y);
 #pragma unroll
         for (int r4 = 0; r4 < SPL; r4 += 4) {
-            float c, s;
-            nco(st.ph2 + (unsigned)(SPL * lane + r4) * cp.inc2, c, s);
+            float2 w;
+            nco(st.ph2 + (unsigned)(SPL * lane + r4) * cp.inc2, w.x, w.y);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                a[r4 + i] = acc[r4 + i].x * c - acc[r4 + i].y * s;       // Re(z * exp(+j theta2))
-                const float cn = c * c2 - s * s2;
-                s = s * c2 + c * s2;
-                c = cn;
+                a[r4 + i] = acc[r4 + i].x * w.x - acc[r4 + i].y * w.y;   // Re(z * exp(+j theta2))
+                if (i < 3) w = cmul2(w, r2);
             }
         }
     }
@@ -218,7 +231,10 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
         for (int r = 0; r < SPL; ++r) out[r] = a[r];
     } else if (!cp.agc_on) {
 #pragma unroll
-        for (int r = 0; r < SPL; ++r) out[r] = a[r] * cp.man_gain;
+        for (int r = 0; r < SPL; r += 2) {
+            const float2 o = __fmul2_rn(make_float2(a[r], a[r + 1]), make_float2(cp.man_gain, cp.man_gain));
+            out[r] = o.x; out[r + 1] = o.y;
+        }
     } else {
         // Envelope and gain in the log2-of-POWER domain (round 2; the linear form -- u[k] = hm[k] 2^(k c2), prefix max, e[k] =
         // M[k] 2^(-k c2), gain = AGC_OUT 2^(max(log2(e / FS), knee2) (slope/100 - 1)) -- cost 13 instructions per sample,
@@ -273,10 +289,12 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
         const float knee = 2.0f * (cp.knee2 + 15.0f), gs = 0.5f * cp.slope_m1, gc = fmaf(-15.0f, cp.slope_m1, -1.0f);
         float e2_last = ninf;
 #pragma unroll
-        for (int r = 0; r < SPL; ++r) {
-            const float e2 = fmaf(-(float)r, c2d, fmaxf(W[r], pre));
-            out[r] = a[r] * ex2_approx(fmaf(fmaxf(e2, knee), gs, gc));
-            e2_last = e2;
+        for (int r = 0; r < SPL; r += 2) {
+            const float e2a = fmaf(-(float)r, c2d, fmaxf(W[r], pre)), e2b = fmaf(-(float)(r + 1), c2d, fmaxf(W[r + 1], pre));
+            const float2 o = __fmul2_rn(make_float2(a[r], a[r + 1]), make_float2(ex2_approx(fmaf(fmaxf(e2a, knee), gs, gc)),
+                                                                                   ex2_approx(fmaf(fmaxf(e2b, knee), gs, gc))));
+            out[r] = o.x; out[r + 1] = o.y;
+            e2_last = e2b;
         }
         st.e_in = ex2_approx(0.5f * LM::from(e2_last, 31));
     }

@@ -371,8 +371,8 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
         unsigned ph1_mix = st.ph1;                          // the back end advances st.ph1 one frame later than the mixer
         // mixer, part 1: every lane takes four consecutive samples of each quarter frame (coalesced 16 / 32-byte loads):
         // y[4 q + i] = sample 128 q + 4 lane + i.  One NCO evaluation per four samples, the other three by rotation.
-        float rc1, rs1;
-        nco(cp.inc1, rc1, rs1);
+        float2 r1;
+        nco(cp.inc1, r1.x, r1.y);
         auto mix_compute = [&](int b, float2 (&y)[SPL]) {
             const size_t s0 = (size_t)ch * kp.pitch + (size_t)b * FR;
             float2 xin[SPL];
@@ -384,15 +384,12 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float c, s;
-                nco(ph1_mix + (unsigned)(128 * q + 4 * lane) * cp.inc1, c, s);
+                float2 w;
+                nco(ph1_mix + (unsigned)(128 * q + 4 * lane) * cp.inc1, w.x, w.y);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float2 x = xin[4 * q + i];
-                    y[4 * q + i] = make_float2(x.x * c + x.y * s, x.y * c - x.x * s);      // x exp(-j theta)
-                    const float cn = c * rc1 - s * rs1;
-                    s = s * rc1 + c * rs1;
-                    c = cn;
+                    y[4 * q + i] = cmulc2(xin[4 * q + i], w);                              // x exp(-j theta)
+                    if (i < 3) w = cmul2(w, r1);
                 }
             }
             ph1_mix += (unsigned)FR * cp.inc1;
@@ -429,7 +426,10 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
                 tmem_ld32(taddr + 32u, w);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += w[i];
+                for (int i = 0; i < 32; i += 2) {           // consecutive columns = consecutive registers: packed adds
+                    const float2 t = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(w[i], w[i + 1]));
+                    v[i] = t.x; v[i + 1] = t.y;
+                }
             }
             if (!active) return;
             // pair exchange: lanes p and p ^ 16 swap the halves they do not keep
