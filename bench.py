@@ -527,6 +527,14 @@ def main():
                     pk = 1590.0 / 2
                 comp = {"bound": "tensor", "achieved": gs * fl / 1e3, "peak": pk, "unit": "TFLOP/s (TF32-equivalent, executed)",
                         "frac": gs * fl / 1e3 / pk, "peak_source": "half the measured sustained bf16 cuBLAS rate (TF32 = bf16 / 2)"}
+                # the pipe that binds this engine: shared-memory data pipe, 128-byte wavefronts.  Per sample
+                # (ncu, config 3, profiles/r2final_demod_tc_ncu_summary.txt): 89.1 M tensor-core operand wavefronts + 47.3 M LSU
+                # wavefronts per 134.2 M samples = 1.017; peak = one wavefront per cycle and SM at the nominal clock
+                wf_per_sample, smem_peak = (89128960 + 47344057) / 134217728.0, 148 * 1.965
+                return {"hbm": hbm, "compute": comp,
+                        "smem": {"bound": "shared-memory data pipe", "achieved": gs * wf_per_sample, "peak": smem_peak,
+                                 "unit": "Gwavefronts/s (128 B)", "frac": gs * wf_per_sample / smem_peak,
+                                 "peak_source": "nominal: 148 SMs x 1 wavefront/cycle x 1965 MHz; wavefronts per sample from ncu"}}
             return {"hbm": hbm, "compute": comp}
 
         def demod_case_run(key, workload, B, ns_ch, params):
@@ -564,8 +572,8 @@ def main():
             d = {"workload": workload, "value": world * ns / dms / 1e3, "unit": "Msamples/s", "ms_per_step": dms,
                  "hbm_gbs": ns * 12 / dms / 1e6, "engine": best, "engines": per_engine,
                  "bound": "HBM bound 12 B/sample; ffma engine: fp32 pipe (direct-form 127-tap FIR, 4*127+~30 flop/sample); tcgen05 "
-                          "engine: FIR as a split-precision (TF32 + bfloat16) Toeplitz GEMM (bound by the tensor core's shared-memory operand "
-                          "reads) + the fp32/MUFU mixer, detector and AGC"}
+                          "engine: FIR as a split-precision (TF32 + bfloat16) Toeplitz GEMM + the fp32/MUFU mixer, detector and AGC: bound by the "
+                          "shared-memory data pipe (tensor-core operand reads 55 % + operand stores / read-back 29 % under ncu), see roofline.smem"}
             if not args.no_e2e:
                 hq = S.PinnedArray((B, ns_ch), np.complex64)
                 ho = S.PinnedArray((B, ns_ch), np.float32)
