@@ -215,7 +215,8 @@ int ssdr_demod_reset(ssdr_demod_t h);   /* zero all per-channel streaming state 
 /* FIR engine of the fused kernel.  FFMA: direct form on the fp32 pipe (one warp per channel).  TCGEN05: the FIR as a
  * Toeplitz GEMM on the 5th-generation tensor cores (TF32 + bfloat16 split, accumulators in TMEM); four channels that share a
  * filter (bitwise-equal taps) make one tile, so it pays when channels share pass-band widths.  AUTO (default): TCGEN05
- * when at least half of the tile rows would carry a channel, else FFMA.  Same per-channel state, same outputs to the
+ * when at least half of the tile rows would carry a channel and -- for banks of more rounds than SMs -- its measured cost
+ * model (rounds share one filter: few channels per filter leave tiles empty) beats the FFMA engine's, else FFMA.  Same per-channel state, same outputs to the
  * demodulator's tolerance (1e-5 relative RMS); engines may be switched between calls.  No reference counterpart (the
  * DSP is remote, utils_supersdr.py:1022-1029). */
 #define SSDR_DEMOD_ENGINE_FFMA    0

@@ -129,6 +129,7 @@ struct ssdr_demod {
     std::vector<int> h_work;       // per channel: detector / AGC variant (channels of one quad should cost the same)
     bool quads_dirty = true;
     int n_quads = 0;               // rounds of demod_tc_tiles() quads
+    int used_quads = 0;            // non-empty quads (tiles that carry at least one channel) over all rounds
     int4* d_quad_ch = nullptr;
     int* d_quad_fid = nullptr;
     int* d_round_ctr = nullptr;    // work counter of the tcgen05 kernel (dynamic round scheduling)
@@ -758,8 +759,25 @@ static int demod_build_quads(ssdr_demod_t h) {
     SSDR_CUDA(cudaMemcpy(h->d_quad_ch, qc.data(), sizeof(int4) * qc.size(), cudaMemcpyHostToDevice));
     SSDR_CUDA(cudaMemcpy(h->d_quad_fid, qf.data(), sizeof(int) * qf.size(), cudaMemcpyHostToDevice));
     h->n_quads = (int)(qc.size() / tiles);                  // rounds
+    h->used_quads = 0;
+    for (const int4& q : qc) h->used_quads += q.x >= 0;
     h->quads_dirty = false;
     return SSDR_OK;
+}
+
+// AUTO rule.  The tcgen05 engine shares ONE Toeplitz operand per CTA round (four tiles of four channels), so a bank with few
+// channels per filter runs rounds with empty tiles and warps.  Measured on a B200 (scripts/demod_hetero.py, 4096 USB channels x
+// 32 frames, profiles/r2final_demod_hetero.jsonl): a round of k tiles over F frames costs 25 + F (1.22 + 0.734 k) us of
+// one SM (k = 1, 2, 4: 88, 111, 158 us at F = 32), the FFMA engine 0.916 F us of one SM per channel -- 2 channels per filter:
+// 58 against 83 Gsamples/s (FFMA wins), 4: 111 against 83, 16: 170, one filter: 215.  Tiles at least half full as before; and once
+// there are more rounds than SMs (throughput, not latency, decides) the cheaper total wins.
+static bool demod_auto_prefers_tc(const ssdr_demod_t h, int n_samples) {
+    if (h->quad_fill < 0.5) return false;
+    if (h->n_quads <= sm_count()) return true;
+    const double F = (double)n_samples / SSDR_FRAME;
+    const double tc = (double)h->n_quads * (25.0 + 1.22 * F) + 0.734 * F * (double)h->used_quads;
+    const double ff = 0.916 * F * (double)h->batch;
+    return tc < ff;
 }
 
 static int demod_launch_block(ssdr_demod_t h, const void* iq_dev, int iq_format, int n_samples, int pitch,
@@ -769,7 +787,7 @@ static int demod_launch_block(ssdr_demod_t h, const void* iq_dev, int iq_format,
     a.pcm_f32 = pcm_f32_dev; a.pcm_i16 = pcm_i16_dev; a.rssi = rssi_dev; a.batch = h->batch; a.n_samples = n_samples; a.pitch = pitch;
     for (int s = 0; s < 5; ++s) a.am_pow16[s] = h->am_pow16[s];
     if (h->engine != SSDR_DEMOD_ENGINE_FFMA && h->quads_dirty) { int rc = demod_build_quads(h); if (rc) return rc; }
-    if (h->engine == SSDR_DEMOD_ENGINE_TCGEN05 || (h->engine == SSDR_DEMOD_ENGINE_AUTO && h->quad_fill >= 0.5)) {
+    if (h->engine == SSDR_DEMOD_ENGINE_TCGEN05 || (h->engine == SSDR_DEMOD_ENGINE_AUTO && demod_auto_prefers_tc(h, n_samples))) {
         return demod_tc_launch(a, h->d_quad_ch, h->d_quad_fid, h->n_quads, h->d_round_ctr, h->compute);
     }
     return demod_launch(a, h->compute);

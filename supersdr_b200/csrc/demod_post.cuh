@@ -45,6 +45,35 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     return copysignf(r, y);
 }
 
+// Two samples at once, scaled by K = 32767 / pi (the NBFM detector's output unit): the reduction to t = min / max in [0, 1]
+// is scalar (one MUFU.RCP each), the polynomial runs as packed fp32x2 FFMA2 on (t0, t1) with the coefficients pre-multiplied
+// by K, the octant fix-ups use K pi / 2 and K pi.  Same approximation as atan2_fast (the scaled coefficients round once more:
+// +1 ulp).  (0, 0) -> 0 is handled here: min = max = 0 gives t = 0 * inf = NaN, so the caller's zero test selects 0.
+__device__ __forceinline__ float2 atan2_fast2_scaled(float y0, float x0, float y1, float x1) {
+    constexpr float K = 32767.0f / 3.14159265358979f;
+    const float mx0 = fmaxf(fabsf(x0), fabsf(y0)), mn0 = fminf(fabsf(x0), fabsf(y0));
+    const float mx1 = fmaxf(fabsf(x1), fabsf(y1)), mn1 = fminf(fabsf(x1), fabsf(y1));
+    float rc0, rc1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc0) : "f"(mx0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc1) : "f"(mx1));
+    const float2 t = __fmul2_rn(make_float2(mn0, mn1), make_float2(rc0, rc1));
+    const float2 q = __fmul2_rn(t, t);
+    float2 p = make_float2(-0.00455979211255908f * K, -0.00455979211255908f * K);
+    p = __ffma2_rn(p, q, make_float2(0.023780519142746925f * K, 0.023780519142746925f * K));
+    p = __ffma2_rn(p, q, make_float2(-0.05882975459098816f * K, -0.05882975459098816f * K));
+    p = __ffma2_rn(p, q, make_float2(0.09868865460157394f * K, 0.09868865460157394f * K));
+    p = __ffma2_rn(p, q, make_float2(-0.14003290235996246f * K, -0.14003290235996246f * K));
+    p = __ffma2_rn(p, q, make_float2(0.19966961443424225f * K, 0.19966961443424225f * K));
+    p = __ffma2_rn(p, q, make_float2(-0.3333181142807007f * K, -0.3333181142807007f * K));
+    p = __ffma2_rn(p, q, make_float2(0.9999998807907104f * K, 0.9999998807907104f * K));
+    float2 r = __fmul2_rn(p, t);
+    if (fabsf(y0) > fabsf(x0)) r.x = 1.57079637f * K - r.x;
+    if (fabsf(y1) > fabsf(x1)) r.y = 1.57079637f * K - r.y;
+    if (x0 < 0.0f) r.x = 3.14159274f * K - r.x;
+    if (x1 < 0.0f) r.y = 3.14159274f * K - r.y;
+    return make_float2(copysignf(r.x, y0), copysignf(r.y, y1));
+}
+
 // cos / sin of a 32-bit phase (2 pi phase / 2^32), MUFU path: abs error ~4e-7
 __device__ __forceinline__ void nco(unsigned ph, float& c, float& s) {
     float a = (float)(int)ph * 1.4629180792671596e-9f;   // 2 pi / 2^32
@@ -145,19 +174,26 @@ __device__ __forceinline__ void demod_frame_tail(const float2 (&acc)[kDemodSpl],
         float2 last = acc[SPL - 1];
         float2 prv = make_float2(LM::up(last.x, 1), LM::up(last.y, 1));
         if (lane == 0) prv = st.zprev;
+#ifndef SSDR_DEMOD_LIB_ATAN2
+#pragma unroll
+        for (int r = 0; r < SPL; r += 2) {                 // two samples per step: packed products and polynomial
+            const float2 d0 = cmulc2(acc[r], prv), d1 = cmulc2(acc[r + 1], acc[r]);      // z conj(prev) = (re, im)
+            const float2 ph = atan2_fast2_scaled(d0.y, d0.x, d1.y, d1.x);
+            // a zero product (first sample of a stream, or silence) demodulates to 0, not +-pi
+            a[r] = (d0.x == 0.0f && d0.y == 0.0f) ? 0.0f : ph.x;
+            a[r + 1] = (d1.x == 0.0f && d1.y == 0.0f) ? 0.0f : ph.y;
+            prv = acc[r + 1];
+        }
+#else
 #pragma unroll
         for (int r = 0; r < SPL; ++r) {
             float2 z = acc[r];
             float re = z.x * prv.x + z.y * prv.y;     // z * conj(prev)
             float im = z.y * prv.x - z.x * prv.y;
-            // a zero product (first sample of a stream, or silence) demodulates to 0, not +-pi
-#ifndef SSDR_DEMOD_LIB_ATAN2
-            a[r] = (re == 0.0f && im == 0.0f) ? 0.0f : atan2_fast(im, re) * (32767.0f / 3.14159265358979f);
-#else
             a[r] = (re == 0.0f && im == 0.0f) ? 0.0f : atan2f(im, re) * (32767.0f / 3.14159265358979f);
-#endif
             prv = z;
         }
+#endif
     } else if (cp.mode == SSDR_MODE_AM) {
         // carrier tracker dc[k] = dc[k-1] + beta (mag[k] - dc[k-1]): lane-local recurrence from a zero (lane 0: true) carry-in,
         // then an affine warp scan.  SSDR_DEMOD_AM_F64 = 1 keeps the float64 recurrence of round 1; the default is float32

@@ -154,6 +154,7 @@ __device__ __forceinline__ constexpr unsigned idesc_tf32(int m, int n) {
 __device__ __forceinline__ constexpr unsigned idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
+#if !SSDR_TC_ISSUE_BLOCK
 // MMAs for a warp-UNIFORM issue section (every lane holds the same operands, one elected lane issues): descriptors
 // as (lo, hi) words so that stepping through the operand is one 32-bit add on the low word (start-address field).
 __device__ __forceinline__ void mma_tf32_elect(unsigned tmem, unsigned da_lo, unsigned da_hi, unsigned db_lo, unsigned db_hi, unsigned idesc, unsigned accumulate) {
@@ -166,6 +167,7 @@ __device__ __forceinline__ void mma_f16_elect(unsigned tmem, unsigned da_lo, uns
                  "@p tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, q;\n\t}"
                  ::"r"(tmem), "r"(da_lo), "r"(da_hi), "r"(db_lo), "r"(db_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+#endif
 __device__ __forceinline__ unsigned pack_bf16(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const unsigned*>(&v);

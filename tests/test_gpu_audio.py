@@ -183,6 +183,27 @@ def test_demod_auto_engine_picks_by_tile_fill(ssdr):
         assert _rel_rms(out["ffma"].astype(np.float64), out["tcgen05"].astype(np.float64)) < RMS_TOL
 
 
+def test_demod_auto_engine_many_filters_cost_model(ssdr):
+    """More rounds than SMs (the tcgen05 engine shares one filter per CTA round): with two channels per filter the
+    measured cost model of AUTO (capi.cu: demod_auto_prefers_tc, scripts/demod_hetero.py) picks the FFMA engine although
+    the tiles are half full; with one shared filter it stays on the tensor cores.  Bit for bit the explicit engine."""
+    n = 512 * 8
+    for per, expect in ((2, "ffma"), (600, "tcgen05")):
+        B = 600
+        uniq = [ssdr.demod_params("usb", hc=2400.0 + g) for g in range(B // per)]
+        params = [uniq[b // per] for b in range(B)]
+        iq = np.stack([tier_u.synth_demod_iq("usb", n, seed=300 + b % 7) for b in range(B)])
+        out = {}
+        for eng in ("auto", expect):
+            bank = ssdr.DemodBank(B, n, engine=eng)
+            bank.set_params(0, params)
+            out[eng] = bank.process(iq)["pcm_f32"]
+            bank.close()
+        assert np.array_equal(out["auto"], out[expect]), per
+        ref, _ = tier_u.demod(iq[B - 1], tier_u.DemodParams("usb", hc=2400.0 + (B - 1) // per), tier_u.DemodState())
+        assert _rel_rms(out["auto"][B - 1], ref) < RMS_TOL
+
+
 def test_interp_reference_golden(ssdr):
     """kiwi_sound.play_buffer (utils_supersdr.py:1121-1138) fixtures from the unmodified reference:
     int16 stereo within 1 LSB (np.convolve's summation order is BLAS-dependent)."""
