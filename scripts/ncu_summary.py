@@ -18,7 +18,11 @@ for vals in rows[2:]:
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "launch__occupancy_limit_registers",
             "launch__occupancy_limit_shared_mem", "smsp__thread_inst_executed_per_inst_executed.ratio",
             "sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active",
-            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]
+            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+            # tensor-core side (tcgen05 kernels): operand reads through the shared-memory data pipe, tensor pipe activity
+            "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]
     for k in keys:
         if k in d: print("  %-80s %s %s" % (k, d[k], u[k]))
     st = [(k, float(v)) for k, v in d.items() if k.startswith("smsp__average_warps_issue_stalled") and v]
