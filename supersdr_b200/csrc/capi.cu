@@ -687,10 +687,11 @@ static void demod_plan_rounds(const float* t, const int* work, int B, size_t til
     size_t used = 0;
     for (const int4& q : qc) used += q.x >= 0;
     *fill = used ? (double)B / (4.0 * (double)used) : 0.0;
-    // dearest rounds first (NBFM: atan2; AM: float64 carrier tracker), the cheap ones fill the tail
+    // dearest rounds first (measured per mode, profiles/r2final_demod_modes.jsonl: AM 207 < LSB / USB / CW 215 < NBFM 217 Gsamples/s
+    // since the detectors were trimmed in round 2), the cheap ones fill the tail
     {
         const size_t nr = qc.size() / tiles;
-        auto cost = [&](size_t r) { const int m = work[qc[r * tiles].x] / 4; return m == SSDR_MODE_NBFM ? 2 : m == SSDR_MODE_AM ? 1 : 0; };
+        auto cost = [&](size_t r) { const int m = work[qc[r * tiles].x] / 4; return m == SSDR_MODE_AM ? 2 : m == SSDR_MODE_NBFM ? 0 : 1; };
         std::vector<size_t> ro(nr);
         for (size_t r = 0; r < nr; ++r) ro[r] = r;
         std::stable_sort(ro.begin(), ro.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
@@ -711,13 +712,23 @@ static void demod_plan_rounds(const float* t, const int* work, int B, size_t til
             if (qc[i].x >= 0) { tq.push_back(qc[i]); tf.push_back(qf[i]); }
         const size_t per = (tq.size() + nsm - 1) / nsm;           // quads per narrow round
         if (per < tiles) {
-            qc.resize((nr - tail) * tiles); qf.resize((nr - tail) * tiles);
+            std::vector<int4> nq;
+            std::vector<int> nf;
             size_t i = 0;
             while (i < tq.size()) {
                 size_t k = 0;
                 const int f = tf[i];
-                for (; k < per && i < tq.size() && tf[i] == f; ++k, ++i) { qc.push_back(tq[i]); qf.push_back(f); }
-                for (; k < tiles; ++k) { qc.push_back(empty); qf.push_back(f); }
+                for (; k < per && i < tq.size() && tf[i] == f; ++k, ++i) { nq.push_back(tq[i]); nf.push_back(f); }
+                for (; k < tiles; ++k) { nq.push_back(empty); nf.push_back(f); }
+            }
+            // A round cannot mix filters, so with many filters the narrow rounds can outnumber the SMs (27 filters x 16 quads at 3
+            // per round: 162 rounds on 148 SMs) -- a third, mostly idle wave instead of the one the split was meant to fill
+            // (measured, scripts/demod_hetero.py: 64 channels per filter ran at 171 instead of 215 Gsamples/s).  Split only when the
+            // narrow rounds fit one wave.
+            if (nq.size() / tiles <= nsm) {
+                qc.resize((nr - tail) * tiles); qf.resize((nr - tail) * tiles);
+                qc.insert(qc.end(), nq.begin(), nq.end());
+                qf.insert(qf.end(), nf.begin(), nf.end());
             }
         }
     }
@@ -769,7 +780,7 @@ static int demod_build_quads(ssdr_demod_t h) {
 // channels per filter runs rounds with empty tiles and warps.  Measured on a B200 (scripts/demod_hetero.py, 4096 USB channels x
 // 32 frames, profiles/r2final_demod_hetero.jsonl): a round of k tiles over F frames costs 25 + F (1.22 + 0.734 k) us of
 // one SM (k = 1, 2, 4: 88, 111, 158 us at F = 32), the FFMA engine 0.916 F us of one SM per channel -- 2 channels per filter:
-// 58 against 83 Gsamples/s (FFMA wins), 4: 111 against 83, 16: 170, one filter: 215.  Tiles at least half full as before; and once
+// 58 against 83 Gsamples/s (FFMA wins), 4: 111 against 83, 16: 196, one filter: 216.  Tiles at least half full as before; and once
 // there are more rounds than SMs (throughput, not latency, decides) the cheaper total wins.
 static bool demod_auto_prefers_tc(const ssdr_demod_t h, int n_samples) {
     if (h->quad_fill < 0.5) return false;

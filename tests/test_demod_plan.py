@@ -54,7 +54,7 @@ def test_plan_mixed_modes_cost_order_and_padding():
     qc, qf, tiles, fill = _check_plan(params, 8)
     assert len(set(qf.tolist())) == 3                                    # AM / NBFM share +-6 kHz, USB / LSB share, CW
     first_mode = [params[r[0, 0]].mode for r in qc.reshape(-1, tiles, 4)]
-    cost = [2 if m == MODE_IDS["nbfm"] else 1 if m == MODE_IDS["am"] else 0 for m in first_mode]
+    cost = [2 if m == MODE_IDS["am"] else 0 if m == MODE_IDS["nbfm"] else 1 for m in first_mode]      # measured per-mode cost, round 2
     full = [c for c, r in zip(cost, qc.reshape(-1, tiles, 4)) if (r[:, 0] >= 0).all()]
     assert full == sorted(full, reverse=True)                            # dearest detectors first
     assert 0.5 < fill <= 1.0
@@ -65,3 +65,15 @@ def test_plan_distinct_filters_degenerate_to_single_channel_quads():
     qc, qf, tiles, fill = _check_plan(params, 148)
     assert fill == pytest.approx(0.25)                                   # AUTO falls back to the FFMA engine below 0.5
     assert int((qc >= 0).sum()) == 9 and len(set(qf[qc[:, 0] >= 0].tolist())) == 9
+
+
+def test_plan_many_filters_never_adds_a_wave():
+    """A round cannot mix filters: with 64 filters x 64 channels the narrow tail rounds (3 quads each) would outnumber the
+    SMs (162 on 148) and add a mostly idle wave; the planner then keeps the full rounds (scripts/demod_hetero.py)."""
+    B, n_sm = 4096, 148
+    uniq = [demod_params("usb", 300, 2700 + g) for g in range(64)]
+    qc, qf, tiles, fill = _check_plan([uniq[c % 64] for c in range(B)], n_sm)
+    per_round = (qc.reshape(-1, tiles, 4)[:, :, 0] >= 0).sum(1)
+    full = int((per_round == tiles).sum())
+    assert len(per_round) - (full // n_sm) * n_sm <= n_sm                # whatever follows the whole waves fits one wave
+    assert len(per_round) == 256 and full == 256
