@@ -10,7 +10,7 @@ for v in "$@"; do
   n=${v%%:*}; f=${v#*:}
   ( nvcc $FLAGS $f -c demod_tc_kernels.cu -o ../../build/exp/tc_$n.o &&
     nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build/exp/libssdr_exp$n.so ../../build/csrc/capi.o ../../build/csrc/wf_kernels.o \
-         ../../build/csrc/demod_kernels.o ../../build/exp/tc_$n.o ../../build/csrc/misc_kernels.o ) &
+         ../../build/csrc/demod_kernels.o ../../build/exp/tc_$n.o ../../build/csrc/misc_kernels.o ../../build/csrc/nccl_comm.o -ldl ) &
 done
 wait
 ls -la ../../build/exp/*.so

@@ -44,6 +44,9 @@
 #ifndef SSDR_TC_ISSUE_BLOCK
 #define SSDR_TC_ISSUE_BLOCK 1     // 1: the frame's 30 MMAs + commit as one asm block (one elect); 0: one asm statement per MMA
 #endif
+#ifndef SSDR_TC_WAIT_NS
+#define SSDR_TC_WAIT_NS 0           // 0: mbarrier.try_wait with a suspend-time hint; > 0: test_wait + __nanosleep(ns) back-off
+#endif
 #ifndef SSDR_TC_TILES
 #define SSDR_TC_TILES 4           // tiles (groups of four warps) per CTA: 16 warps at 128 registers
 #endif
@@ -530,11 +533,23 @@ demod_tc_kernel(const DemodKernelParams kp, const int4* __restrict__ quad_ch, co
 #endif
             // suspend-time hint: the warp sleeps in hardware until the commit arrives (or 2 us pass) instead of spinning
             // through try_wait / yield / branch -- a fifth of the kernel's issued instructions were this loop
+#if SSDR_TC_WAIT_NS == 0
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
                 "WAIT_%=:\n\t"
                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
                 "@!p bra WAIT_%=;\n\t}" ::"r"(barp), "r"(phase), "r"(2000u) : "memory");
+#else
+            // plain poll with a fixed back-off: every mbarrier poll is a shared-memory transaction, and the suspend form above
+            // wakes ~38 times per frame (ncu: 78 SYNCS per warp and frame) on a shared-memory pipe that is 85 % busy
+            for (;;) {
+                unsigned done;
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(barp), "r"(phase) : "memory");
+                if (done) break;
+                __nanosleep(SSDR_TC_WAIT_NS);
+            }
+#endif
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             DTRACE(3);
