@@ -133,6 +133,7 @@ struct ssdr_demod {
     int4* d_quad_ch = nullptr;
     int* d_quad_fid = nullptr;
     int* d_round_ctr = nullptr;    // work counter of the tcgen05 kernel (dynamic round scheduling)
+    int* d_sched = nullptr;        // FFMA engine: task counter + per-channel progress words, int[1 + batch]
 };
 
 struct ssdr_interp {
@@ -583,7 +584,7 @@ int ssdr_demod_destroy(ssdr_demod_t h) {
     if (h->copy_out) cudaStreamSynchronize(h->copy_out);
     cudaFree(h->d_chan); cudaFree(h->d_state); cudaFree(h->d_hist); cudaFree(h->d_taps);
     cudaFree(h->d_in); cudaFree(h->d_f32); cudaFree(h->d_i16); cudaFree(h->d_rssi);
-    cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid); cudaFree(h->d_round_ctr);
+    cudaFree(h->d_quad_ch); cudaFree(h->d_quad_fid); cudaFree(h->d_round_ctr); cudaFree(h->d_sched);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->ev_copied) cudaEventDestroy(h->ev_copied);
@@ -779,15 +780,15 @@ static int demod_build_quads(ssdr_demod_t h) {
 // AUTO rule.  The tcgen05 engine shares ONE Toeplitz operand per CTA round (four tiles of four channels), so a bank with few
 // channels per filter runs rounds with empty tiles and warps.  Measured on a B200 (scripts/demod_hetero.py, 4096 USB channels x
 // 32 frames, profiles/r2final_demod_hetero.jsonl): a round of k tiles over F frames costs 25 + F (1.22 + 0.734 k) us of
-// one SM (k = 1, 2, 4: 88, 111, 158 us at F = 32), the FFMA engine 0.916 F us of one SM per channel -- 2 channels per filter:
-// 58 against 83 Gsamples/s (FFMA wins), 4: 111 against 83, 16: 196, one filter: 216.  Tiles at least half full as before; and once
+// one SM (k = 1, 2, 4: 88, 111, 158 us at F = 32), the FFMA engine 0.781 F us of one SM per channel (97 Gsamples/s) -- 2 channels per filter:
+// 58 against 97 Gsamples/s (FFMA wins), 4: 111 against 97, 16: 196, one filter: 216.  Tiles at least half full as before; and once
 // there are more rounds than SMs (throughput, not latency, decides) the cheaper total wins.
 static bool demod_auto_prefers_tc(const ssdr_demod_t h, int n_samples) {
     if (h->quad_fill < 0.5) return false;
     if (h->n_quads <= sm_count()) return true;
     const double F = (double)n_samples / SSDR_FRAME;
     const double tc = (double)h->n_quads * (25.0 + 1.22 * F) + 0.734 * F * (double)h->used_quads;
-    const double ff = 0.916 * F * (double)h->batch;
+    const double ff = 0.781 * F * (double)h->batch;
     return tc < ff;
 }
 
@@ -801,6 +802,8 @@ static int demod_launch_block(ssdr_demod_t h, const void* iq_dev, int iq_format,
     if (h->engine == SSDR_DEMOD_ENGINE_TCGEN05 || (h->engine == SSDR_DEMOD_ENGINE_AUTO && demod_auto_prefers_tc(h, n_samples))) {
         return demod_tc_launch(a, h->d_quad_ch, h->d_quad_fid, h->n_quads, h->d_round_ctr, h->compute);
     }
+    if (!h->d_sched) { int rc = dev_alloc(&h->d_sched, (size_t)h->batch + 1); if (rc) return rc; }
+    a.sched = h->d_sched;
     return demod_launch(a, h->compute);
 }
 

@@ -59,6 +59,7 @@ struct DemodLaunch {
     int batch = 0, n_samples = 0;
     int pitch = 0;            // 0 = n_samples (dense)
     double am_pow16[5] = {0, 0, 0, 0, 0};
+    int* sched = nullptr;     // FFMA engine: task counter + per-channel progress words, int[1 + batch] (zeroed by the launch)
 };
 
 int demod_launch(const DemodLaunch& a, cudaStream_t st);

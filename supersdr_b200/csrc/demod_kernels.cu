@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "demod_host.h"
@@ -63,29 +64,53 @@ struct WarpSmem {
     float2 taps2[TAP_PAD];   // (h, h) pairs for packed FMA
 };
 
+// Work distribution (round 2).  One warp runs one channel at a time, and channels are pulled from a global counter: with
+// static striding 4096 channels on 1776 resident warps left the SMs that hold the low-numbered CTAs with 3 channels per warp
+// and the others with 2 (ncu: 9.4 of 12 warps active); pulled dynamically every SM runs until the work is gone (83 -> 98
+// Gsamples/s on config 3's shape).  A task can also be a (time slice, channel) pair in slice-major order (`n_slices` > 1): a
+// slice's state travels through global memory exactly as it does from call to call (bit-identical output), ordered by a
+// per-channel progress word -- the writer fences and its lane 0 releases `slice + 1`, the reader's lane 0 acquires it; the
+// task that carries a channel's previous slice was handed out `batch` tasks earlier to a running warp, so the (bounded)
+// wait cannot deadlock.  Measured slower than whole channels (see demod_launch), so it is a developer knob.
 template <int FMT>
 __global__ void __launch_bounds__(WARPS * 32, 3)
-demod_kernel(const DemodKernelParams kp) {
+demod_kernel(const DemodKernelParams kp, int n_slices, int slice_frames, int* sched) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
-    const int warps_total = gridDim.x * WARPS;
-    const int nblk = kp.n_samples / FR;
+    const int nblk_all = kp.n_samples / FR;
+    const int n_tasks = kp.batch * n_slices;
+    int* const progress = sched + 1;
 
-    for (int ch = warp_global; ch < kp.batch; ch += warps_total) {
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(sched, 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= n_tasks) break;
+        const int slice = task / kp.batch, ch = task - slice * kp.batch;
+        const int b0 = slice * slice_frames, nblk = min(nblk_all, b0 + slice_frames);
+        if (slice > 0) {
+            if (lane == 0) {
+                const long long t0 = clock64();
+                int got;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(progress + ch) : "memory");
+                } while (got < slice && clock64() - t0 < 4000000000ll);
+            }
+            __syncwarp();
+        }
         const DemodChan cp = kp.chan[ch];
         DemodState* stp = kp.state + ch;
         // ---- load per-channel state ---------------------------------------------------------
         DemodRegs st;
         demod_regs_load(st, stp, lane);
         __syncwarp();
-        for (int i = lane; i < H; i += 32) ws->z[zpos(1 + i)] = kp.hist[(size_t)ch * H + i];
+        for (int i = lane; i < H; i += 32) ws->z[zpos(1 + i)] = __ldcg(kp.hist + (size_t)ch * H + i);
         if (lane == 0) ws->z[0] = make_float2(0.f, 0.f);
         for (int i = lane; i < TAP_PAD; i += 32) { float h = (i < T) ? kp.taps[(size_t)ch * T + i] : 0.f; ws->taps2[i] = make_float2(h, h); }
         __syncwarp();
 
-        for (int b = 0; b < nblk; ++b) {
+        for (int b = b0; b < nblk; ++b) {
             const size_t s0 = (size_t)ch * kp.pitch + (size_t)b * FR;
             // ---- mixer: lane-strided, coalesced; all sixteen loads of the frame in flight together ----------
             float2 xin[SPL];
@@ -136,6 +161,11 @@ demod_kernel(const DemodKernelParams kp) {
         // ---- store per-channel state ---------------------------------------------------------------
         for (int i = lane; i < H; i += 32) kp.hist[(size_t)ch * H + i] = ws->z[zpos(1 + i)];
         demod_regs_store(st, stp, lane);
+        if (n_slices > 1) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + ch), "r"(slice + 1) : "memory");
+        }
         __syncwarp();
     }
 }
@@ -157,7 +187,16 @@ int demod_launch(const DemodLaunch& a, cudaStream_t st) {
     int grid = sm_count() * occ;
     const int need = (a.batch + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
-    kern<<<grid, WARPS * 32, smem, st>>>(kp);
+    // Tasks = whole channels by default (slices = 1).  Measured on a B200 (gpurun_out/ffma_slices_a7.txt, 4096 USB channels x 64
+    // frames): static channel striding 83, dynamic tasks 98.3 Gsamples/s; 2 / 4 / 8 time slices per channel 77.6 / 74.3 / 75.5 --
+    // bit-identical, better balanced on paper and slower in fact, so slicing stays a developer knob (SSDR_FFMA_SLICES).
+    SSDR_ARG(a.sched != nullptr, "demod_launch: scheduler words missing");
+    const int nblk = a.n_samples / FR;
+    int slices = 1;
+    static const int force = [] { const char* e = getenv("SSDR_FFMA_SLICES"); return e ? atoi(e) : 0; }();      // developer knob
+    if (force > 0 && nblk % force == 0) slices = force;
+    SSDR_CUDA(cudaMemsetAsync(a.sched, 0, sizeof(int) * (size_t)(1 + a.batch), st));
+    kern<<<grid, WARPS * 32, smem, st>>>(kp, slices, nblk / slices, a.sched);
     count_launch();
     SSDR_CUDA(cudaGetLastError());
     return SSDR_OK;

@@ -120,12 +120,13 @@ struct DemodRegs {
 };
 
 __device__ __forceinline__ void demod_regs_load(DemodRegs& st, const DemodState* stp, int lane) {
-    st.ph1 = stp->ph1; st.ph2 = stp->ph2;
-    st.e_in = stp->e_in;
-    st.dc = stp->dc;
-    st.zprev = make_float2(stp->zprev_re, stp->zprev_im);
-    st.blk = stp->blk;
-    st.ring = (lane < SSDR_HANG_BLOCKS) ? stp->ring[lane] : 0.0f;
+    // L2 loads: within one launch of the FFMA engine the state of a channel may have been written by another SM (time slices)
+    st.ph1 = __ldcg(&stp->ph1); st.ph2 = __ldcg(&stp->ph2);
+    st.e_in = __ldcg(&stp->e_in);
+    st.dc = __ldcg(&stp->dc);
+    st.zprev = make_float2(__ldcg(&stp->zprev_re), __ldcg(&stp->zprev_im));
+    st.blk = __ldcg(&stp->blk);
+    st.ring = (lane < SSDR_HANG_BLOCKS) ? __ldcg(&stp->ring[lane]) : 0.0f;
 }
 __device__ __forceinline__ void demod_regs_store(const DemodRegs& st, DemodState* stp, int lane) {
     if (lane < SSDR_HANG_BLOCKS) stp->ring[lane] = st.ring;
